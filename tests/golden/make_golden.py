@@ -1,0 +1,192 @@
+"""Generate the golden fixtures in this directory by running THE REFERENCE ITSELF.
+
+Run in the build container only (needs /root/reference; the GPU box has neither it nor
+this need):   python tests/golden/make_golden.py
+
+It imports the reference's ``step.step_arch.STEP`` unmodified with the shims SURVEY.md
+section 8(c) lists (timm.trunc_normal_, an empty ``easytorch`` module, ``torch.load`` mapped to
+CPU, a synthetic ``datasets/<NAME>/data_in12_out12.pkl`` in a temp CWD), loads the
+deterministic synthetic parameters from ``oracle.step_oracle`` into it, injects the Gumbel
+uniforms, runs forward + ``step_loss`` + backward on CPU in fp32 and stores small slices
+of every result.  It also cross-checks the oracle restatement against the reference on
+the spot and refuses to write fixtures if they disagree.
+"""
+import os
+import pickle
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+from oracle import step_oracle as O  # noqa: E402
+
+GRAD_SAMPLE = 257        # values sampled per large gradient tensor
+
+
+def import_reference():
+    vt = types.ModuleType("timm.models.vision_transformer")
+    vt.trunc_normal_ = torch.nn.init.trunc_normal_
+    sys.modules.setdefault("timm", types.ModuleType("timm"))
+    sys.modules.setdefault("timm.models", types.ModuleType("timm.models"))
+    sys.modules["timm.models.vision_transformer"] = vt
+    sys.modules.setdefault("easytorch", types.ModuleType("easytorch"))
+    # stub the packages that pull the whole BasicTS zoo / easytorch at import time
+    bts = types.ModuleType("basicts"); bts.__path__ = [os.path.join(REF, "basicts")]
+    sys.modules["basicts"] = bts
+    butils = types.ModuleType("basicts.utils")
+
+    def load_pkl(path):
+        with open(path, "rb") as f:
+            return pickle.load(f)
+    butils.load_pkl = load_pkl
+    sys.modules["basicts.utils"] = butils
+    spkg = types.ModuleType("refstep"); spkg.__path__ = [os.path.join(REF, "step")]
+    sys.modules["refstep"] = spkg
+    import importlib
+    arch = importlib.import_module("refstep.step_arch")
+    dgl = importlib.import_module("refstep.step_arch.discrete_graph_learning")
+    # step_loss imports basicts.losses -> basicts.metrics (plain torch); import by path
+    bl = types.ModuleType("basicts.losses")
+    mae = importlib.machinery.SourceFileLoader("ref_mae", os.path.join(REF, "basicts/metrics/mae.py")).load_module()
+    bl.masked_mae = mae.masked_mae
+    sys.modules["basicts.losses"] = bl
+    loss = importlib.machinery.SourceFileLoader("ref_step_loss", os.path.join(REF, "step/step_loss/step_loss.py")).load_module()
+    return arch, dgl, loss.step_loss
+
+
+def sample_idx(numel, n=GRAD_SAMPLE):
+    if numel <= n:
+        return torch.arange(numel)
+    return (torch.arange(n, dtype=torch.int64) * (numel - 1)) // (n - 1)
+
+
+def pack_bits(t):
+    return torch.from_numpy(np.packbits(t.reshape(t.shape[0], -1).numpy().astype(np.uint8), axis=1))
+
+
+def build(dataset, batch, patches, real_ckpt, arch, dglmod, ref_loss, seed=0):
+    N = O.NUM_NODES[dataset]
+    ts_args = dict(patch_size=12, in_channel=1, embed_dim=96, num_heads=4, mlp_ratio=4, dropout=0.1,
+                   num_token=patches, mask_ratio=0.75, encoder_depth=4, decoder_depth=1, mode="forecasting")
+    gw_args = dict(num_nodes=N, support_len=2, dropout=0.3, gcn_bool=True, addaptadj=True, aptinit=None, in_dim=2,
+                   out_dim=12, residual_channels=32, dilation_channels=32, skip_channels=256, end_channels=512,
+                   kernel_size=2, blocks=4, layers=2)
+    dgl_args = dict(dataset_name=dataset, k=10, input_seq_len=12, output_seq_len=12)
+
+    node_feats = O.synthetic_node_feats(dataset, seed)
+    if real_ckpt:
+        ts_sd = torch.load(os.path.join(REF, f"tsformer_ckpt/TSFormer_{dataset}.pt"), map_location="cpu")["model_state_dict"]
+    else:
+        ts_sd = O.synthetic_tsformer_params(seed)
+
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "datasets", dataset))
+        with open(os.path.join(tmp, "datasets", dataset, "data_in12_out12.pkl"), "wb") as f:
+            pickle.dump({"processed_data": node_feats.unsqueeze(-1).numpy()}, f)
+        torch.save({"model_state_dict": ts_sd}, os.path.join(tmp, "ts.pt"))
+        os.chdir(tmp)
+        try:
+            model = arch.STEP(dataset, os.path.join(tmp, "ts.pt"), ts_args, gw_args, dgl_args)
+        finally:
+            os.chdir(cwd)
+
+    params = O.synthetic_trainable_params(dataset, seed)
+    full = dict(params)
+    full.update(O.bn_buffers(dataset))
+    full.update({"tsformer." + k: v for k, v in ts_sd.items()})
+    model.load_state_dict(full, strict=True)
+
+    # train() everywhere (BatchNorm batch statistics) but every dropout switched off (SURVEY Appx D.4 suite B)
+    model.train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+        if hasattr(m, "dropout") and isinstance(getattr(m, "dropout"), float):
+            m.dropout = 0.0
+
+    history, long_history, future, uniform = O.synthetic_batch(dataset, batch, patches, seed)
+
+    def injected_gumbel(shape, eps=1e-20, device=None):
+        assert tuple(shape) == tuple(uniform.shape)
+        return -torch.log(-torch.log(uniform + eps) + eps)
+    dglmod.sample_gumbel = injected_gumbel
+
+    y_hat, theta, adj_knn, coeff = model(history_data=history, long_history_data=long_history, future_data=None,
+                                         batch_seen=0, epoch=1)
+    loss = ref_loss(y_hat[..., [0]], future[..., [0]], theta, adj_knn, coeff, null_val=0.0)
+    loss.backward()
+    with torch.no_grad():
+        bern, hidden, adj_knn2, sampled = model.discrete_graph_learning(long_history, model.tsformer)
+    assert torch.equal(adj_knn, adj_knn2)
+
+    # ---- oracle cross-check (the restatement must agree with the reference) ----
+    sd = {k: v.clone() for k, v in full.items()}
+    for k in params:
+        sd[k].requires_grad_(True)
+    # loss/grad cross-check uses the reference's adj_knn: threshold ties of the global top-k are
+    # implementation-defined (SURVEY Appx D.3) and are counted separately as "knn_mismatch"
+    o_loss, o_y = O.train_step(sd, history, long_history, future, node_feats, uniform, epoch=1, null_val=0.0,
+                               adj_knn_override=adj_knn)
+    o_loss.backward()
+    o_yhat, o_theta, o_knn, _ = O.step_forward(sd, history, long_history, node_feats, uniform, 1)
+    report = {"y_hat_mae": float((o_y - y_hat).abs().mean()), "loss_abs": float((o_loss - loss).abs()),
+              "theta_max": float((o_theta - theta).abs().max()),
+              "knn_mismatch": int((o_knn != adj_knn).sum())}
+    gerr = {}
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            assert sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0, k
+            continue
+        g = sd[k].grad
+        assert g is not None, k
+        gerr[k] = float((g - p.grad).abs().max() / max(float(p.grad.abs().max()), 1e-6))
+    report["grad_rel_max"] = max(gerr.values())
+    print(dataset, report)
+    assert report["y_hat_mae"] < 1e-5 and report["loss_abs"] < 1e-5 and report["theta_max"] < 1e-5, report
+    assert report["knn_mismatch"] <= 4 and report["grad_rel_max"] < 5e-3, report  # fp32 summation-order noise through BN over ~5M elements
+
+    fx = {"dataset": dataset, "batch": batch, "patches": patches, "seed": seed, "real_ckpt": real_ckpt,
+          "y_hat": y_hat.detach().clone(), "theta0": theta[0].detach().clone(), "loss": loss.detach().clone(),
+          "adj_knn_bits": pack_bits(adj_knn), "sampled_adj_bits": pack_bits(sampled),
+          "hidden_last": hidden[:, :, -1, :].clone(),
+          "hidden_slice": hidden[:, ::23, ::17, :].clone(),
+          "hidden_sum": hidden.double().sum().item(), "hidden_abs_sum": hidden.double().abs().sum().item(),
+          "bernoulli_unnorm0": bern[0].detach().clone(),
+          "oracle_vs_reference": report, "grads": {}, "no_grad": []}
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            fx["no_grad"].append(k)
+            continue
+        g = p.grad.reshape(-1)
+        idx = sample_idx(g.numel())
+        fx["grads"][k] = {"norm": float(g.double().norm()), "absmax": float(g.abs().max()),
+                          "idx": idx, "val": g[idx].clone(), "full": g.clone().reshape(p.shape) if g.numel() <= 8192 else None}
+    return fx
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    arch, dglmod, ref_loss = import_reference()
+    os.makedirs(HERE, exist_ok=True)
+    # real METR-LA encoder weights travel with the fixtures (the GPU box has no /root/reference)
+    ck = torch.load(os.path.join(REF, "tsformer_ckpt/TSFormer_METR-LA.pt"), map_location="cpu")["model_state_dict"]
+    torch.save({k: v.clone() for k, v in ck.items()}, os.path.join(HERE, "tsformer_METR-LA_state.pt"))
+    for dataset, batch, patches, real in (("METR-LA", 2, 168, True), ("PEMS08", 1, 336, False)):
+        fx = build(dataset, batch, patches, real, arch, dglmod, ref_loss)
+        torch.save(fx, os.path.join(HERE, f"step_{dataset}_b{batch}.pt"))
+        print("wrote", dataset)
+
+
+if __name__ == "__main__":
+    main()
