@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""STEP fwd+bwd throughput benchmark (BASELINE.json metric) - see the contract in DESIGN.md section 6.
+
+  python bench.py --gpus 1 --steps 10 --warmup 3            # our B200-native path
+  python bench.py --impl reference --steps 2 --warmup 1     # the reference algorithm on the host CPU cores
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W               # one rank per GPU, batch-parallel
+
+A "step" = one training step of STEP_METR-LA (N=207 nodes, per-GPU batch 32, 168 patches of 12 = 2016-step
+long history): forward (frozen TSFormer in train() exactly as the reference runs it, discrete graph
+learning, Graph WaveNet), step_loss, backward to every trainable parameter (+ NCCL gradient all-reduce
+when N > 1).  Synthetic N(0,1) inputs, real pre-trained TSFormer weights (tests/golden fixture), seeded
+random GWNet/DGL weights.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import pickle
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DATASET = "METR-LA"
+NODES, BATCH, PATCHES = 207, 32, 168
+METRIC = "STEP fwd+bwd samples/sec (STEP_METR-LA, N=207, per-GPU batch 32, 12->12)"
+TS_ARGS = dict(patch_size=12, in_channel=1, embed_dim=96, num_heads=4, mlp_ratio=4, dropout=0.1, num_token=168.0,
+               mask_ratio=0.75, encoder_depth=4, decoder_depth=1, mode="forecasting")
+GW_ARGS = dict(num_nodes=NODES, support_len=2, dropout=0.3, gcn_bool=True, addaptadj=True, aptinit=None, in_dim=2,
+               out_dim=12, residual_channels=32, dilation_channels=32, skip_channels=256, end_channels=512,
+               kernel_size=2, blocks=4, layers=2)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="per-GPU batch (default: the config's 32)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropout", action="store_true", help="parity-style run (all dropout off); not the headline")
+    ap.add_argument("--chunk-seqs", type=int, default=int(os.environ.get("STEP_B200_TS_CHUNK", "0")))
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 8 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def write_dataset(tmp, node_feats):
+    d = os.path.join(tmp, "datasets", DATASET)
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "data_in12_out12.pkl"), "wb") as f:
+        pickle.dump({"processed_data": node_feats.unsqueeze(-1).numpy()}, f)
+
+
+def ts_state():
+    return torch.load(os.path.join(ROOT, "tests", "golden", "tsformer_METR-LA_state.pt"))
+
+
+# --------------------------------------------------------------------------------------------- CPU comparator
+def cpu_reference_run(steps, warmup, batch, dropout=True):
+    """The reference algorithm (oracle/step_oracle.py restatement of the reference's torch modules) on the
+    host cores, all threads, same config except a bounded per-step batch.  Returns (samples/s, info)."""
+    from oracle import step_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = O.synthetic_trainable_params(DATASET, 0)
+    sd = dict(params)
+    sd.update(O.bn_buffers(DATASET))
+    sd.update({"tsformer." + k: v for k, v in ts_state().items()})
+    for k in params:
+        sd[k] = sd[k].clone().requires_grad_(True)
+    node_feats = O.synthetic_node_feats(DATASET, 0)
+    history, long_history, future, uniform = O.synthetic_batch(DATASET, batch, PATCHES, 0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss, _ = O.train_step(sd, history, long_history, future, node_feats, uniform, epoch=1, null_val=0.0,
+                               gw_drop=0.3 if dropout else 0.0, ts_drop=0.1 if dropout else 0.0)
+        loss.backward()
+        for k in params:
+            sd[k].grad = None
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return batch / dt, {"cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{steps} timed fwd+bwd steps (after {warmup} warm-up) of STEP_METR-LA at batch {batch} "
+                                  f"(CPU samples/s is ~flat in batch), fp32, dropout {'live as in the reference train()' if dropout else 'off'}, "
+                                  f"{dt:.2f} s/step"}
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        b = 2 if (args.steps + args.warmup) <= 12 else 1
+        v, info = cpu_reference_run(args.steps, args.warmup, b)
+        info["value"] = v
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * b / v,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+                          "data": "synthetic", "config": {"workload": "STEP_METR-LA N=207 P=168 12->12, CPU sample batch %d" % b},
+                          "cpu_baseline": info,
+                          "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200-native path has no CPU fallback "
+                         "(use --impl reference for the CPU comparator)")
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from oracle import step_oracle as O          # only for the deterministic synthetic tensors + the CPU leg
+    from step.step_arch import STEP
+    from step.step_loss import step_loss
+    from step_b200 import ops
+
+    B = args.batch
+    node_feats = O.synthetic_node_feats(DATASET, 0)
+    tmp = tempfile.mkdtemp(prefix="step_bench_")
+    write_dataset(tmp, node_feats)
+    torch.save({"model_state_dict": ts_state()}, os.path.join(tmp, "ts.pt"))
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    try:
+        model = STEP(DATASET, os.path.join(tmp, "ts.pt"), dict(TS_ARGS), dict(GW_ARGS),
+                     dict(dataset_name=DATASET, k=10, input_seq_len=12, output_seq_len=12))
+    finally:
+        os.chdir(cwd)
+    full = dict(O.synthetic_trainable_params(DATASET, 0))
+    model.load_state_dict(full, strict=False)
+    model = model.to(dev).train()                 # the reference trains with the frozen TSFormer left in train()
+    model.tsformer.chunk_seqs = args.chunk_seqs
+    if args.no_dropout:
+        model.tsformer.dropout_p = 0.0
+        model.backend.dropout = 0.0
+    trainable = [p for p in model.parameters() if p.requires_grad]
+
+    torch.manual_seed(1234 + rank)
+    n_host = 4                                    # rotate a few distinct host batches (inputs differ step to step)
+    host = []
+    for i in range(n_host):
+        h, lh, f, _ = O.synthetic_batch(DATASET, B, PATCHES, 100 + 17 * rank + i)
+        host.append((h.pin_memory(), lh.pin_memory(), f.pin_memory()))
+    resident = [(h.to(dev), lh.to(dev), f.to(dev)) for (h, lh, f) in host[:2]]
+    h2d_bytes = sum(t.numel() * 4 for t in host[0])
+
+    def train_step(history, long_history, future):
+        y_hat, theta, adj_knn, coeff = model(history_data=history, long_history_data=long_history, future_data=None,
+                                             batch_seen=0, epoch=1)
+        loss = step_loss(y_hat[..., [0]], future[..., [0]], theta, adj_knn, coeff, null_val=0.0)
+        for p in trainable:
+            p.grad = None
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in trainable if p.grad is not None])
+            dist.all_reduce(flat)
+            flat.div_(world)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    # ---- warm-up, then the device-resident measurement ----
+    for i in range(max(args.warmup, 3)):
+        train_step(*resident[i % 2])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    k0 = ops.launch_counter["kernels"]
+    ms_res = timed(lambda i: train_step(*resident[i % 2]), args.steps)
+    launches = ops.launch_counter["kernels"] - k0
+
+    # ---- end-to-end: pinned host batch -> H2D copies -> step -> loss read back, all inside the timed region ----
+    losses = []
+
+    def e2e_step(i):
+        h, lh, f = host[i % n_host]
+        loss = train_step(h.to(dev, non_blocking=True), lh.to(dev, non_blocking=True), f.to(dev, non_blocking=True))
+        losses.append(loss.item())                # D2H read of the step's result
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel: the encoder's token GEMMs (hand-written gemm_tn_kernel) ----
+    pk = peaks()
+    tokens = B * NODES * PATCHES
+    a = torch.randn(tokens, 96, device=dev)
+    w = torch.randn(288, 96, device=dev) * 0.1
+    bias = torch.zeros(288, device=dev)
+    for _ in range(3):
+        ops.linear(a, w, bias)
+    reps = 10
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ops.linear(a, w, bias)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    gemm_ms = e0.elapsed_time(e1) / reps
+    gemm_tflops = 2.0 * tokens * 96 * 288 / (gemm_ms * 1e-3) / 1e12
+    del a, w, bias
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_samples = B * world * args.steps
+    value = total_samples / (ms_res * 1e-3)
+    e2e = total_samples / (ms_e2e * 1e-3)
+    out = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "STEP_METR-LA fwd+loss+bwd, N=207, per-GPU batch %d, P=168 (2016-step history), 12->12" % B,
+                   "parallelism": "dp%d (batch-parallel, NCCL grad all-reduce)" % world if world > 1 else "single GPU",
+                   "dropout": "off" if args.no_dropout else "live (TSFormer 0.1 in train(), gcn 0.3) as the reference trains",
+                   "l2": "inputs > L2: each step streams a fresh 160 MB long-history batch and ~1 GB of activations",
+                   "ts_chunk_seqs": args.chunk_seqs, "weights": "real TSFormer_METR-LA encoder, seeded random GWNet/DGL"},
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "gemm_tn_kernel (TSFormer QKV projection, [%d,96]x[96,288], fp32 CUDA-core path)" % tokens,
+                     "bound": "tensor", "achieved": gemm_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": gemm_tflops / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " (burst, kernel timed alone)",
+                     "ms": gemm_ms},
+        "loss": losses[-1] if losses else None,
+    }
+    if not args.no_cpu_baseline:
+        v, info = cpu_reference_run(2, 1, 2)
+        info["value"] = v
+        info["unit"] = "samples/s"
+        out["cpu_baseline"] = info
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,213 @@
+/*
+ * step_b200.h - C ABI of the B200-native STEP hot path (libstep_b200.so).
+ *
+ * The reference (GestaltCogTeam/STEP) is pure Python/PyTorch and has no native
+ * interface; every entry point below replaces a span of reference Python that
+ * PyTorch-eager executes as a chain of library kernels.  The span is cited as
+ * file:line relative to the reference repository root.
+ *
+ * Conventions:
+ *   - plain `extern "C"`, pointers + sizes only, no torch / C++ types;
+ *   - every pointer is a DEVICE pointer unless its name starts with `h_`;
+ *   - the caller allocates every input, output and workspace buffer; the
+ *     callee never allocates, frees or retains a pointer past return;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), the call
+ *     returns without synchronising;
+ *   - return value: 0 ok, <0 bad argument / unsupported shape (see
+ *     step_last_error_string), >0 a cudaError_t from the launch;
+ *   - all floating point buffers are fp32, row-major, densely packed unless a
+ *     stride argument says otherwise.
+ */
+#ifndef STEP_B200_H_
+#define STEP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STEP_B200_ABI_VERSION 1
+
+#define STEP_OK 0
+#define STEP_EINVAL (-1)
+#define STEP_EUNSUPPORTED (-2)
+#define STEP_EWORKSPACE (-3)
+
+int step_abi_version(void);
+/* The library carries its own (statically linked) CUDA runtime; select the device the following
+ * calls of this host thread launch on (the caller's framework keeps a separate "current device"). */
+int step_set_device(int device);
+/* Text of the last error raised on the calling thread ("" if none). */
+const char *step_last_error_string(void);
+
+/* ------------------------------------------------------------------------ *
+ * TSFormer encoder, forecasting mode (frozen, forward only)
+ *   step/step_arch/tsformer/tsformer.py:86-105,189-191
+ * ------------------------------------------------------------------------ */
+
+/* One nn.TransformerEncoderLayer(96, 4, 384) worth of weights
+ * (step/step_arch/tsformer/transformer_layers.py:10-11; state-dict names in
+ * SURVEY.md Appx C). */
+typedef struct step_ts_layer_weights {
+  const float *in_proj_w;  /* [288, 96] */
+  const float *in_proj_b;  /* [288]     */
+  const float *out_proj_w; /* [96, 96]  */
+  const float *out_proj_b; /* [96]      */
+  const float *lin1_w;     /* [384, 96] */
+  const float *lin1_b;     /* [384]     */
+  const float *lin2_w;     /* [96, 384] */
+  const float *lin2_b;     /* [96]      */
+  const float *norm1_w, *norm1_b, *norm2_w, *norm2_b; /* [96] each */
+} step_ts_layer_weights;
+
+/* Patch embedding + positional embedding + sqrt(d) scaling:
+ *   patch.py:31-42 (Conv2d(1,96,(12,1),stride 12) == [12]->[96] map per patch),
+ *   positional_encoding.py:24-35, transformer_layers.py:15.
+ * series element (b, t, n) is read at series[b*sB + t*sT + n*sN] (element
+ * strides, so a channel-0 view of long_history [B, P*12, N, C] needs no copy).
+ * x: [B*N*P, 96], token order (b, n, p).
+ * drop_p > 0 applies inverted dropout with the counter-based generator keyed
+ * by `seed` (reference: positional_encoding.py:32 while the module is in
+ * train()); drop_p == 0 is the deterministic parity path. */
+int step_ts_embed_fwd(const float *series, long long sB, long long sT, long long sN, int B, int N, int P,
+                      const float *patch_w /*[96,12]*/, const float *patch_b /*[96]*/,
+                      const float *pos /*[>=P,96]*/, float *x, float drop_p, unsigned long long seed,
+                      void *stream);
+
+/* C[M,Nout] = A[M,K] * W[Nout,K]^T + bias, then
+ *   epilogue 0: nothing, 1: ReLU,
+ *   epilogue 2 (Nout == 96 only): C = LayerNorm(residual + drop(C)) * ln_w + ln_b, eps 1e-5
+ *     (the post-norm residual blocks of nn.TransformerEncoderLayer).
+ * drop_p / seed / drop_site: inverted dropout on the GEMM result (before the residual add /
+ * after the ReLU), 0 disables. */
+int step_linear_f32(const float *A, const float *W, const float *bias, float *C, long long M, int K, int Nout,
+                    int epilogue, const float *residual, const float *ln_w, const float *ln_b,
+                    float drop_p, unsigned long long seed, unsigned drop_site, void *stream);
+
+/* Multi-head self attention over S independent sequences of P tokens, 4 heads x 24:
+ *   softmax(q k^T / sqrt(24)) v   (torch MultiheadAttention as used at
+ *   transformer_layers.py:10-18, no mask).  qkv: [S*P, 288] = (q | k | v),
+ * heads are contiguous 24-wide slices; out: [S*P, 96].  drop_p: dropout on the
+ * attention probabilities. */
+int step_attn_fwd_f32(const float *qkv, float *out, int S, int P, float drop_p, unsigned long long seed,
+                      unsigned drop_site, void *stream);
+
+/* Row LayerNorm over 96 features (encoder_norm, tsformer.py:103). */
+int step_layernorm96_f32(const float *x, const float *w, const float *b, float *y, long long M, void *stream);
+
+/* Bytes of workspace step_ts_encoder_fwd needs for `chunk_seqs` sequences of P tokens in flight. */
+size_t step_ts_encoder_workspace_bytes(int chunk_seqs, int P);
+
+/* Whole frozen encoder: series -> hidden [B, N, P, 96] (tsformer.py:189-191).
+ * Sequences are processed `chunk_seqs` at a time so that the per-layer
+ * intermediates of a chunk stay L2-resident (chunk_seqs <= 0: all at once).
+ * drop_p: dropout probability of every dropout site inside TSFormer (the
+ * reference leaves the frozen TSFormer in train() during STEP training). */
+int step_ts_encoder_fwd(const float *series, long long sB, long long sT, long long sN, int B, int N, int P,
+                        const float *patch_w, const float *patch_b, const float *pos,
+                        const step_ts_layer_weights *h_layers, int n_layers,
+                        const float *final_norm_w, const float *final_norm_b, float *hidden,
+                        void *workspace, size_t workspace_bytes, int chunk_seqs,
+                        float drop_p, unsigned long long seed, void *stream);
+
+/* ------------------------------------------------------------------------ *
+ * kNN prior graph: cosine-similarity Gram matrix + global top-k select
+ *   step/step_arch/similarity.py:6-16,
+ *   step/step_arch/discrete_graph_learning.py:91-111,164-166
+ * ------------------------------------------------------------------------ */
+
+/* x: [B, N, D] -> sim [B, N, N] = (x x^T) / ((|x_i|+1e-7)(|x_j|+1e-7)); norms: [B, N] scratch. */
+int step_cosine_gram_f32(const float *x, int B, int N, long long D, float *norms, float *sim, void *stream);
+
+/* adj[b,i,j] = 1 if sim[b,i,j] is among the k largest of the N*N entries of
+ * sample b (ties at the threshold: lowest flat index first), is non-zero, and
+ * i != j; else 0. */
+int step_topk_mask_f32(const float *sim, int B, int N, int k, float *adj, void *stream);
+
+/* ------------------------------------------------------------------------ *
+ * Edge logits + hard Gumbel-softmax sample
+ *   step/step_arch/discrete_graph_learning.py:11-45,148-161
+ * ------------------------------------------------------------------------ */
+
+/* logits[i,j,c] = fc_cat(relu(ut[:,j] + v[i,:]))[c] for the batch-invariant edge MLP.
+ *   ut = (feat @ W_out[:, :100]^T)^T  [100, N]  (sender half, transposed),
+ *   v  =  feat @ W_out[:, 100:]^T + b_out  [N, 100]  (receiver half + bias).
+ * theta[i,j] = softmax(logits[i,j,:])[0]  (step/step_arch/step.py:72). */
+int step_edge_logits_fwd(const float *ut, const float *v, const float *cat_w /*[2,100]*/, const float *cat_b /*[2]*/,
+                         int N, int F, float *logits /*[N,N,2]*/, float *theta /*[N,N]*/, void *stream);
+
+/* Backward of step_edge_logits_fwd.  dlogits: [N,N,2].  Outputs (overwritten):
+ * dut [F,N], dv [N,F], dcat_w [2,F], dcat_b [2]. */
+int step_edge_logits_bwd(const float *dlogits, const float *ut, const float *v, const float *cat_w,
+                         int N, int F, float *dut, float *dv, float *dcat_w, float *dcat_b, void *stream);
+
+/* sampled[b,i,j] in {0,1}: class-0 indicator of the hard Gumbel-softmax sample at
+ * temperature tau with Gumbel noise g = -log(-log(U+1e-10)+1e-10), diagonal forced to 0.
+ * y0[b,i,j]: the soft class-0 probability (saved for the straight-through backward).
+ * uniform: [B, N*N, 2] externally supplied U(0,1) draws (parity / injection), or NULL to
+ * draw them in-kernel from the counter-based generator keyed by `seed`. */
+int step_gumbel_sample_fwd(const float *logits /*[N,N,2]*/, const float *uniform, int B, int N, float tau,
+                           unsigned long long seed, float *sampled, float *y0, void *stream);
+
+/* dlogits[i,j,0] = sum_b dsampled[b,i,j] * y0 (1 - y0) / tau (0 on the diagonal), dlogits[i,j,1] = -dlogits[i,j,0];
+ * if accumulate != 0 the result is added to dlogits. */
+int step_gumbel_sample_bwd(const float *dsampled, const float *y0, int B, int N, float tau, int accumulate,
+                           float *dlogits, void *stream);
+
+/* ------------------------------------------------------------------------ *
+ * Graph WaveNet layer stack (8 x gated dilated conv + skip + diffusion GCN + BN)
+ *   step/step_arch/graphwavenet/model.py:169-213 (+ gcn :35-48, nconv :10-16)
+ * Activation layout is [B, T, N, 32] (channels innermost).
+ * ------------------------------------------------------------------------ */
+typedef struct step_gw_layer_params {
+  const float *filter_w; /* [32,32,1,2] */
+  const float *filter_b; /* [32] */
+  const float *gate_w;   /* [32,32,1,2] */
+  const float *gate_b;   /* [32] */
+  const float *skip_w;   /* [256,32] */
+  const float *skip_b;   /* [256] */
+  const float *mlp_w;    /* [32,224]  (NULL for the last layer: its gcn output is dead, model.py:217-218) */
+  const float *mlp_b;    /* [32] */
+  const float *bn_w;     /* [32] */
+  const float *bn_b;     /* [32] */
+} step_gw_layer_params;
+
+typedef struct step_gw_layer_grads {
+  float *filter_w, *filter_b, *gate_w, *gate_b, *skip_w, *skip_b, *mlp_w, *mlp_b, *bn_w, *bn_b;
+} step_gw_layer_grads;
+
+/* Size in floats of the activation stash / scratch the stack needs. */
+size_t step_gwnet_stash_floats(int B, int N, int n_layers);
+
+/* Forward of the layer stack.
+ *   x0:       [B, 13, N, 32]   start_conv output (model.py:155)
+ *   supports: P1,P2 [B,N,N] (random-walk normalised sampled graph and its transpose-graph,
+ *             model.py:160), P3 [N,N] (adaptive adjacency, model.py:165)
+ *   skip_out: [B, N, 256]  sum over layers of the skip conv at the last time step (the only
+ *             column that survives the reference's truncation `skip[..., -T:]`, model.py:188-192)
+ *   bn_stats: [n_layers, 4, 32] per layer (mean, biased var, scale, shift) of the batch statistics
+ *             when training != 0; when training == 0 the caller pre-fills scale/shift from the running
+ *             statistics and they are used as is.
+ *   stash:    activations kept for the backward pass (step_gwnet_stash_floats).
+ *   drop_p/seed: dropout on the gcn output (model.py:47) when training != 0. */
+int step_gwnet_stack_fwd(const float *x0, const float *P1, const float *P2, const float *P3,
+                         const step_gw_layer_params *h_layers, int n_layers, int B, int N,
+                         int training, float drop_p, unsigned long long seed,
+                         float *skip_out, float *bn_stats, float *stash, void *stream);
+
+/* Backward of the layer stack (training mode).  dskip: [B,N,256].  P1t/P2t/P3t are the
+ * transposed supports.  Outputs: dx0 [B,13,N,32], dP1,dP2 [B,N,N], dP3 [N,N], per-layer
+ * parameter gradients (all overwritten). */
+int step_gwnet_stack_bwd(const float *dskip, const float *x0, const float *P1, const float *P2, const float *P3,
+                         const float *P1t, const float *P2t, const float *P3t,
+                         const step_gw_layer_params *h_layers, const step_gw_layer_grads *h_grads, int n_layers,
+                         int B, int N, float drop_p, unsigned long long seed,
+                         const float *bn_stats, float *stash, float *dx0, float *dP1, float *dP2, float *dP3,
+                         void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEP_B200_H_ */

@@ -1,0 +1,93 @@
+"""Discrete graph learning on the B200-native kernels (drop-in for the reference module).
+
+Reference: ``step/step_arch/discrete_graph_learning.py:48-168``.  Same constructor, ``forward``
+signature/returns and state-dict keys.  Differences in *how* (not what):
+  * the N^2 x N one-hot matmuls (rel_rec / rel_send, :88-89,148-149) are an index gather folded into
+    the edge-logit kernel, evaluated once per step because the result is identical for every sample;
+  * Gumbel uniforms come from the in-kernel counter-based generator (inject ``gumbel_uniform`` to
+    reproduce a given draw); ``node_feats`` stays resident on the device instead of being re-uploaded.
+"""
+import pickle
+
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from step_b200 import ops
+
+_NUM_NODES = {"METR-LA": 207, "PEMS04": 307, "PEMS03": 358, "PEMS-BAY": 325, "PEMS07": 883, "PEMS08": 170}
+_TRAIN_LENGTH = {"METR-LA": 23990, "PEMS04": 13599, "PEMS03": 15303, "PEMS07": 16513, "PEMS-BAY": 36482, "PEMS08": 14284}
+_DIM_FC = {"METR-LA": 383552, "PEMS04": 217296, "PEMS03": 244560, "PEMS07": 263920, "PEMS-BAY": 583424, "PEMS08": 228256}
+_DIM_FC_MEAN = {"METR-LA": 16128, "PEMS-BAY": 16128, "PEMS03": 16128 * 2, "PEMS04": 16128 * 2, "PEMS07": 16128,
+                "PEMS08": 16128 * 2}
+
+
+def _load_pkl(path):
+    with open(path, "rb") as f:
+        try:
+            return pickle.load(f)
+        except UnicodeDecodeError:
+            f.seek(0)
+            return pickle.load(f, encoding="latin1")
+
+
+class DiscreteGraphLearning(nn.Module):
+    """Dynamic graph learning module."""
+
+    def __init__(self, dataset_name, k, input_seq_len, output_seq_len):
+        super().__init__()
+        self.k = k
+        self.num_nodes = _NUM_NODES[dataset_name]
+        self.train_length = _TRAIN_LENGTH[dataset_name]
+        data = _load_pkl("datasets/" + dataset_name + "/data_in{0}_out{1}.pkl".format(input_seq_len, output_seq_len))
+        # plain attribute (not a buffer) so that the state dict matches the reference's
+        self.node_feats = torch.from_numpy(data["processed_data"]).float()[:self.train_length, :, 0]
+        self.dim_fc = _DIM_FC[dataset_name]
+        self.embedding_dim = 100
+        self.conv1 = nn.Conv1d(1, 8, 10, stride=1)
+        self.conv2 = nn.Conv1d(8, 16, 10, stride=1)
+        self.fc = nn.Linear(self.dim_fc, self.embedding_dim)
+        self.bn1 = nn.BatchNorm1d(8)
+        self.bn2 = nn.BatchNorm1d(16)
+        self.bn3 = nn.BatchNorm1d(self.embedding_dim)
+        self.dim_fc_mean = _DIM_FC_MEAN[dataset_name]
+        self.fc_mean = nn.Linear(self.dim_fc_mean, 100)          # unused (as in the reference, :74,142)
+        self.fc_cat = nn.Linear(self.embedding_dim, 2)
+        self.fc_out = nn.Linear(self.embedding_dim * 2, self.embedding_dim)
+        self.dropout = nn.Dropout(0.5)                            # unused (as in the reference)
+        self.gumbel_uniform = None     # optional [B, N*N, 2] U(0,1) draws to inject (tests / reproduction)
+        self.theta = None              # softmax(bernoulli_unnorm)[..., 0] of the last forward, [N, N]
+        self._calls = 0
+        self._feats_dev = None
+
+    def _global_feature(self, device):
+        """Batch-invariant node embedding, reference :131-135.  [N, 100]."""
+        if self._feats_dev is None or self._feats_dev.device != device:
+            self._feats_dev = self.node_feats.to(device).t().contiguous().unsqueeze(1)     # [N,1,L], uploaded once
+        x = self.bn1(F.relu(self.conv1(self._feats_dev)))
+        x = self.bn2(F.relu(self.conv2(x)))
+        x = F.relu(self.fc(x.view(self.num_nodes, -1)))
+        return self.bn3(x)
+
+    def get_k_nn_neighbor(self, data, k=11 * 207, metric="cosine"):
+        if metric != "cosine":
+            raise NotImplementedError("only the cosine metric is used by STEP")
+        with torch.no_grad():
+            return ops.topk_mask(ops.cosine_gram(data), k)
+
+    def forward(self, long_term_history, tsformer):
+        """long_term_history [B, P*L, N, C] -> (bernoulli_unnorm [B,N*N,2], hidden [B,N,P,d], adj_knn, sampled_adj)."""
+        batch_size, _, num_nodes, _ = long_term_history.shape
+        feat = self._global_feature(long_term_history.device)
+        hidden_states = tsformer(long_term_history[..., [0]])
+        half = self.embedding_dim
+        ut = self.fc_out.weight[:, :half] @ feat.t()                          # [100, N]  sender half (index j)
+        v = feat @ self.fc_out.weight[:, half:].t() + self.fc_out.bias        # [N, 100]  receiver half (index i)
+        logits, theta = ops.EdgeLogits.apply(ut, v, self.fc_cat.weight, self.fc_cat.bias)
+        self.theta = theta
+        bernoulli_unnorm = logits.view(1, num_nodes * num_nodes, 2).expand(batch_size, -1, -1)
+        self._calls += 1
+        seed = (torch.initial_seed() + 0xC2B2AE35 * self._calls) & (2 ** 63 - 1)
+        sampled_adj = ops.GumbelSample.apply(logits, self.gumbel_uniform, batch_size, 0.5, seed)
+        adj_knn = ops.knn_prior(hidden_states, self.k * self.num_nodes)
+        return bernoulli_unnorm, hidden_states, adj_knn, sampled_adj

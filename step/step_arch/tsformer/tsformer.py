@@ -1,0 +1,149 @@
+"""TSFormer on the B200-native kernels (drop-in for the reference module of the same name).
+
+Same constructor / ``forward`` signature and the same 72 state-dict keys as the reference
+(``step/step_arch/tsformer/tsformer.py:21-191``, checkpoint contract in SURVEY.md Appx C), so
+``tsformer_ckpt/*.pt`` load with ``strict=True``.  The sub-modules below only *hold parameters*
+under the reference's names; the arithmetic is ``step_b200.ops.ts_encoder_forward`` (hand-written
+sm_100a kernels).  There is no PyTorch fallback.
+"""
+import math
+
+import torch
+from torch import nn
+
+from step_b200 import ops
+
+
+class _AttnParams(nn.Module):
+    """Parameter holder with nn.MultiheadAttention's names (in_proj_weight/in_proj_bias/out_proj)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * dim, dim))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * dim))
+        self.out_proj = nn.Linear(dim, dim)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.zeros_(self.out_proj.bias)
+
+
+class _EncoderLayerParams(nn.Module):
+    """Parameter holder with nn.TransformerEncoderLayer's names."""
+
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.self_attn = _AttnParams(dim)
+        self.linear1 = nn.Linear(dim, hidden)
+        self.linear2 = nn.Linear(hidden, dim)
+        self.norm1 = nn.LayerNorm(dim)
+        self.norm2 = nn.LayerNorm(dim)
+
+    def kernel_weights(self):
+        return {"in_proj_w": self.self_attn.in_proj_weight, "in_proj_b": self.self_attn.in_proj_bias,
+                "out_proj_w": self.self_attn.out_proj.weight, "out_proj_b": self.self_attn.out_proj.bias,
+                "lin1_w": self.linear1.weight, "lin1_b": self.linear1.bias,
+                "lin2_w": self.linear2.weight, "lin2_b": self.linear2.bias,
+                "norm1_w": self.norm1.weight, "norm1_b": self.norm1.bias,
+                "norm2_w": self.norm2.weight, "norm2_b": self.norm2.bias}
+
+
+class _LayerList(nn.Module):
+    def __init__(self, dim, hidden, depth):
+        super().__init__()
+        self.layers = nn.ModuleList([_EncoderLayerParams(dim, hidden) for _ in range(depth)])
+
+
+class TransformerLayers(nn.Module):
+    """Holds ``transformer_encoder.layers.{i}.*`` (reference: tsformer/transformer_layers.py:6-20)."""
+
+    def __init__(self, hidden_dim, nlayers, mlp_ratio, num_heads=4, dropout=0.1):
+        super().__init__()
+        self.d_model = hidden_dim
+        self.num_heads = num_heads
+        self.dropout = dropout
+        self.transformer_encoder = _LayerList(hidden_dim, hidden_dim * mlp_ratio, nlayers)
+
+    def kernel_weights(self):
+        return [layer.kernel_weights() for layer in self.transformer_encoder.layers]
+
+
+class PatchEmbedding(nn.Module):
+    """Holds ``input_embedding.{weight,bias}`` (reference: tsformer/patch.py:4-42)."""
+
+    def __init__(self, patch_size, in_channel, embed_dim, norm_layer=None):
+        super().__init__()
+        self.len_patch = patch_size
+        self.input_channel = in_channel
+        self.output_channel = embed_dim
+        self.input_embedding = nn.Conv2d(in_channel, embed_dim, kernel_size=(patch_size, 1), stride=(patch_size, 1))
+
+
+class PositionalEncoding(nn.Module):
+    """Holds ``position_embedding`` (reference: tsformer/positional_encoding.py:5-35)."""
+
+    def __init__(self, hidden_dim, dropout=0.1, max_len: int = 1000):
+        super().__init__()
+        self.p = dropout
+        self.position_embedding = nn.Parameter(torch.empty(max_len, hidden_dim), requires_grad=True)
+
+
+class TSFormer(nn.Module):
+    """Masked-patch transformer for long time series; ``mode="forecasting"`` is the STEP hot path."""
+
+    def __init__(self, patch_size, in_channel, embed_dim, num_heads, mlp_ratio, dropout, num_token, mask_ratio,
+                 encoder_depth, decoder_depth, mode="pre-train"):
+        super().__init__()
+        assert mode in ["pre-train", "forecasting"], "Error mode."
+        if (patch_size, in_channel, embed_dim, num_heads, mlp_ratio) != (12, 1, 96, 4, 4):
+            raise NotImplementedError(
+                "step_b200 kernels are specialised for the STEP configuration patch_size=12, in_channel=1, "
+                "embed_dim=96, num_heads=4, mlp_ratio=4 (every shipped STEP_*.py / TSFormer_*.py config)")
+        self.patch_size, self.in_channel, self.embed_dim, self.num_heads = patch_size, in_channel, embed_dim, num_heads
+        self.num_token, self.mask_ratio, self.encoder_depth, self.mode, self.mlp_ratio = \
+            num_token, mask_ratio, encoder_depth, mode, mlp_ratio
+        self.dropout_p = dropout
+        self.selected_feature = 0
+        self.encoder_norm = nn.LayerNorm(embed_dim)
+        self.decoder_norm = nn.LayerNorm(embed_dim)
+        self.patch_embedding = PatchEmbedding(patch_size, in_channel, embed_dim, norm_layer=None)
+        self.positional_encoding = PositionalEncoding(embed_dim, dropout=dropout)
+        self.encoder = TransformerLayers(embed_dim, encoder_depth, mlp_ratio, num_heads, dropout)
+        self.enc_2_dec_emb = nn.Linear(embed_dim, embed_dim, bias=True)
+        self.mask_token = nn.Parameter(torch.zeros(1, 1, 1, embed_dim))
+        self.decoder = TransformerLayers(embed_dim, decoder_depth, mlp_ratio, num_heads, dropout)
+        self.output_layer = nn.Linear(embed_dim, patch_size)
+        # kernel launch options
+        self.chunk_seqs = 0          # sequences per L2-resident chunk (0 = all at once)
+        self._calls = 0
+        self.initialize_weights()
+
+    def initialize_weights(self):
+        nn.init.uniform_(self.positional_encoding.position_embedding, -.02, .02)
+        nn.init.trunc_normal_(self.mask_token, std=.02)
+
+    def _next_seed(self):
+        self._calls += 1
+        return (torch.initial_seed() + 0x9E3779B1 * self._calls) & (2 ** 63 - 1)
+
+    def encoding(self, long_term_history, mask=False):
+        """long_term_history: [B, N, 1, P*L] view -> hidden states [B, N, P, d] (no masking on this path)."""
+        if mask:
+            raise NotImplementedError("masked pre-training encoder is listed as 'next' in DESIGN.md (SURVEY section 8(f).3)")
+        series = long_term_history[:, :, 0, :].permute(0, 2, 1)      # [B, P*L, N] view, no copy
+        drop = self.dropout_p if self.training else 0.0
+        hidden = ops.ts_encoder_forward(
+            series, self.patch_embedding.input_embedding.weight, self.patch_embedding.input_embedding.bias,
+            self.positional_encoding.position_embedding, self.encoder.kernel_weights(),
+            self.encoder_norm.weight, self.encoder_norm.bias, drop_p=drop, seed=self._next_seed() if drop > 0 else 0,
+            chunk_seqs=self.chunk_seqs)
+        return hidden, None, None
+
+    def forward(self, history_data: torch.Tensor, future_data: torch.Tensor = None, batch_seen: int = None,
+                epoch: int = None, **kwargs) -> torch.Tensor:
+        """history_data: [B, L*P, N, 1].  forecasting mode -> [B, N, P, d]."""
+        history_data = history_data.permute(0, 2, 3, 1)     # B, N, 1, L*P (view)
+        if self.mode == "pre-train":
+            raise NotImplementedError("TSFormer pre-training (mask + decoder + encoder backward) is not part of the "
+                                      "round-1 hot path; see DESIGN.md 'what comes next'")
+        with torch.no_grad():
+            hidden_states_full, _, _ = self.encoding(history_data, mask=False)
+        return hidden_states_full

@@ -1,0 +1,26 @@
+"""STEP loss: masked MAE + graph-structure BCE (reference: step/step_loss/step_loss.py:5-16,
+basicts/metrics/mae.py:5-28)."""
+import numpy as np
+import torch
+
+
+def masked_mae(preds: torch.Tensor, labels: torch.Tensor, null_val: float = np.nan) -> torch.Tensor:
+    if np.isnan(null_val):
+        mask = ~torch.isnan(labels)
+    else:
+        mask = (labels - null_val).abs() > 5e-5
+    mask = mask.float()
+    mask = mask / torch.mean(mask)
+    mask = torch.where(torch.isnan(mask), torch.zeros_like(mask), mask)
+    loss = torch.abs(preds - labels) * mask
+    loss = torch.where(torch.isnan(loss), torch.zeros_like(loss), loss)
+    return torch.mean(loss)
+
+
+def step_loss(prediction, real_value, theta, priori_adj, gsl_coefficient, null_val=np.nan):
+    # theta may be an expanded (stride-0) view of the batch-invariant [N,N] probabilities
+    log_t = torch.log(theta).clamp_min(-100.0)
+    log_1mt = torch.log(1.0 - theta).clamp_min(-100.0)
+    loss_graph = -(priori_adj * log_t + (1.0 - priori_adj) * log_1mt).mean()
+    loss_pred = masked_mae(preds=prediction, labels=real_value, null_val=null_val)
+    return loss_pred + loss_graph * gsl_coefficient

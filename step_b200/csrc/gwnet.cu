@@ -1,0 +1,984 @@
+// Graph WaveNet layer stack: gated dilated temporal conv + skip conv + diffusion graph convolution
+// (3 supports x 2 hops) + residual + BatchNorm, forward and backward, fp32.
+//
+// Reference semantics (file:line relative to the reference repo):
+//   step/step_arch/graphwavenet/model.py:169-213   layer body
+//   step/step_arch/graphwavenet/model.py:35-48     gcn (concat of 7 node-mixed copies -> 1x1 conv -> dropout)
+//   step/step_arch/graphwavenet/model.py:10-16     nconv: out[w] = sum_v A[v,w] x[v]
+//
+// Design: activations are [B, T, N, 32] (channels innermost = one 128 B line per
+// (b,t,n)); one CTA owns one (sample, time-step) column, i.e. all N nodes x 32 channels, so both
+// diffusion hops, the 1x1 mixing, the residual and the BatchNorm partial sums happen in a single
+// launch per layer.  The 224-channel concat of the reference is never formed: because node mixing
+// and channel mixing commute, h = W0 u + sum_s P_s^T ( W_s1 u + P_s^T ( W_s2 u ) )  (Horner form),
+// which needs the same 6 node-mixes per layer but only 32-channel operands.  BatchNorm of layer i is
+// applied on load by layer i+1 (scale/shift from the batch statistics), the 256-channel skip conv is
+// evaluated only at the last time step (the only column that survives `skip[..., -T:]`).
+#include "common.cuh"
+
+namespace stepk {
+
+constexpr int GC = 32;        // residual / dilation channels
+constexpr int GSKIP = 256;    // skip channels
+constexpr int GW_THREADS = 256;
+constexpr int GW_MAX_LAYERS = 8;
+
+struct GwPlan {
+  int B, N, L;
+  int Tin[GW_MAX_LAYERS], Tout[GW_MAX_LAYERS], dil[GW_MAX_LAYERS];
+  size_t col;                       // floats per (b,t) column = N*32
+  size_t off_sums_fwd, off_sums_bwd;  // doubles, [L][2][32] each (offsets in floats)
+  size_t off_coef;                  // [L][4][32] floats: BN-backward coefficients
+  size_t off_z[GW_MAX_LAYERS], off_f[GW_MAX_LAYERS], off_g[GW_MAX_LAYERS], off_q[GW_MAX_LAYERS][3];
+  size_t off_U, off_M, off_H;       // forward scratch, [B,12,N,32]
+  size_t off_DH, off_DZC, off_DQ[3], off_A[3], off_DA, off_DU, off_DPF, off_DPG, off_DR[2];
+  size_t total;
+};
+
+static GwPlan make_plan(int B, int N, int L) {
+  GwPlan p{};
+  p.B = B; p.N = N; p.L = L;
+  p.col = (size_t)N * GC;
+  int T = 13;
+  for (int i = 0; i < L; ++i) {
+    p.dil[i] = (i % 2 == 0) ? 1 : 2;
+    p.Tin[i] = T;
+    T -= p.dil[i];
+    p.Tout[i] = T;
+  }
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += (n + 63) / 64 * 64; return r; };
+  p.off_sums_fwd = take((size_t)L * 2 * 32 * 2);
+  p.off_sums_bwd = take((size_t)L * 2 * 32 * 2);
+  p.off_coef = take((size_t)L * 4 * 32);
+  for (int i = 0; i < L; ++i) {
+    const size_t n = (size_t)B * p.Tout[i] * p.col;
+    p.off_z[i] = take(n); p.off_f[i] = take(n); p.off_g[i] = take(n);
+    for (int s = 0; s < 3; ++s) p.off_q[i][s] = take(n);
+  }
+  const size_t big = (size_t)B * 12 * p.col;
+  p.off_U = take(big); p.off_M = take(big); p.off_H = take(big);
+  p.off_DH = take(big); p.off_DZC = take(big);
+  for (int s = 0; s < 3; ++s) { p.off_DQ[s] = take(big); p.off_A[s] = take(big); }
+  p.off_DA = take(big); p.off_DU = take(big); p.off_DPF = take(big); p.off_DPG = take(big);
+  p.off_DR[0] = take((size_t)B * 13 * p.col);
+  p.off_DR[1] = take((size_t)B * 13 * p.col);
+  p.total = o;
+  return p;
+}
+
+// ---------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void load_row(const float *p, float (&r)[GC]) {
+#pragma unroll
+  for (int c = 0; c < GC; c += 4) {
+    const float4 v = *reinterpret_cast<const float4 *>(p + c);
+    r[c] = v.x; r[c + 1] = v.y; r[c + 2] = v.z; r[c + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void store_row(float *p, const float (&r)[GC]) {
+#pragma unroll
+  for (int c = 0; c < GC; c += 4) *reinterpret_cast<float4 *>(p + c) = make_float4(r[c], r[c + 1], r[c + 2], r[c + 3]);
+}
+// For cg = 0..7: f(cg, float4{ sum_ci W[4cg+j][ci] x[ci] }_j)   (W: smem [32][32] row-major [co][ci]).
+// The output chunk loop is deliberately not unrolled: outputs go straight to memory through `f`, which
+// keeps the code small and every register index static.
+template <typename F>
+__device__ __forceinline__ void matvec_chunks(const float *W, const float (&x)[GC], F f) {
+#pragma unroll 1
+  for (int cg = 0; cg < 8; ++cg) {
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 *w = reinterpret_cast<const float4 *>(W + (4 * cg + j) * GC);
+      float a = 0.f;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 ww = w[c4];
+        a = fmaf(ww.x, x[4 * c4], a); a = fmaf(ww.y, x[4 * c4 + 1], a);
+        a = fmaf(ww.z, x[4 * c4 + 2], a); a = fmaf(ww.w, x[4 * c4 + 3], a);
+      }
+      o[j] = a;
+    }
+    f(cg, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+// out[ci] += sum_co W[co][ci] xp[co]   (xp: a row in shared or global memory)
+__device__ __forceinline__ void matvec_t_acc(const float *W, const float *xp, float (&out)[GC]) {
+#pragma unroll 4
+  for (int co = 0; co < GC; ++co) {
+    const float4 *w = reinterpret_cast<const float4 *>(W + co * GC);
+    const float xv = xp[co];
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 ww = w[c4];
+      out[4 * c4] = fmaf(ww.x, xv, out[4 * c4]); out[4 * c4 + 1] = fmaf(ww.y, xv, out[4 * c4 + 1]);
+      out[4 * c4 + 2] = fmaf(ww.z, xv, out[4 * c4 + 2]); out[4 * c4 + 3] = fmaf(ww.w, xv, out[4 * c4 + 3]);
+    }
+  }
+}
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// out[w][c] = sum_k Pm[k][w] * Y[k][c]; Pm [N][N] in global (reduction index = row), Y [N][32] in smem.
+// Thread <-> output node w (all 32 channels in registers); the Pm reads are coalesced across the warp,
+// the Y reads are warp-wide broadcasts.
+template <typename Sink>
+__device__ __forceinline__ void mix_nodes(const float *__restrict__ Pm, const float *Y, int N, Sink sink) {
+  for (int w0 = 0; w0 < N; w0 += GW_THREADS) {
+    if (w0 + (int)(threadIdx.x & ~31u) >= N) continue;  // whole warp past the end
+    const int w = w0 + threadIdx.x;
+    const bool ok = w < N;
+    const float *pc = Pm + (ok ? w : N - 1);
+    float acc[GC];
+#pragma unroll
+    for (int c = 0; c < GC; ++c) acc[c] = 0.f;
+    int k = 0;
+    for (; k + 8 <= N; k += 8) {
+      float p[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p[j] = pc[(size_t)(k + j) * N];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 *y = reinterpret_cast<const float4 *>(Y + (size_t)(k + j) * GC);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 yy = y[c4];
+          acc[4 * c4] = fmaf(p[j], yy.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(p[j], yy.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(p[j], yy.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(p[j], yy.w, acc[4 * c4 + 3]);
+        }
+      }
+    }
+    for (; k < N; ++k) {
+      const float pv = pc[(size_t)k * N];
+      const float4 *y = reinterpret_cast<const float4 *>(Y + (size_t)k * GC);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 yy = y[c4];
+        acc[4 * c4] = fmaf(pv, yy.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(pv, yy.y, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(pv, yy.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(pv, yy.w, acc[4 * c4 + 3]);
+      }
+    }
+    if (ok) sink(w, acc);
+  }
+}
+
+// global [N][32] -> smem Y (coalesced float4 copy)
+__device__ __forceinline__ void copy_to_smem(float *Y, const float *src, int N) {
+  const float4 *s = reinterpret_cast<const float4 *>(src);
+  float4 *d = reinterpret_cast<float4 *>(Y);
+  for (int i = threadIdx.x; i < N * (GC / 4); i += GW_THREADS) d[i] = s[i];
+}
+
+// per-channel sums over the N rows of the smem tile Y (and of Y*Y), added to two double accumulators.
+// red: smem scratch of >= 512 floats.
+__device__ __forceinline__ void column_sums_to(const float *Y, int N, float *red, double *sum_dst, double *sq_dst) {
+  const int c = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  float s = 0.f, q = 0.f;
+  for (int n = grp; n < N; n += GW_THREADS / 32) {
+    const float v = Y[(size_t)n * GC + c];
+    s += v;
+    q = fmaf(v, v, q);
+  }
+  red[grp * 32 + c] = s;
+  red[256 + grp * 32 + c] = q;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float ts = 0.f, tq = 0.f;
+#pragma unroll
+    for (int g2 = 0; g2 < GW_THREADS / 32; ++g2) { ts += red[g2 * 32 + c]; tq += red[256 + g2 * 32 + c]; }
+    if (sum_dst) atomicAdd(sum_dst + c, (double)ts);
+    if (sq_dst) atomicAdd(sq_dst + c, (double)tq);
+  }
+  __syncthreads();
+}
+
+// dst[co*ldd + ci] += sum_n X[n][co] * U[n][ci]   (X, U: [N][32] in global, CTA-local data)
+// tiles: smem scratch of 2*64*33 floats.
+__device__ __forceinline__ void outer_acc(const float *X, const float *U, int N, float *tiles, float *dst, int ldd) {
+  float *T1 = tiles, *T2 = tiles + 64 * 33;
+  const int co = threadIdx.x >> 3, ci4 = (threadIdx.x & 7) * 4;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int n0 = 0; n0 < N; n0 += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * GC; i += GW_THREADS) {
+      const int n = i >> 5, c = i & 31;
+      const bool ok = (n0 + n) < N;
+      T1[n * 33 + c] = ok ? X[(size_t)(n0 + n) * GC + c] : 0.f;
+      T2[n * 33 + c] = ok ? U[(size_t)(n0 + n) * GC + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int n = 0; n < 64; ++n) {
+      const float x = T1[n * 33 + co];
+      a0 = fmaf(x, T2[n * 33 + ci4], a0); a1 = fmaf(x, T2[n * 33 + ci4 + 1], a1);
+      a2 = fmaf(x, T2[n * 33 + ci4 + 2], a2); a3 = fmaf(x, T2[n * 33 + ci4 + 3], a3);
+    }
+  }
+  float *d = dst + (size_t)co * ldd + ci4;
+  atomicAdd(d, a0); atomicAdd(d + 1, a1); atomicAdd(d + 2, a2); atomicAdd(d + 3, a3);
+  __syncthreads();
+}
+
+__device__ __forceinline__ void dropout_row(float (&h)[GC], uint64_t elem0, uint32_t thr, float scale, uint64_t key) {
+  // elem0: flat index of channel 0 of this row (multiple of 32)
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) {
+    const uint4 r = philox4x32((elem0 >> 2) + c4, key);
+    h[4 * c4] = (r.x >= thr) ? h[4 * c4] * scale : 0.f;
+    h[4 * c4 + 1] = (r.y >= thr) ? h[4 * c4 + 1] * scale : 0.f;
+    h[4 * c4 + 2] = (r.z >= thr) ? h[4 * c4 + 2] * scale : 0.f;
+    h[4 * c4 + 3] = (r.w >= thr) ? h[4 * c4 + 3] * scale : 0.f;
+  }
+}
+
+__device__ __forceinline__ float4 dropout4(float4 h, uint64_t elem0, int c4, uint32_t thr, float scale, uint64_t key) {
+  const uint4 r = philox4x32((elem0 >> 2) + c4, key);
+  return make_float4((r.x >= thr) ? h.x * scale : 0.f, (r.y >= thr) ? h.y * scale : 0.f,
+                     (r.z >= thr) ? h.z * scale : 0.f, (r.w >= thr) ? h.w * scale : 0.f);
+}
+
+// ---------------------------------------------------------------------------
+// forward layer kernel: grid (T_out, B)
+// ---------------------------------------------------------------------------
+struct GwFwdArgs {
+  const float *zin; float *zout;
+  int Tin, Tout, dil, N, has_gcn, has_in_bn, collect_stats;
+  const float *in_scale, *in_shift;      // [32] BN-on-load of the previous layer
+  const float *P[3]; long long pstride[3];  // supports, per-sample stride (0 for the shared adaptive one)
+  step_gw_layer_params w;
+  float *f, *g, *q[3], *U, *M, *H, *skip;
+  double *sums;                           // [2][32]
+  uint32_t drop_thr; float drop_scale; uint64_t key;
+};
+
+__global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int N = a.N, tid = threadIdx.x, t = blockIdx.x, b = blockIdx.y;
+  float *Y = smem;                          // [N][32]
+  float *Wb = smem + (size_t)N * GC;        // 7 * 1024 floats
+  const size_t col = (size_t)N * GC;
+  const float *z0 = a.zin + ((size_t)b * a.Tin + t) * col;
+  const float *z1 = a.zin + ((size_t)b * a.Tin + t + a.dil) * col;
+  const size_t ocol = ((size_t)b * a.Tout + t) * col;
+  float *U = a.U + ocol, *Mb = a.M + ocol, *Hb = a.H + ocol;
+
+  for (int i = tid; i < 1024; i += GW_THREADS) {
+    Wb[i] = a.w.filter_w[2 * i]; Wb[1024 + i] = a.w.filter_w[2 * i + 1];
+    Wb[2048 + i] = a.w.gate_w[2 * i]; Wb[3072 + i] = a.w.gate_w[2 * i + 1];
+  }
+  __syncthreads();
+
+  // ---- phase A: gated dilated conv, u = tanh(.) * sigmoid(.) ----
+  for (int n = tid; n < N; n += GW_THREADS) {
+    float r0[GC], r1[GC];
+    load_row(z0 + (size_t)n * GC, r0);
+    load_row(z1 + (size_t)n * GC, r1);
+    if (a.has_in_bn) {
+#pragma unroll
+      for (int c = 0; c < GC; ++c) {
+        const float sc = a.in_scale[c], sh = a.in_shift[c];
+        r0[c] = fmaf(r0[c], sc, sh);
+        r1[c] = fmaf(r1[c], sc, sh);
+      }
+    }
+    float *fo = a.f + ocol + (size_t)n * GC, *go = a.g + ocol + (size_t)n * GC, *uo = U + (size_t)n * GC;
+#pragma unroll 1
+    for (int cg = 0; cg < GC; cg += 4) {
+      float fv[4], gv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int co = cg + j;
+        const float4 *wf0 = reinterpret_cast<const float4 *>(Wb + co * GC);
+        const float4 *wf1 = reinterpret_cast<const float4 *>(Wb + 1024 + co * GC);
+        const float4 *wg0 = reinterpret_cast<const float4 *>(Wb + 2048 + co * GC);
+        const float4 *wg1 = reinterpret_cast<const float4 *>(Wb + 3072 + co * GC);
+        float af = a.w.filter_b[co], ag = a.w.gate_b[co];
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 A0 = wf0[c4], A1 = wf1[c4], G0 = wg0[c4], G1 = wg1[c4];
+          af = fmaf(A0.x, r0[4 * c4], af); af = fmaf(A0.y, r0[4 * c4 + 1], af);
+          af = fmaf(A0.z, r0[4 * c4 + 2], af); af = fmaf(A0.w, r0[4 * c4 + 3], af);
+          af = fmaf(A1.x, r1[4 * c4], af); af = fmaf(A1.y, r1[4 * c4 + 1], af);
+          af = fmaf(A1.z, r1[4 * c4 + 2], af); af = fmaf(A1.w, r1[4 * c4 + 3], af);
+          ag = fmaf(G0.x, r0[4 * c4], ag); ag = fmaf(G0.y, r0[4 * c4 + 1], ag);
+          ag = fmaf(G0.z, r0[4 * c4 + 2], ag); ag = fmaf(G0.w, r0[4 * c4 + 3], ag);
+          ag = fmaf(G1.x, r1[4 * c4], ag); ag = fmaf(G1.y, r1[4 * c4 + 1], ag);
+          ag = fmaf(G1.z, r1[4 * c4 + 2], ag); ag = fmaf(G1.w, r1[4 * c4 + 3], ag);
+        }
+        fv[j] = tanhf(af);
+        gv[j] = 1.0f / (1.0f + expf(-ag));
+      }
+      *reinterpret_cast<float4 *>(fo + cg) = make_float4(fv[0], fv[1], fv[2], fv[3]);
+      *reinterpret_cast<float4 *>(go + cg) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+      *reinterpret_cast<float4 *>(uo + cg) = make_float4(fv[0] * gv[0], fv[1] * gv[1], fv[2] * gv[2], fv[3] * gv[3]);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase S: skip conv at the last time step only ----
+  if (t == a.Tout - 1) {
+    copy_to_smem(Y, U, N);
+    __syncthreads();
+    {
+      const int k = tid;  // 256 skip channels
+      float wk[GC];
+      load_row(a.w.skip_w + (size_t)k * GC, wk);
+      const float bk = a.w.skip_b[k];
+      float *sk = a.skip + (size_t)b * N * GSKIP + k;
+      for (int n = 0; n < N; ++n) {
+        const float4 *y = reinterpret_cast<const float4 *>(Y + (size_t)n * GC);
+        float acc = bk;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 yy = y[c4];
+          acc = fmaf(wk[4 * c4], yy.x, acc); acc = fmaf(wk[4 * c4 + 1], yy.y, acc);
+          acc = fmaf(wk[4 * c4 + 2], yy.z, acc); acc = fmaf(wk[4 * c4 + 3], yy.w, acc);
+        }
+        sk[(size_t)n * GSKIP] += acc;
+      }
+    }
+    __syncthreads();
+  }
+  if (!a.has_gcn) return;
+
+  // ---- stage the 7 [32x32] blocks of the gcn 1x1 conv: Wb[k][co][ci] = mlp_w[co][k*32+ci] ----
+  for (int i = tid; i < 7 * 1024; i += GW_THREADS) {
+    const int k = i >> 10, co = (i >> 5) & 31, ci = i & 31;
+    Wb[i] = a.w.mlp_w[(size_t)co * 224 + k * 32 + ci];
+  }
+  __syncthreads();
+
+  // ---- phase M: diffusion, Horner form per support ----
+  for (int s = 0; s < 3; ++s) {
+    const float *Ps = a.P[s] + (size_t)b * a.pstride[s];
+    const float *W1 = Wb + (1 + 2 * s) * 1024, *W2 = Wb + (2 + 2 * s) * 1024;
+    // a = W_s2 u  -> Y
+    for (int n = tid; n < N; n += GW_THREADS) {
+      float u[GC];
+      load_row(U + (size_t)n * GC, u);
+      float *yr = Y + (size_t)n * GC;
+      matvec_chunks(W2, u, [&](int cg, float4 v) { st4(yr + 4 * cg, v); });
+    }
+    __syncthreads();
+    // m = P^T a -> M (global scratch)
+    mix_nodes(Ps, Y, N, [&](int w, float (&acc)[GC]) { store_row(Mb + (size_t)w * GC, acc); });
+    __syncthreads();
+    // q = W_s1 u + m -> Y and stash
+    float *qs = a.q[s] + ocol;
+    for (int n = tid; n < N; n += GW_THREADS) {
+      float u[GC];
+      load_row(U + (size_t)n * GC, u);
+      float *yr = Y + (size_t)n * GC, *qr = qs + (size_t)n * GC;
+      const float *mr = Mb + (size_t)n * GC;
+      matvec_chunks(W1, u, [&](int cg, float4 v) {
+        v = add4(v, ld4(mr + 4 * cg));
+        st4(yr + 4 * cg, v);
+        st4(qr + 4 * cg, v);
+      });
+    }
+    __syncthreads();
+    // o = P^T q, accumulated into H
+    if (s == 0) {
+      mix_nodes(Ps, Y, N, [&](int w, float (&acc)[GC]) { store_row(Hb + (size_t)w * GC, acc); });
+    } else {
+      mix_nodes(Ps, Y, N, [&](int w, float (&acc)[GC]) {
+        float h[GC];
+        load_row(Hb + (size_t)w * GC, h);
+#pragma unroll
+        for (int c = 0; c < GC; ++c) h[c] += acc[c];
+        store_row(Hb + (size_t)w * GC, h);
+      });
+    }
+    __syncthreads();
+  }
+
+  // ---- phase F: h = bm + W0 u + H; dropout; residual; pre-BN output + BN partial sums ----
+  for (int n = tid; n < N; n += GW_THREADS) {
+    float u[GC];
+    load_row(U + (size_t)n * GC, u);
+    const float *hr = Hb + (size_t)n * GC, *zr = z1 + (size_t)n * GC;
+    float *yr = Y + (size_t)n * GC, *zo = a.zout + ocol + (size_t)n * GC;
+    const uint64_t elem0 = (uint64_t)(ocol + (size_t)n * GC);
+    matvec_chunks(Wb, u, [&](int cg, float4 v) {
+      v = add4(add4(v, ld4(hr + 4 * cg)), ld4(a.w.mlp_b + 4 * cg));
+      if (a.drop_thr) v = dropout4(v, elem0, cg, a.drop_thr, a.drop_scale, a.key);
+      float4 r = ld4(zr + 4 * cg);
+      if (a.has_in_bn) {
+        const float4 sc = ld4(a.in_scale + 4 * cg), sh = ld4(a.in_shift + 4 * cg);
+        r = make_float4(fmaf(r.x, sc.x, sh.x), fmaf(r.y, sc.y, sh.y), fmaf(r.z, sc.z, sh.z), fmaf(r.w, sc.w, sh.w));
+      }
+      v = add4(v, r);
+      st4(zo + 4 * cg, v);
+      st4(yr + 4 * cg, v);
+    });
+  }
+  __syncthreads();
+  if (a.collect_stats) column_sums_to(Y, N, Wb, a.sums, a.sums + 32);
+}
+
+// sums (double [2][32]) -> stats [4][32] floats: mean, biased var, scale, shift
+__global__ void bn_finalize_kernel(const double *sums, double count, const float *gamma, const float *beta, float *stats) {
+  const int c = threadIdx.x;
+  const double mean = sums[c] / count;
+  double var = sums[32 + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+  stats[c] = (float)mean;
+  stats[32 + c] = (float)var;
+  stats[64 + c] = gamma[c] * rstd;
+  stats[96 + c] = beta[c] - (float)mean * gamma[c] * rstd;
+}
+
+// ---------------------------------------------------------------------------
+// backward, phase 1: grid (T_out, B).  From d(BN output) of this layer (or nothing for the dead last
+// gcn) and dskip, through the gcn and the gate non-linearities, to d(pre-activations) of both convs.
+// ---------------------------------------------------------------------------
+struct GwBwdArgs {
+  int Tin, Tout, dil, N, has_gcn;
+  const float *drnext;      // [B,Tout,N,32] grad wrt BN(z) of this layer
+  const float *z;           // [B,Tout,N,32] pre-BN output of this layer
+  const float *stats;       // this layer's BN [4][32]
+  const float *coef;        // BN backward: [0]=gamma*rstd, [1]=S1/M, [2]=S2/M   ([4][32])
+  const float *Pt[3]; long long pstride[3];
+  step_gw_layer_params w;
+  step_gw_layer_grads gr;
+  const float *f, *g;
+  const float *dskip;       // [B,N,256]
+  float *U, *DH, *DZC, *DQ[3], *A[3], *DA, *DU, *DPF, *DPG;
+  uint32_t drop_thr; float drop_scale; uint64_t key;
+};
+
+__global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int N = a.N, tid = threadIdx.x, t = blockIdx.x, b = blockIdx.y;
+  float *Y = smem;
+  float *Wb = smem + (size_t)N * GC;          // 7*1024
+  float *tiles = Wb + 7 * 1024;               // 2*64*33
+  const size_t col = (size_t)N * GC;
+  const size_t ocol = ((size_t)b * a.Tout + t) * col;
+  float *U = a.U + ocol, *DH = a.DH + ocol, *DZC = a.DZC + ocol, *DA = a.DA + ocol, *DU = a.DU + ocol;
+  const float *fb = a.f + ocol, *gb = a.g + ocol;
+
+  if (a.has_gcn) {
+    for (int i = tid; i < 7 * 1024; i += GW_THREADS) {
+      const int k = i >> 10, co = (i >> 5) & 31, ci = i & 31;
+      Wb[i] = a.w.mlp_w[(size_t)co * 224 + k * 32 + ci];
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 0: u, dz (through BatchNorm), dh (through dropout), du = W0^T dh ----
+  for (int n = tid; n < N; n += GW_THREADS) {
+    {
+      float fv[GC], gv[GC];
+      load_row(fb + (size_t)n * GC, fv);
+      load_row(gb + (size_t)n * GC, gv);
+#pragma unroll
+      for (int c = 0; c < GC; ++c) fv[c] *= gv[c];
+      store_row(U + (size_t)n * GC, fv);
+    }
+    float du[GC];
+#pragma unroll
+    for (int c = 0; c < GC; ++c) du[c] = 0.f;
+    if (a.has_gcn) {
+      float dh[GC];
+      {
+        float zz[GC];
+        load_row(a.drnext + ocol + (size_t)n * GC, dh);
+        load_row(a.z + ocol + (size_t)n * GC, zz);
+#pragma unroll
+        for (int c = 0; c < GC; ++c) {
+          const float xhat = (zz[c] - a.stats[c]) * a.coef[96 + c];
+          dh[c] = a.coef[c] * (dh[c] - a.coef[32 + c] - xhat * a.coef[64 + c]);
+        }
+      }
+      store_row(DZC + (size_t)n * GC, dh);
+      if (a.drop_thr) dropout_row(dh, (uint64_t)(ocol + (size_t)n * GC), a.drop_thr, a.drop_scale, a.key);
+      store_row(DH + (size_t)n * GC, dh);
+      store_row(Y + (size_t)n * GC, dh);
+      matvec_t_acc(Wb, Y + (size_t)n * GC, du);
+    }
+    store_row(DU + (size_t)n * GC, du);
+  }
+  __syncthreads();
+
+  if (a.has_gcn) {
+    // d mlp bias = column sums of dh
+    {
+      const int c = tid & 31, grp = tid >> 5;
+      float s = 0.f;
+      for (int n = grp; n < N; n += GW_THREADS / 32) s += Y[(size_t)n * GC + c];
+      tiles[grp * 32 + c] = s;
+      __syncthreads();
+      if (tid < 32) {
+        float ts = 0.f;
+#pragma unroll
+        for (int g2 = 0; g2 < GW_THREADS / 32; ++g2) ts += tiles[g2 * 32 + c];
+        atomicAdd(a.gr.mlp_b + c, ts);
+      }
+      __syncthreads();
+    }
+    outer_acc(DH, U, N, tiles, a.gr.mlp_w, 224);  // block 0: dW0[co][ci] += dh[n][co] u[n][ci]
+
+    for (int s = 0; s < 3; ++s) {
+      const float *Pts = a.Pt[s] + (size_t)b * a.pstride[s];
+      const float *W1 = Wb + (1 + 2 * s) * 1024, *W2 = Wb + (2 + 2 * s) * 1024;
+      float *DQ = a.DQ[s] + ocol, *As = a.A[s] + ocol;
+      // Y holds dh.  dq = P dh
+      mix_nodes(Pts, Y, N, [&](int v, float (&acc)[GC]) { store_row(DQ + (size_t)v * GC, acc); });
+      __syncthreads();
+      copy_to_smem(Y, DQ, N);
+      __syncthreads();
+      // da = P dq
+      mix_nodes(Pts, Y, N, [&](int v, float (&acc)[GC]) { store_row(DA + (size_t)v * GC, acc); });
+      __syncthreads();
+      // per node: a = W_s2 u (stash for dP), du += W_s1^T dq + W_s2^T da
+      for (int n = tid; n < N; n += GW_THREADS) {
+        {
+          float u[GC];
+          load_row(U + (size_t)n * GC, u);
+          float *ar = As + (size_t)n * GC;
+          matvec_chunks(W2, u, [&](int cg, float4 v) { st4(ar + 4 * cg, v); });
+        }
+        float du[GC];
+        load_row(DU + (size_t)n * GC, du);
+        matvec_t_acc(W1, Y + (size_t)n * GC, du);   // dq
+        matvec_t_acc(W2, DA + (size_t)n * GC, du);
+        store_row(DU + (size_t)n * GC, du);
+      }
+      outer_acc(DQ, U, N, tiles, a.gr.mlp_w + (1 + 2 * s) * 32, 224);
+      outer_acc(DA, U, N, tiles, a.gr.mlp_w + (2 + 2 * s) * 32, 224);
+      copy_to_smem(Y, DH, N);
+      __syncthreads();
+    }
+  }
+
+  // ---- skip path (last time step only): du += Wk^T dskip, dWk, dbk ----
+  if (t == a.Tout - 1) {
+    const float *ds = a.dskip + (size_t)b * N * GSKIP;
+    for (int n = tid; n < N; n += GW_THREADS) {
+      float du[GC];
+      load_row(DU + (size_t)n * GC, du);
+      const float *dsn = ds + (size_t)n * GSKIP;
+      for (int k = 0; k < GSKIP; ++k) {
+        const float d = dsn[k];
+        const float4 *wk = reinterpret_cast<const float4 *>(a.w.skip_w + (size_t)k * GC);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 ww = wk[c4];
+          du[4 * c4] = fmaf(ww.x, d, du[4 * c4]); du[4 * c4 + 1] = fmaf(ww.y, d, du[4 * c4 + 1]);
+          du[4 * c4 + 2] = fmaf(ww.z, d, du[4 * c4 + 2]); du[4 * c4 + 3] = fmaf(ww.w, d, du[4 * c4 + 3]);
+        }
+      }
+      store_row(DU + (size_t)n * GC, du);
+    }
+    __syncthreads();
+    copy_to_smem(Y, U, N);
+    __syncthreads();
+    {
+      const int k = tid;
+      float acc[GC];
+#pragma unroll
+      for (int c = 0; c < GC; ++c) acc[c] = 0.f;
+      float bsum = 0.f;
+      for (int n = 0; n < N; ++n) {
+        const float d = ds[(size_t)n * GSKIP + k];
+        bsum += d;
+        const float4 *y = reinterpret_cast<const float4 *>(Y + (size_t)n * GC);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 yy = y[c4];
+          acc[4 * c4] = fmaf(d, yy.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(d, yy.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(d, yy.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(d, yy.w, acc[4 * c4 + 3]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < GC; ++c) atomicAdd(a.gr.skip_w + (size_t)k * GC + c, acc[c]);
+      atomicAdd(a.gr.skip_b + k, bsum);
+    }
+    __syncthreads();
+  }
+
+  // ---- through the gate: d(pre-tanh), d(pre-sigmoid) ----
+  for (int n = tid; n < N; n += GW_THREADS) {
+    float fv[GC], gv[GC], du[GC], pf[GC], pg[GC];
+    load_row(fb + (size_t)n * GC, fv);
+    load_row(gb + (size_t)n * GC, gv);
+    load_row(DU + (size_t)n * GC, du);
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      pf[c] = du[c] * gv[c] * (1.f - fv[c] * fv[c]);
+      pg[c] = du[c] * fv[c] * gv[c] * (1.f - gv[c]);
+    }
+    store_row(a.DPF + ocol + (size_t)n * GC, pf);
+    store_row(a.DPG + ocol + (size_t)n * GC, pg);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// dP_s[b][v][w] += sum_t sum_c ( Q_s[b,t,v,c] DH[b,t,w,c] + A_s[b,t,v,c] DQ_s[b,t,w,c] )
+// grid (ceil(N/64), ceil(N/64), 3*B); 64x64 tile, 4x4 per thread.
+// ---------------------------------------------------------------------------
+struct GwDpArgs {
+  int N, T, B;
+  const float *Q[3], *A[3], *DQ[3], *DH;
+  float *dP[3]; long long pstride[3];
+};
+
+__global__ void __launch_bounds__(256) gw_dP_kernel(GwDpArgs a) {
+  __shared__ __align__(16) float Xs[GC][68];
+  __shared__ __align__(16) float Ws[GC][68];
+  const int N = a.N, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int s = blockIdx.z / a.B, b = blockIdx.z % a.B;
+  const int v0 = blockIdx.y * 64, w0 = blockIdx.x * 64;
+  const size_t col = (size_t)N * GC;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int it = 0; it < 2 * a.T; ++it) {
+    const int t = it >> 1, pair = it & 1;
+    const float *X = (pair ? a.A[s] : a.Q[s]) + ((size_t)b * a.T + t) * col;
+    const float *Wm = (pair ? a.DQ[s] : a.DH) + ((size_t)b * a.T + t) * col;
+    __syncthreads();
+    for (int i = tid; i < 64 * 8; i += 256) {
+      const int n = i >> 3, c4 = (i & 7) * 4;
+      float4 xv = make_float4(0, 0, 0, 0), wv = xv;
+      if (v0 + n < N) xv = *reinterpret_cast<const float4 *>(X + (size_t)(v0 + n) * GC + c4);
+      if (w0 + n < N) wv = *reinterpret_cast<const float4 *>(Wm + (size_t)(w0 + n) * GC + c4);
+      Xs[c4][n] = xv.x; Xs[c4 + 1][n] = xv.y; Xs[c4 + 2][n] = xv.z; Xs[c4 + 3][n] = xv.w;
+      Ws[c4][n] = wv.x; Ws[c4 + 1][n] = wv.y; Ws[c4 + 2][n] = wv.z; Ws[c4 + 3][n] = wv.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      const float4 xv = *reinterpret_cast<const float4 *>(&Xs[c][ty * 4]);
+      const float4 wv = *reinterpret_cast<const float4 *>(&Ws[c][tx * 4]);
+      const float x[4] = {xv.x, xv.y, xv.z, xv.w}, w[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(x[i], w[j], acc[i][j]);
+    }
+  }
+  float *dP = a.dP[s] + (size_t)b * a.pstride[s];
+  const bool shared_across_batch = (a.pstride[s] == 0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int v = v0 + ty * 4 + i;
+    if (v >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int w = w0 + tx * 4 + j;
+      if (w >= N) continue;
+      if (shared_across_batch) atomicAdd(dP + (size_t)v * N + w, acc[i][j]);
+      else dP[(size_t)v * N + w] += acc[i][j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// backward, phase 2: grid (T_in, B).  Transposed temporal conv + residual path -> d(normalised
+// input); conv weight/bias grads; partial sums for the previous layer's BatchNorm backward.
+// ---------------------------------------------------------------------------
+struct GwBwdInArgs {
+  int Tin, Tout, dil, N, has_gcn, has_in_bn;
+  const float *zin;          // [B,Tin,N,32] pre-BN output of the previous layer (or x0)
+  const float *in_stats;     // previous layer's BN [4][32] (mean,var,scale,shift)
+  const float *DPF, *DPG, *DZC;
+  step_gw_layer_params w;
+  step_gw_layer_grads gr;
+  float *drin;               // [B,Tin,N,32]
+  double *sums;              // previous layer's backward sums [2][32] (S1, S2) or null
+};
+
+__global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_in_kernel(GwBwdInArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int N = a.N, tid = threadIdx.x, tau = blockIdx.x, b = blockIdx.y;
+  float *Y = smem;                       // r (normalised input) [N][32]
+  float *Wb = smem + (size_t)N * GC;     // 4*1024 conv weights
+  float *tiles = Wb + 4 * 1024;          // 2*64*33
+  float *red = tiles + 2 * 64 * 33;      // 128 floats
+  const size_t col = (size_t)N * GC;
+  const bool has0 = tau < a.Tout, has1 = (tau - a.dil) >= 0;
+  const size_t c0 = ((size_t)b * a.Tout + tau) * col, c1 = ((size_t)b * a.Tout + (tau - a.dil)) * col;
+  const size_t icol = ((size_t)b * a.Tin + tau) * col;
+
+  for (int i = tid; i < 1024; i += GW_THREADS) {
+    Wb[i] = a.w.filter_w[2 * i]; Wb[1024 + i] = a.w.filter_w[2 * i + 1];
+    Wb[2048 + i] = a.w.gate_w[2 * i]; Wb[3072 + i] = a.w.gate_w[2 * i + 1];
+  }
+  if (tid < 128) red[tid] = 0.f;
+  __syncthreads();
+
+  float p1[GC], p2[GC], pbf[GC], pbg[GC];   // per-thread partials: S1, S2, d filter_b, d gate_b
+#pragma unroll
+  for (int c = 0; c < GC; ++c) { p1[c] = 0.f; p2[c] = 0.f; pbf[c] = 0.f; pbg[c] = 0.f; }
+
+  for (int n = tid; n < N; n += GW_THREADS) {
+    float acc[GC], x[GC];
+#pragma unroll
+    for (int c = 0; c < GC; ++c) acc[c] = 0.f;
+    if (has0) {
+      load_row(a.DPF + c0 + (size_t)n * GC, x);
+      matvec_t_acc(Wb, a.DPF + c0 + (size_t)n * GC, acc);
+#pragma unroll
+      for (int c = 0; c < GC; ++c) pbf[c] += x[c];
+      load_row(a.DPG + c0 + (size_t)n * GC, x);
+      matvec_t_acc(Wb + 2048, a.DPG + c0 + (size_t)n * GC, acc);
+#pragma unroll
+      for (int c = 0; c < GC; ++c) pbg[c] += x[c];
+    }
+    if (has1) {
+      matvec_t_acc(Wb + 1024, a.DPF + c1 + (size_t)n * GC, acc);
+      matvec_t_acc(Wb + 3072, a.DPG + c1 + (size_t)n * GC, acc);
+      if (a.has_gcn) {
+        load_row(a.DZC + c1 + (size_t)n * GC, x);
+#pragma unroll
+        for (int c = 0; c < GC; ++c) acc[c] += x[c];
+      }
+    }
+    store_row(a.drin + icol + (size_t)n * GC, acc);
+    load_row(a.zin + icol + (size_t)n * GC, x);
+    if (a.has_in_bn) {
+#pragma unroll
+      for (int c = 0; c < GC; ++c) {
+        const float mean = a.in_stats[c], var = a.in_stats[32 + c];
+        const float xhat = (x[c] - mean) * (1.0f / sqrtf(var + 1e-5f));
+        p1[c] += acc[c];
+        p2[c] = fmaf(acc[c], xhat, p2[c]);
+        x[c] = fmaf(x[c], a.in_stats[64 + c], a.in_stats[96 + c]);
+      }
+    }
+    store_row(Y + (size_t)n * GC, x);
+  }
+  // reduce the per-thread partials: warp shuffle per channel, lane c keeps channel c
+  {
+    const int lane = tid & 31;
+    float k1 = 0.f, k2 = 0.f, kf = 0.f, kg = 0.f;
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      const float s1 = warp_sum(p1[c]), s2 = warp_sum(p2[c]), sf = warp_sum(pbf[c]), sg = warp_sum(pbg[c]);
+      if (lane == c) { k1 = s1; k2 = s2; kf = sf; kg = sg; }
+    }
+    atomicAdd(&red[lane], k1); atomicAdd(&red[32 + lane], k2);
+    atomicAdd(&red[64 + lane], kf); atomicAdd(&red[96 + lane], kg);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    if (a.sums != nullptr) {
+      atomicAdd(a.sums + tid, (double)red[tid]);
+      atomicAdd(a.sums + 32 + tid, (double)red[32 + tid]);
+    }
+    if (has0) {
+      atomicAdd(a.gr.filter_b + tid, red[64 + tid]);
+      atomicAdd(a.gr.gate_b + tid, red[96 + tid]);
+    }
+  }
+  // conv weight grads: dW[co][ci][tap] += sum_n dpre[tau - tap*dil][n][co] * r[tau][n][ci]
+  // r rows live in Y (smem); outer_acc wants global operands, so route Y through the U-like path:
+  // second operand read from smem directly.
+  auto outer_from_smem = [&](const float *X, float *dst, int tap) {
+    float *T1 = tiles;
+    const int co = tid >> 3, ci4 = (tid & 7) * 4;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int n0 = 0; n0 < N; n0 += 64) {
+      __syncthreads();
+      for (int i = tid; i < 64 * GC; i += GW_THREADS) {
+        const int n = i >> 5, c = i & 31;
+        T1[n * 33 + c] = ((n0 + n) < N) ? X[(size_t)(n0 + n) * GC + c] : 0.f;
+      }
+      __syncthreads();
+      const int nmax = (N - n0 < 64) ? (N - n0) : 64;
+      for (int n = 0; n < nmax; ++n) {
+        const float xv = T1[n * 33 + co];
+        const float4 r = *reinterpret_cast<const float4 *>(Y + (size_t)(n0 + n) * GC + ci4);
+        a0 = fmaf(xv, r.x, a0); a1 = fmaf(xv, r.y, a1); a2 = fmaf(xv, r.z, a2); a3 = fmaf(xv, r.w, a3);
+      }
+    }
+    float *d = dst + ((size_t)co * GC + ci4) * 2 + tap;
+    atomicAdd(d, a0); atomicAdd(d + 2, a1); atomicAdd(d + 4, a2); atomicAdd(d + 6, a3);
+  };
+  if (has0) {
+    outer_from_smem(a.DPF + c0, a.gr.filter_w, 0);
+    outer_from_smem(a.DPG + c0, a.gr.gate_w, 0);
+  }
+  if (has1) {
+    outer_from_smem(a.DPF + c1, a.gr.filter_w, 1);
+    outer_from_smem(a.DPG + c1, a.gr.gate_w, 1);
+  }
+}
+
+// backward sums (double [2][32]: S1 = sum d, S2 = sum d*xhat) -> coef [4][32] + BN param grads
+__global__ void bn_bwd_finalize_kernel(const double *sums, double count, const float *gamma, const float *stats,
+                                       float *coef, float *dgamma, float *dbeta) {
+  const int c = threadIdx.x;
+  const float rstd = 1.0f / sqrtf(stats[32 + c] + 1e-5f);
+  coef[c] = gamma[c] * rstd;
+  coef[32 + c] = (float)(sums[c] / count);
+  coef[64 + c] = (float)(sums[32 + c] / count);
+  coef[96 + c] = rstd;
+  dgamma[c] = (float)sums[32 + c];
+  dbeta[c] = (float)sums[c];
+}
+
+}  // namespace stepk
+
+using namespace stepk;
+
+extern "C" size_t step_gwnet_stash_floats(int B, int N, int n_layers) {
+  if (B <= 0 || N <= 0 || n_layers <= 0 || n_layers > GW_MAX_LAYERS) return 0;
+  return make_plan(B, N, n_layers).total;
+}
+
+static size_t fwd_smem_bytes(int N) { return ((size_t)N * GC + 7 * 1024) * sizeof(float); }
+static size_t bwd_smem_bytes(int N) { return ((size_t)N * GC + 7 * 1024 + 2 * 64 * 33) * sizeof(float); }
+static size_t bwd_in_smem_bytes(int N) { return ((size_t)N * GC + 4 * 1024 + 2 * 64 * 33 + 128) * sizeof(float); }
+
+static int gw_prepare(int N) {
+  if (bwd_smem_bytes(N) > 227 * 1024)
+    return fail(STEP_EUNSUPPORTED, "gwnet: N=%lld needs more shared memory than one SM has", N);
+  int rc;
+  if ((rc = allow_smem(gw_layer_fwd_kernel, 227 * 1024))) return rc;
+  if ((rc = allow_smem(gw_layer_bwd_kernel, 227 * 1024))) return rc;
+  if ((rc = allow_smem(gw_layer_bwd_in_kernel, 227 * 1024))) return rc;
+  return STEP_OK;
+}
+
+extern "C" int step_gwnet_stack_fwd(const float *x0, const float *P1, const float *P2, const float *P3,
+                                    const step_gw_layer_params *Lp, int n_layers, int B, int N, int training,
+                                    float drop_p, unsigned long long seed, float *skip_out, float *bn_stats, float *stash,
+                                    void *stream) {
+  STEP_REQUIRE(x0 && P1 && P2 && P3 && Lp && skip_out && bn_stats && stash, "gwnet_fwd: null pointer");
+  STEP_REQUIRE(B > 0 && B <= 65535 && N > 0 && n_layers >= 1 && n_layers <= GW_MAX_LAYERS, "gwnet_fwd: bad shape");
+  int rc = gw_prepare(N);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GwPlan p = make_plan(B, N, n_layers);
+  cudaError_t e = cudaMemsetAsync(skip_out, 0, (size_t)B * N * GSKIP * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(stash + p.off_sums_fwd, 0, (size_t)n_layers * 2 * 32 * sizeof(double), st);
+  if (e != cudaSuccess) return fail_msg((int)e, cudaGetErrorString(e));
+  for (int i = 0; i < n_layers; ++i) {
+    GwFwdArgs a{};
+    a.zin = (i == 0) ? x0 : stash + p.off_z[i - 1];
+    a.zout = stash + p.off_z[i];
+    a.Tin = p.Tin[i]; a.Tout = p.Tout[i]; a.dil = p.dil[i]; a.N = N;
+    a.has_gcn = (Lp[i].mlp_w != nullptr);
+    a.has_in_bn = (i > 0);
+    a.collect_stats = training ? 1 : 0;
+    if (i > 0) { a.in_scale = bn_stats + (size_t)(i - 1) * 128 + 64; a.in_shift = bn_stats + (size_t)(i - 1) * 128 + 96; }
+    a.P[0] = P1; a.P[1] = P2; a.P[2] = P3;
+    a.pstride[0] = (long long)N * N; a.pstride[1] = (long long)N * N; a.pstride[2] = 0;
+    a.w = Lp[i];
+    a.f = stash + p.off_f[i]; a.g = stash + p.off_g[i];
+    for (int s = 0; s < 3; ++s) a.q[s] = stash + p.off_q[i][s];
+    a.U = stash + p.off_U; a.M = stash + p.off_M; a.H = stash + p.off_H;
+    a.skip = skip_out;
+    a.sums = reinterpret_cast<double *>(stash + p.off_sums_fwd) + (size_t)i * 64;
+    if (training && drop_p > 0.f) { a.drop_thr = drop_threshold(drop_p); a.drop_scale = 1.f / (1.f - drop_p); }
+    else { a.drop_thr = 0; a.drop_scale = 1.f; }
+    a.key = rng_key(seed, 0x100u + i);
+    gw_layer_fwd_kernel<<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
+    STEP_LAUNCH_CHECK("gw_layer_fwd_kernel");
+    if (a.has_gcn && training) {
+      bn_finalize_kernel<<<1, 32, 0, st>>>(a.sums, (double)B * a.Tout * N, Lp[i].bn_w, Lp[i].bn_b, bn_stats + (size_t)i * 128);
+      STEP_LAUNCH_CHECK("bn_finalize_kernel");
+    }
+  }
+  return STEP_OK;
+}
+
+extern "C" int step_gwnet_stack_bwd(const float *dskip, const float *x0, const float *P1, const float *P2, const float *P3,
+                                    const float *P1t, const float *P2t, const float *P3t,
+                                    const step_gw_layer_params *Lp, const step_gw_layer_grads *Lg, int n_layers, int B,
+                                    int N, float drop_p, unsigned long long seed, const float *bn_stats, float *stash,
+                                    float *dx0, float *dP1, float *dP2, float *dP3, void *stream) {
+  STEP_REQUIRE(dskip && x0 && P1 && P2 && P3 && P1t && P2t && P3t && Lp && Lg && bn_stats && stash && dx0 && dP1 && dP2 && dP3,
+               "gwnet_bwd: null pointer");
+  STEP_REQUIRE(B > 0 && B <= 21845 && N > 0 && n_layers >= 1 && n_layers <= GW_MAX_LAYERS, "gwnet_bwd: bad shape");
+  int rc = gw_prepare(N);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GwPlan p = make_plan(B, N, n_layers);
+  const size_t nn = (size_t)N * N;
+  cudaError_t e = cudaMemsetAsync(dP1, 0, (size_t)B * nn * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dP2, 0, (size_t)B * nn * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dP3, 0, nn * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(stash + p.off_sums_bwd, 0, (size_t)n_layers * 2 * 32 * sizeof(double), st);
+  for (int i = 0; i < n_layers && e == cudaSuccess; ++i) {
+    const step_gw_layer_grads &g = Lg[i];
+    STEP_REQUIRE(g.filter_w && g.filter_b && g.gate_w && g.gate_b && g.skip_w && g.skip_b, "gwnet_bwd: null grad pointer");
+    e = cudaMemsetAsync(g.filter_w, 0, 2048 * sizeof(float), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g.gate_w, 0, 2048 * sizeof(float), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g.filter_b, 0, 32 * sizeof(float), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g.gate_b, 0, 32 * sizeof(float), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g.skip_w, 0, GSKIP * 32 * sizeof(float), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g.skip_b, 0, GSKIP * sizeof(float), st);
+    if (Lp[i].mlp_w != nullptr) {
+      STEP_REQUIRE(g.mlp_w && g.mlp_b && g.bn_w && g.bn_b, "gwnet_bwd: null grad pointer");
+      if (e == cudaSuccess) e = cudaMemsetAsync(g.mlp_w, 0, 32 * 224 * sizeof(float), st);
+      if (e == cudaSuccess) e = cudaMemsetAsync(g.mlp_b, 0, 32 * sizeof(float), st);
+    }
+  }
+  if (e != cudaSuccess) return fail_msg((int)e, cudaGetErrorString(e));
+
+  uint32_t thr = 0; float dscale = 1.f;
+  if (drop_p > 0.f) { thr = drop_threshold(drop_p); dscale = 1.f / (1.f - drop_p); }
+  float *coef = stash + p.off_coef;
+  double *bsums = reinterpret_cast<double *>(stash + p.off_sums_bwd);
+
+  for (int i = n_layers - 1; i >= 0; --i) {
+    const bool has_gcn = (Lp[i].mlp_w != nullptr);
+    GwBwdArgs a{};
+    a.Tin = p.Tin[i]; a.Tout = p.Tout[i]; a.dil = p.dil[i]; a.N = N; a.has_gcn = has_gcn;
+    a.drnext = stash + p.off_DR[(i + 1) & 1];
+    a.z = stash + p.off_z[i];
+    a.stats = bn_stats + (size_t)i * 128;
+    a.coef = coef + (size_t)i * 128;
+    a.Pt[0] = P1t; a.Pt[1] = P2t; a.Pt[2] = P3t;
+    a.pstride[0] = (long long)nn; a.pstride[1] = (long long)nn; a.pstride[2] = 0;
+    a.w = Lp[i]; a.gr = Lg[i];
+    a.f = stash + p.off_f[i]; a.g = stash + p.off_g[i];
+    a.dskip = dskip;
+    a.U = stash + p.off_U; a.DH = stash + p.off_DH; a.DZC = stash + p.off_DZC;
+    for (int s = 0; s < 3; ++s) { a.DQ[s] = stash + p.off_DQ[s]; a.A[s] = stash + p.off_A[s]; }
+    a.DA = stash + p.off_DA; a.DU = stash + p.off_DU; a.DPF = stash + p.off_DPF; a.DPG = stash + p.off_DPG;
+    a.drop_thr = thr; a.drop_scale = dscale; a.key = rng_key(seed, 0x100u + i);
+    gw_layer_bwd_kernel<<<dim3(a.Tout, B), GW_THREADS, bwd_smem_bytes(N), st>>>(a);
+    STEP_LAUNCH_CHECK("gw_layer_bwd_kernel");
+
+    if (has_gcn) {
+      GwDpArgs d{};
+      d.N = N; d.T = p.Tout[i]; d.B = B;
+      for (int s = 0; s < 3; ++s) { d.Q[s] = stash + p.off_q[i][s]; d.A[s] = stash + p.off_A[s]; d.DQ[s] = stash + p.off_DQ[s]; }
+      d.DH = stash + p.off_DH;
+      d.dP[0] = dP1; d.dP[1] = dP2; d.dP[2] = dP3;
+      d.pstride[0] = (long long)nn; d.pstride[1] = (long long)nn; d.pstride[2] = 0;
+      gw_dP_kernel<<<dim3((N + 63) / 64, (N + 63) / 64, 3 * B), 256, 0, st>>>(d);
+      STEP_LAUNCH_CHECK("gw_dP_kernel");
+    }
+
+    GwBwdInArgs c{};
+    c.Tin = p.Tin[i]; c.Tout = p.Tout[i]; c.dil = p.dil[i]; c.N = N; c.has_gcn = has_gcn; c.has_in_bn = (i > 0);
+    c.zin = (i == 0) ? x0 : stash + p.off_z[i - 1];
+    c.in_stats = (i > 0) ? bn_stats + (size_t)(i - 1) * 128 : nullptr;
+    c.DPF = stash + p.off_DPF; c.DPG = stash + p.off_DPG; c.DZC = stash + p.off_DZC;
+    c.w = Lp[i]; c.gr = Lg[i];
+    c.drin = (i == 0) ? dx0 : stash + p.off_DR[i & 1];
+    c.sums = (i > 0) ? bsums + (size_t)(i - 1) * 64 : nullptr;
+    gw_layer_bwd_in_kernel<<<dim3(c.Tin, B), GW_THREADS, bwd_in_smem_bytes(N), st>>>(c);
+    STEP_LAUNCH_CHECK("gw_layer_bwd_in_kernel");
+
+    if (i > 0) {
+      bn_bwd_finalize_kernel<<<1, 32, 0, st>>>(bsums + (size_t)(i - 1) * 64, (double)B * p.Tout[i - 1] * N, Lp[i - 1].bn_w,
+                                              bn_stats + (size_t)(i - 1) * 128, coef + (size_t)(i - 1) * 128,
+                                              Lg[i - 1].bn_w, Lg[i - 1].bn_b);
+      STEP_LAUNCH_CHECK("bn_bwd_finalize_kernel");
+    }
+  }
+  return STEP_OK;
+}

@@ -1,0 +1,296 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes) against the CPU oracle.
+
+Tolerances: everything is fp32; the bar for model outputs is MAE <= 1e-4 (BASELINE.json); kernel-level
+checks use max-abs / relative bounds a few fp32 ulps above accumulated rounding."""
+import math
+
+import pytest
+import torch
+
+from oracle import step_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel_err(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-12)).item()
+
+
+# --------------------------------------------------------------------------- linear / attention / LN
+@pytest.mark.parametrize("M,K,Nout,epi", [(1000, 96, 288, 0), (777, 96, 384, 1), (515, 384, 96, 2), (128, 96, 96, 2),
+                                          (5, 16, 7, 0)])
+def test_linear_epilogues(M, K, Nout, epi):
+    from step_b200 import ops
+    g = torch.Generator().manual_seed(M + K)
+    a, w, b = torch.randn(M, K, generator=g), torch.randn(Nout, K, generator=g) * 0.1, torch.randn(Nout, generator=g)
+    ref = a @ w.t() + b
+    kw = {}
+    if epi == 1:
+        ref = torch.relu(ref)
+    if epi == 2:
+        res, lw, lb = torch.randn(M, Nout, generator=g), torch.rand(Nout, generator=g) + 0.5, torch.randn(Nout, generator=g)
+        ref = O._layer_norm(ref + res, lw, lb)
+        kw = dict(residual=res.to(DEV), ln_w=lw.to(DEV), ln_b=lb.to(DEV))
+    out = ops.linear(a.to(DEV), w.to(DEV), b.to(DEV), epilogue=epi, **kw).cpu()
+    assert (out - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("S,P", [(5, 168), (3, 336), (2, 42), (4, 7)])
+def test_attention(S, P):
+    from step_b200 import ops
+    g = torch.Generator().manual_seed(S * 1000 + P)
+    qkv = torch.randn(S * P, 288, generator=g)
+    q, k, v = qkv.view(S, P, 288).split(96, -1)
+    sh = lambda t: t.reshape(S, P, 4, 24).transpose(1, 2)
+    att = torch.softmax(sh(q) @ sh(k).transpose(-1, -2) / math.sqrt(24), -1)
+    ref = (att @ sh(v)).transpose(1, 2).reshape(S * P, 96)
+    out = ops.attention(qkv.to(DEV), S, P).cpu()
+    assert (out - ref).abs().max().item() < 2e-5
+
+
+def test_attention_dropout_statistics():
+    from step_b200 import ops
+    S, P, p = 8, 168, 0.1
+    qkv = torch.zeros(S * P, 288)
+    qkv[:, 192:] = 1.0            # uniform attention, v = 1  ->  out = (#kept / P) / (1 - p)
+    out = ops.attention(qkv.to(DEV), S, P, drop_p=p, seed=123).cpu()
+    kept = out * (1 - p)
+    assert abs(kept.mean().item() - (1 - p)) < 2e-3
+    assert kept.std().item() == pytest.approx(math.sqrt(p * (1 - p) / P), rel=0.15)
+    out2 = ops.attention(qkv.to(DEV), S, P, drop_p=p, seed=123).cpu()
+    assert torch.equal(out, out2)                                   # counter-based: reproducible
+    out3 = ops.attention(qkv.to(DEV), S, P, drop_p=p, seed=124).cpu()
+    assert not torch.equal(out, out3)
+
+
+# --------------------------------------------------------------------------- whole encoder
+@pytest.mark.parametrize("B,N,P,chunk", [(2, 9, 168, 0), (1, 5, 336, 2), (3, 33, 24, 7)])
+def test_ts_encoder_matches_oracle(B, N, P, chunk):
+    from step_b200 import ops
+    sd = O.synthetic_tsformer_params(1)
+    g = torch.Generator().manual_seed(5)
+    long_history = torch.randn(B, P * 12, N, 3, generator=g)
+    ref = O.tsformer_encode(sd, long_history[..., [0]])
+    layers = []
+    for i in range(4):
+        p = f"encoder.transformer_encoder.layers.{i}."
+        layers.append({"in_proj_w": sd[p + "self_attn.in_proj_weight"], "in_proj_b": sd[p + "self_attn.in_proj_bias"],
+                       "out_proj_w": sd[p + "self_attn.out_proj.weight"], "out_proj_b": sd[p + "self_attn.out_proj.bias"],
+                       "lin1_w": sd[p + "linear1.weight"], "lin1_b": sd[p + "linear1.bias"],
+                       "lin2_w": sd[p + "linear2.weight"], "lin2_b": sd[p + "linear2.bias"],
+                       "norm1_w": sd[p + "norm1.weight"], "norm1_b": sd[p + "norm1.bias"],
+                       "norm2_w": sd[p + "norm2.weight"], "norm2_b": sd[p + "norm2.bias"]})
+    layers = [{k: v.to(DEV) for k, v in l.items()} for l in layers]
+    lh = long_history.to(DEV)
+    out = ops.ts_encoder_forward(lh[..., 0], sd["patch_embedding.input_embedding.weight"].to(DEV),
+                                 sd["patch_embedding.input_embedding.bias"].to(DEV),
+                                 sd["positional_encoding.position_embedding"].to(DEV), layers,
+                                 sd["encoder_norm.weight"].to(DEV), sd["encoder_norm.bias"].to(DEV), chunk_seqs=chunk).cpu()
+    assert out.shape == ref.shape
+    assert (out - ref).abs().mean().item() < 1e-5
+    assert (out - ref).abs().max().item() < 2e-4
+
+
+# --------------------------------------------------------------------------- kNN prior
+@pytest.mark.parametrize("B,N,D", [(3, 50, 96 * 20), (2, 207, 16128), (1, 131, 32)])
+def test_cosine_gram_and_topk(B, N, D):
+    from step_b200 import ops
+    g = torch.Generator().manual_seed(N)
+    x = torch.randn(B, N, D, generator=g)
+    x[:, 1] = x[:, 0] * 2.0            # exact duplicates up to scale -> threshold ties between symmetric pairs
+    ref_sim = O.cosine_similarity_gram(x)
+    sim = ops.cosine_gram(x.to(DEV))
+    assert (sim.cpu() - ref_sim).abs().max().item() < 2e-5
+    # symmetric bit-for-bit (same summation order for (i,j) and (j,i))
+    assert torch.equal(sim, sim.transpose(1, 2))
+    k = 10 * N
+    adj = ops.topk_mask(sim, k).cpu()
+    # exact semantics on OUR similarity values: count, threshold, diagonal, binary
+    s = sim.cpu().reshape(B, -1)
+    kth = torch.topk(s, k, dim=-1).values[:, -1]
+    a = adj.reshape(B, -1)
+    assert set(adj.unique().tolist()) <= {0.0, 1.0}
+    assert adj.diagonal(dim1=1, dim2=2).abs().sum().item() == 0
+    for b in range(B):
+        offdiag = ~torch.eye(N, dtype=torch.bool).reshape(-1)
+        above = (s[b] > kth[b]) & offdiag
+        assert bool((a[b][above] == 1).all())
+        assert bool((a[b][(s[b] < kth[b])] == 0).all())
+        n_diag_sel = int(((s[b] >= kth[b]) & ~offdiag).sum())
+        assert int(a[b].sum()) <= k - min(n_diag_sel, N) + 0
+    # against the oracle end-to-end (tie-breaks may differ)
+    ref_adj = O.knn_prior(x.view(B, N, 1, D), k)
+    assert int((adj != ref_adj).sum()) <= 2 * B + 4
+
+
+def test_topk_tie_break_is_lowest_index_first():
+    from step_b200 import ops
+    N = 6
+    sim = torch.zeros(1, N, N)
+    sim[0] += 0.5
+    sim[0, 2, 3] = 0.9
+    adj = ops.topk_mask(sim.to(DEV), 5).cpu()
+    # 0.9 first, then the four lowest flat indices among the 0.5 ties: (0,0) (0,1) (0,2) (0,3); diagonal dropped
+    expect = torch.zeros(N, N)
+    expect[2, 3] = 1; expect[0, 1] = 1; expect[0, 2] = 1; expect[0, 3] = 1
+    assert torch.equal(adj[0], expect)
+    # exact zeros are never selected (reference: where(res != 0))
+    z = torch.zeros(1, 4, 4); z[0, 0, 1] = 0.3
+    assert ops.topk_mask(z.to(DEV), 3).cpu().sum().item() == 1
+
+
+# --------------------------------------------------------------------------- edge logits + gumbel
+@pytest.mark.parametrize("N", [13, 207])
+def test_edge_logits_fwd_bwd(N):
+    from step_b200 import ops
+    g = torch.Generator().manual_seed(N)
+    sd = {"discrete_graph_learning." + k: torch.randn(*s, generator=g) * 0.3 for k, s in
+          {"fc_out.weight": (100, 200), "fc_out.bias": (100,), "fc_cat.weight": (2, 100), "fc_cat.bias": (2,)}.items()}
+    feat = torch.randn(N, 100, generator=g)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    f_ref = feat.clone().requires_grad_(True)
+    ref = O.edge_logits(leaves, f_ref)                       # [N*N, 2]
+    wgt = torch.randn(N * N, 2, generator=g)
+    th_w = torch.randn(N * N, generator=g)
+    (ref * wgt).sum().add((torch.softmax(ref, -1)[:, 0] * th_w).sum()).backward()
+
+    d = {k: v.to(DEV).requires_grad_(True) for k, v in sd.items()}
+    f = feat.to(DEV).requires_grad_(True)
+    W = d["discrete_graph_learning.fc_out.weight"]
+    ut = W[:, :100] @ f.t()
+    v = f @ W[:, 100:].t() + d["discrete_graph_learning.fc_out.bias"]
+    logits, theta = ops.EdgeLogits.apply(ut, v, d["discrete_graph_learning.fc_cat.weight"], d["discrete_graph_learning.fc_cat.bias"])
+    assert (logits.detach().cpu().reshape(N * N, 2) - ref.detach()).abs().max().item() < 1e-4
+    assert (theta.detach().cpu().reshape(-1) - torch.softmax(ref.detach(), -1)[:, 0]).abs().max().item() < 1e-5
+    ((logits.reshape(N * N, 2) * wgt.to(DEV)).sum() + (theta.reshape(-1) * th_w.to(DEV)).sum()).backward()
+    for k in sd:
+        assert rel_err(d[k].grad.cpu(), leaves[k].grad) < 1e-4, k
+    assert rel_err(f.grad.cpu(), f_ref.grad) < 1e-4
+
+
+def test_gumbel_sample_fwd_bwd():
+    from step_b200 import ops
+    B, N = 3, 41
+    g = torch.Generator().manual_seed(0)
+    logits = (torch.randn(N * N, 2, generator=g)).requires_grad_(True)
+    u = torch.rand(B, N * N, 2, generator=g)
+    y = O.gumbel_hard_sample(logits.unsqueeze(0).expand(B, -1, -1), u)
+    eye = torch.eye(N, dtype=torch.bool)
+    ref = y[..., 0].reshape(B, N, N).masked_fill(eye, 0.0)
+    wgt = torch.randn(B, N, N, generator=g)
+    (ref * wgt).sum().backward()
+    lg = logits.detach().reshape(N, N, 2).to(DEV).requires_grad_(True)
+    out = ops.GumbelSample.apply(lg, u.to(DEV), B, 0.5, 0)
+    assert int((out.detach().cpu() != ref.detach()).sum()) == 0
+    (out * wgt.to(DEV)).sum().backward()
+    assert rel_err(lg.grad.cpu().reshape(N * N, 2), logits.grad) < 1e-4
+    # in-kernel generator: Bernoulli(sigmoid(l0 - l1)) frequencies, reproducible per seed
+    lg0 = torch.zeros(N, N, 2, device=DEV); lg0[..., 0] = 1.0
+    s1 = ops.GumbelSample.apply(lg0, None, 64, 0.5, 7)
+    s2 = ops.GumbelSample.apply(lg0, None, 64, 0.5, 7)
+    assert torch.equal(s1, s2)
+    off = ~torch.eye(N, dtype=torch.bool, device=DEV)
+    freq = s1[:, off].mean().item()
+    assert abs(freq - torch.sigmoid(torch.tensor(1.0)).item()) < 0.01
+
+
+# --------------------------------------------------------------------------- Graph WaveNet stack
+def _gw_case(N, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    shapes = O.gwnet_param_shapes(N)
+    sd = {}
+    for k, s in shapes.items():
+        if k.startswith("nodevec"):
+            sd["backend." + k] = torch.randn(*s, generator=g)
+        elif k.startswith("bn."):
+            sd["backend." + k] = (1.0 if k.endswith("weight") else 0.0) + 0.2 * (torch.rand(*s, generator=g) - 0.5)
+        else:
+            fan = 1
+            for d in (shapes[k[:-4] + "weight"] if k.endswith("bias") else s)[1:]:
+                fan *= d
+            sd["backend." + k] = (torch.rand(*s, generator=g) * 2 - 1) / math.sqrt(fan)
+    history = torch.randn(B, 12, N, 3, generator=g)
+    hidden_last = torch.randn(B, N, 96, generator=g) * 0.4
+    adj = (torch.rand(B, N, N, generator=g) < 0.4).float() * (1 - torch.eye(N))
+    return sd, history, hidden_last, adj
+
+
+@pytest.mark.parametrize("N,B", [(23, 3), (207, 2), (300, 1)])
+def test_gwnet_forward_backward_matches_oracle(N, B):
+    from conftest import gw_args
+    from step.step_arch.graphwavenet import GraphWaveNet
+    sd, history, hidden_last, adj = _gw_case(N, B, N + B)
+    # oracle (CPU autograd)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    adj_ref = adj.clone().requires_grad_(True)
+    hid_ref = hidden_last.clone().requires_grad_(True)
+    full = dict(leaves); full.update({k: v for k, v in O.bn_buffers("PEMS08").items() if k.startswith("backend.")})
+    ref = O.gwnet_forward(full, history, hid_ref, adj_ref, train=True)
+    wgt = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+    (ref * wgt).sum().backward()
+    # ours
+    model = GraphWaveNet(**gw_args(N))
+    state = {k[len("backend."):]: v for k, v in sd.items()}
+    state.update({k[len("backend."):]: v for k, v in O.bn_buffers("PEMS08").items() if k.startswith("backend.")})
+    model.load_state_dict(state, strict=True)
+    model = model.to(DEV).train()
+    model.dropout = 0.0
+    adj_g = adj.to(DEV).requires_grad_(True)
+    hid_g = hidden_last.to(DEV).requires_grad_(True)
+    out = model(history.to(DEV), hid_g, adj_g)
+    assert (out.detach().cpu() - ref.detach()).abs().mean().item() < 1e-5
+    assert (out.detach().cpu() - ref.detach()).abs().max().item() < 2e-4
+    (out * wgt.to(DEV)).sum().backward()
+    assert rel_err(adj_g.grad.cpu(), adj_ref.grad) < 2e-3
+    assert rel_err(hid_g.grad.cpu(), hid_ref.grad) < 1e-3
+    named = dict(model.named_parameters())
+    gmax = max(float(v.grad.abs().max()) for v in leaves.values() if v.grad is not None)
+    for k, v in leaves.items():
+        mine = named[k[len("backend."):]].grad
+        if v.grad is None or float(v.grad.abs().max()) == 0.0:
+            assert mine is None or float(mine.abs().max()) < 1e-6 * max(gmax, 1.0), k
+            continue
+        assert mine is not None, k
+        err = (mine.cpu() - v.grad).abs().max().item() / max(float(v.grad.abs().max()), 1e-5 * gmax)
+        assert err < 3e-3, (k, err)
+    # BatchNorm running statistics follow torch's momentum update for layers whose output is used
+    x = None
+    taps = {}
+    O.gwnet_forward(full, history, hidden_last, adj, train=True, taps=taps)
+    z0 = taps["z0"]
+    assert (model.bn[0].running_mean.cpu() - 0.1 * z0.mean((0, 2, 3))).abs().max().item() < 1e-5
+    assert (model.bn[0].running_var.cpu() - (0.9 + 0.1 * z0.transpose(0, 1).reshape(32, -1).var(1, unbiased=True))).abs().max().item() < 1e-4
+
+
+def test_gwnet_eval_mode_and_dropout():
+    from conftest import gw_args
+    from step.step_arch.graphwavenet import GraphWaveNet
+    N, B = 31, 4
+    sd, history, hidden_last, adj = _gw_case(N, B, 3)
+    buffers = {k: v.clone() for k, v in O.bn_buffers("PEMS08").items() if k.startswith("backend.")}
+    g = torch.Generator().manual_seed(9)
+    for k in buffers:
+        if k.endswith("running_mean"):
+            buffers[k] = torch.randn(32, generator=g) * 0.1
+        if k.endswith("running_var"):
+            buffers[k] = torch.rand(32, generator=g) + 0.5
+    full = dict(sd); full.update(buffers)
+    ref = O.gwnet_forward(full, history, hidden_last, adj, train=False)
+    model = GraphWaveNet(**gw_args(N))
+    model.load_state_dict({k[len("backend."):]: v for k, v in full.items()}, strict=True)
+    model = model.to(DEV).eval()
+    with torch.no_grad():
+        out = model(history.to(DEV), hidden_last.to(DEV), adj.to(DEV))
+    assert (out.cpu() - ref).abs().max().item() < 2e-4
+    # train mode with dropout: runs, is reproducible under the same torch seed, differs from p = 0
+    model.train()
+    torch.manual_seed(11); model._calls = 0
+    a = model(history.to(DEV), hidden_last.to(DEV), adj.to(DEV)).detach()
+    torch.manual_seed(11); model._calls = 0
+    b = model(history.to(DEV), hidden_last.to(DEV), adj.to(DEV)).detach()
+    assert torch.equal(a, b)
+    model.dropout = 0.0
+    c = model(history.to(DEV), hidden_last.to(DEV), adj.to(DEV)).detach()
+    assert not torch.equal(a, c)
+    assert torch.isfinite(a).all()

@@ -1,0 +1,101 @@
+"""GPU parity of the whole STEP module (our drop-in classes over the C ABI) against the committed outputs of
+the reference (tests/golden), plus full-size property checks at the BASELINE configuration."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, build_step_model
+from oracle import step_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def unpack(bits, n):
+    return torch.from_numpy(np.unpackbits(bits.numpy(), axis=1)[:, : n * n].astype(np.float32)).reshape(-1, n, n)
+
+
+@pytest.mark.parametrize("name", ["step_PEMS08_b1.pt", "step_METR-LA_b2.pt"])
+def test_step_forward_backward_matches_reference_golden(name, tmp_path):
+    from step.step_loss import step_loss
+    fx = torch.load(os.path.join(GOLDEN, name), weights_only=False)
+    ds, n = fx["dataset"], O.NUM_NODES[fx["dataset"]]
+    model, _, _ = build_step_model(tmp_path, ds, fx["seed"], real_ckpt=fx["real_ckpt"])
+    model = model.to(DEV).train()
+    model.tsformer.dropout_p = 0.0          # parity suite B (SURVEY Appx D.4): train() everywhere, dropout off
+    model.backend.dropout = 0.0
+    history, long_history, future, uniform = O.synthetic_batch(ds, fx["batch"], fx["patches"], fx["seed"])
+    model.discrete_graph_learning.gumbel_uniform = uniform.to(DEV)
+    y_hat, theta, adj_knn, coeff = model(history_data=history.to(DEV), long_history_data=long_history.to(DEV),
+                                         future_data=None, batch_seen=0, epoch=1)
+    assert list(y_hat.shape) == [fx["batch"], 12, n, 1] and coeff == 1.0
+    # --- forward parity (BASELINE.json: fp32 MAE <= 1e-4 vs the reference)
+    assert (y_hat.detach().cpu() - fx["y_hat"]).abs().mean().item() <= 1e-4
+    assert (theta[0].detach().cpu() - fx["theta0"]).abs().max().item() < 1e-5
+    ref_knn = unpack(fx["adj_knn_bits"], n)
+    assert int((adj_knn.cpu() != ref_knn).sum()) <= 8          # threshold ties are implementation-defined
+    with torch.no_grad():
+        bern, hidden, _, sampled = model.discrete_graph_learning(long_history.to(DEV), model.tsformer)
+    assert (hidden[:, :, -1, :].cpu() - fx["hidden_last"]).abs().max().item() < 2e-4
+    assert (hidden[:, ::23, ::17, :].cpu() - fx["hidden_slice"]).abs().max().item() < 2e-4
+    assert abs(hidden.double().sum().item() - fx["hidden_sum"]) / fx["hidden_abs_sum"] < 1e-5
+    assert (bern[0].cpu() - fx["bernoulli_unnorm0"]).abs().max().item() < 1e-4
+    assert int((sampled.cpu() != unpack(fx["sampled_adj_bits"], n)).sum()) <= 2
+    # --- loss + gradients (use the reference's kNN graph so that tie-breaks do not leak into the loss)
+    loss = step_loss(y_hat[..., [0]], future.to(DEV)[..., [0]], theta, ref_knn.to(DEV), coeff, null_val=0.0)
+    assert abs(loss.item() - fx["loss"].item()) < 5e-5
+    loss.backward()
+    named = dict(model.named_parameters())
+    for k, g in fx["grads"].items():
+        mine = named[k].grad
+        assert mine is not None, k
+        got = mine.reshape(-1)[g["idx"].to(DEV)].cpu()
+        scale = max(g["absmax"], 1e-6)
+        assert (got - g["val"]).abs().max().item() / scale < 1e-2, k
+        assert abs(float(mine.double().norm()) - g["norm"]) / max(g["norm"], 1e-9) < 1e-2 or g["absmax"] < 1e-8, k
+    for k in fx["no_grad"]:
+        assert named[k].grad is None or float(named[k].grad.abs().max()) == 0.0, k
+
+
+def test_full_size_properties_metr_la(tmp_path):
+    """BASELINE configs[1] shape (N=207, B=32, P=168): size-independent properties of the path."""
+    model, _, _ = build_step_model(tmp_path, "METR-LA", 0, real_ckpt=True)
+    model = model.to(DEV)
+    B, n = 32, 207
+    history, long_history, future, _ = O.synthetic_batch("METR-LA", B, 168, 3)
+    history, long_history = history.to(DEV), long_history.to(DEV)
+    model.eval()
+    with torch.no_grad():
+        y32, theta, knn, _ = model(history_data=history, long_history_data=long_history, future_data=None, batch_seen=0, epoch=1)
+        bern, hidden, knn2, sampled = model.discrete_graph_learning(long_history, model.tsformer)
+    assert torch.isfinite(y32).all() and torch.isfinite(hidden).all()
+    # adjacency properties
+    assert set(sampled.unique().tolist()) <= {0.0, 1.0} and sampled.diagonal(dim1=1, dim2=2).sum().item() == 0
+    assert set(knn.unique().tolist()) <= {0.0, 1.0} and knn.diagonal(dim1=1, dim2=2).sum().item() == 0
+    ones = knn.sum((1, 2))
+    assert bool((ones <= 10 * n).all()) and bool((ones >= 10 * n - n).all())
+    assert torch.equal(knn, knn2)                       # deterministic
+    # eval mode: samples are independent -> a sub-batch reproduces the same rows bit for bit in the encoder
+    with torch.no_grad():
+        h4 = model.tsformer(long_history[:4, :, :, [0]])
+    assert torch.equal(h4, hidden[:4])
+    # encoder is permutation-equivariant over nodes
+    perm = torch.randperm(n, device=DEV)
+    with torch.no_grad():
+        hp = model.tsformer(long_history[:2, :, perm][..., [0]])
+    assert torch.equal(hp, hidden[:2, perm])
+    # train mode runs fwd+bwd at full size and produces finite grads for every trainable parameter that the reference trains
+    from step.step_loss import step_loss
+    model.train()
+    y, theta, knn, coeff = model(history_data=history, long_history_data=long_history, future_data=None, batch_seen=0, epoch=1)
+    loss = step_loss(y[..., [0]], future.to(DEV)[..., [0]], theta, knn, coeff, null_val=0.0)
+    loss.backward()
+    assert torch.isfinite(loss)
+    dead = ("residual_convs", "bn.7", "gconv.7", "fc_mean")
+    for k, p in model.named_parameters():
+        if k.startswith("tsformer.") or any(d in k for d in dead):
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+        else:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), k

@@ -1,0 +1,49 @@
+"""CPU: host-side mirror of the reference interface - constructor signatures, state-dict contract,
+and the no-fallback rule (a CPU tensor must raise, never silently run in PyTorch)."""
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN, build_step_model
+from oracle import step_oracle as O
+
+
+def expected_keys(dataset):
+    keys = set(O.synthetic_trainable_params(dataset).keys()) | set(O.bn_buffers(dataset).keys())
+    keys |= {"tsformer." + k for k in O.synthetic_tsformer_params().keys()}
+    return keys
+
+
+def test_state_dict_contract_and_ckpt_load(tmp_path):
+    model, full, _ = build_step_model(tmp_path, "PEMS08")
+    assert set(model.state_dict().keys()) == expected_keys("PEMS08")
+    for k, v in model.state_dict().items():
+        assert tuple(v.shape) == tuple(full[k].shape), k
+    # frozen TSFormer, trainable rest (reference step.py:34-35)
+    assert not any(p.requires_grad for p in model.tsformer.parameters())
+    assert all(p.requires_grad for p in model.backend.parameters())
+    # the real METR-LA checkpoint's 72 keys load strictly
+    real = torch.load(os.path.join(GOLDEN, "tsformer_METR-LA_state.pt"))
+    assert len(real) == 72
+    model.tsformer.load_state_dict(real, strict=True)
+
+
+def test_no_cpu_fallback(tmp_path):
+    from step_b200.lib import StepB200Error
+    model, _, _ = build_step_model(tmp_path, "PEMS08")
+    history, long_history, _, _ = O.synthetic_batch("PEMS08", 1, 2, 0)
+    with pytest.raises(StepB200Error):
+        model(history_data=history, long_history_data=long_history, future_data=None, batch_seen=0, epoch=1)
+
+
+def test_step_loss_matches_oracle():
+    from step.step_loss import step_loss
+    g = torch.Generator().manual_seed(0)
+    pred, real = torch.randn(3, 12, 11, 1, generator=g), torch.randn(3, 12, 11, 1, generator=g)
+    real[0, :, 3] = 0.0
+    theta = torch.rand(11, 11, generator=g).unsqueeze(0).expand(3, 11, 11)
+    prior = (torch.rand(3, 11, 11, generator=g) > 0.9).float()
+    a = step_loss(pred, real, theta, prior, 0.5, null_val=0.0)
+    b = O.step_loss(pred, real, theta, prior, 0.5, null_val=0.0)
+    assert abs(a.item() - b.item()) < 1e-6
