@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="per-GPU batch (default: the config's 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-resident", action="store_true", help="profiling aid: run only the device-resident loop")
     ap.add_argument("--no-dropout", action="store_true", help="parity-style run (all dropout off); not the headline")
     ap.add_argument("--chunk-seqs", type=int, default=int(os.environ.get("STEP_B200_TS_CHUNK", "0")))
     return ap.parse_args()
@@ -114,7 +115,9 @@ def cpu_reference_run(steps, warmup, batch, dropout=True):
     """The reference algorithm (oracle/step_oracle.py restatement of the reference's torch modules) on the
     host cores, all threads, same config except a bounded per-step batch.  Returns (samples/s, info)."""
     from oracle import step_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    # torch CPU ops on these shapes slow down badly past ~16-32 threads (measured on the 128-thread GPU host:
+    # 83 s/step with 128 threads); use the best-performing setting and report it as `cores`
+    torch.set_num_threads(min(os.cpu_count() or 1, int(os.environ.get("STEP_B200_CPU_THREADS", "32"))))
     params = O.synthetic_trainable_params(DATASET, 0)
     sd = dict(params)
     sd.update(O.bn_buffers(DATASET))
@@ -247,6 +250,11 @@ def main():
     k0 = ops.launch_counter["kernels"]
     ms_res = timed(lambda i: train_step(*resident[i % 2]), args.steps)
     launches = ops.launch_counter["kernels"] - k0
+    if args.only_resident:
+        if rank == 0:
+            sampler.stop()
+            print(json.dumps({"only_resident": True, "ms_per_step": ms_res / args.steps, "gpu_launches": launches}))
+        return
 
     # ---- end-to-end: pinned host batch -> H2D copies -> step -> loss read back, all inside the timed region ----
     losses = []

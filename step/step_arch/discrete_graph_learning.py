@@ -60,14 +60,34 @@ class DiscreteGraphLearning(nn.Module):
         self._calls = 0
         self._feats_dev = None
 
+    @staticmethod
+    def _batch_norm(x, bn, training):
+        """BatchNorm1d semantics (batch statistics + running-stat update in train(), running statistics in
+        eval()) written as plain reductions: cuDNN's spatial-BN kernels take ~20 ms on the [N, C, 24k] trunk
+        activations, these take <1 ms."""
+        dims = (0, 2) if x.dim() == 3 else (0,)
+        shape = (1, -1, 1) if x.dim() == 3 else (1, -1)
+        if training:
+            var, mean = torch.var_mean(x, dim=dims, unbiased=False)
+            with torch.no_grad():
+                n = x.numel() // x.shape[1]
+                bn.running_mean.mul_(1 - bn.momentum).add_(mean, alpha=bn.momentum)
+                bn.running_var.mul_(1 - bn.momentum).add_(var, alpha=bn.momentum * n / max(n - 1, 1))
+                bn.num_batches_tracked += 1
+        else:
+            mean, var = bn.running_mean, bn.running_var
+        scale = bn.weight * torch.rsqrt(var + bn.eps)
+        return x * scale.view(shape) + (bn.bias - mean * scale).view(shape)
+
     def _global_feature(self, device):
         """Batch-invariant node embedding, reference :131-135.  [N, 100]."""
         if self._feats_dev is None or self._feats_dev.device != device:
             self._feats_dev = self.node_feats.to(device).t().contiguous().unsqueeze(1)     # [N,1,L], uploaded once
-        x = self.bn1(F.relu(self.conv1(self._feats_dev)))
-        x = self.bn2(F.relu(self.conv2(x)))
+        t = self.training
+        x = self._batch_norm(F.relu(self.conv1(self._feats_dev)), self.bn1, t)
+        x = self._batch_norm(F.relu(self.conv2(x)), self.bn2, t)
         x = F.relu(self.fc(x.view(self.num_nodes, -1)))
-        return self.bn3(x)
+        return self._batch_norm(x, self.bn3, t)
 
     def get_k_nn_neighbor(self, data, k=11 * 207, metric="cosine"):
         if metric != "cosine":

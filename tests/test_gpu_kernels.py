@@ -246,8 +246,14 @@ def test_gwnet_forward_backward_matches_oracle(N, B):
     assert rel_err(hid_g.grad.cpu(), hid_ref.grad) < 1e-3
     named = dict(model.named_parameters())
     gmax = max(float(v.grad.abs().max()) for v in leaves.values() if v.grad is not None)
+    import re
     for k, v in leaves.items():
         mine = named[k[len("backend."):]].grad
+        if re.fullmatch(r"backend\.gconv\.[0-6]\.mlp\.mlp\.bias", k):
+            # a bias in front of a train-mode BatchNorm has an exactly-zero analytic gradient: both sides are
+            # cancellation noise, so bound it instead of comparing it
+            assert float(mine.abs().max()) < 1e-4 * gmax and float(v.grad.abs().max()) < 1e-4 * gmax, k
+            continue
         if v.grad is None or float(v.grad.abs().max()) == 0.0:
             assert mine is None or float(mine.abs().max()) < 1e-6 * max(gmax, 1.0), k
             continue
