@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only-resident", action="store_true", help="profiling aid: run only the device-resident loop")
     ap.add_argument("--no-dropout", action="store_true", help="parity-style run (all dropout off); not the headline")
+    ap.add_argument("--precision", default=os.environ.get("STEP_B200_PRECISION", "bf16"), choices=["bf16", "fp32"],
+                    help="TSFormer encoder kernels: bf16 tcgen05 tensor cores (default, BASELINE config) or fp32 CUDA cores")
     ap.add_argument("--chunk-seqs", type=int, default=int(os.environ.get("STEP_B200_TS_CHUNK", "0")))
     return ap.parse_args()
 
@@ -194,6 +196,7 @@ def main():
     model.load_state_dict(full, strict=False)
     model = model.to(dev).train()                 # the reference trains with the frozen TSFormer left in train()
     model.tsformer.chunk_seqs = args.chunk_seqs
+    model.tsformer.precision = args.precision
     if args.no_dropout:
         model.tsformer.dropout_p = 0.0
         model.backend.dropout = 0.0
@@ -267,26 +270,33 @@ def main():
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline of the dominant kernel: the encoder's token GEMMs (hand-written gemm_tn_kernel) ----
+    # ---- roofline of the dominant kernel group, timed alone with CUDA events on the launching stream ----
     pk = peaks()
     tokens = B * NODES * PATCHES
-    a = torch.randn(tokens, 96, device=dev)
-    w = torch.randn(288, 96, device=dev) * 0.1
-    bias = torch.zeros(288, device=dev)
+    enc_flops = B * NODES * (4 * (PATCHES * (2 * 96 * 288 + 2 * 96 * 96 + 4 * 96 * 384) + 4 * 4 * PATCHES * PATCHES * 24)
+                             + 2 * PATCHES * 12 * 96)
+    lh = resident[0][1]
+
+    def enc_once():
+        with torch.no_grad():
+            return model.tsformer(lh[..., [0]])
     for _ in range(3):
-        ops.linear(a, w, bias)
+        enc_once()
     reps = 10
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        ops.linear(a, w, bias)
+        enc_once()
     e1.record()
     torch.cuda.synchronize(dev)
-    gemm_ms = e0.elapsed_time(e1) / reps
-    gemm_tflops = 2.0 * tokens * 96 * 288 / (gemm_ms * 1e-3) / 1e12
-    del a, w, bias
-
+    enc_ms = e0.elapsed_time(e1) / reps
+    enc_tflops = enc_flops / (enc_ms * 1e-3) / 1e12
+    if args.precision == "bf16":
+        roof_name = ("TSFormer encoder, 21 launches: tc_embed + 4 x (tc_linear[QKV] + tc_attn + tc_linear[out+LN1] + "
+                     "tc_linear[FFN1] + tc_linear[FFN2+LN2]) on tcgen05, %d tokens" % tokens)
+    else:
+        roof_name = "TSFormer encoder, fp32 CUDA-core kernels (gemm_tn_kernel / attn_fwd_kernel), %d tokens" % tokens
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -298,20 +308,22 @@ def main():
     out = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "fp32", "data": "synthetic",
+        "dtype": "bf16" if args.precision == "bf16" else "fp32", "data": "synthetic",
         "config": {"workload": "STEP_METR-LA fwd+loss+bwd, N=207, per-GPU batch %d, P=168 (2016-step history), 12->12" % B,
                    "parallelism": "dp%d (batch-parallel, NCCL grad all-reduce)" % world if world > 1 else "single GPU",
                    "dropout": "off" if args.no_dropout else "live (TSFormer 0.1 in train(), gcn 0.3) as the reference trains",
                    "l2": "inputs > L2: each step streams a fresh 160 MB long-history batch and ~1 GB of activations",
+                   "precision": ("TSFormer encoder bf16 operands / fp32 accumulate on tcgen05; graph learning + GWNet fp32"
+                                 if args.precision == "bf16" else "fp32 everywhere"),
                    "ts_chunk_seqs": args.chunk_seqs, "weights": "real TSFormer_METR-LA encoder, seeded random GWNet/DGL"},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "gemm_tn_kernel (TSFormer QKV projection, [%d,96]x[96,288], fp32 CUDA-core path)" % tokens,
-                     "bound": "tensor", "achieved": gemm_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": gemm_tflops / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " (burst, kernel timed alone)",
-                     "ms": gemm_ms},
+        "roofline": {"kernel": roof_name, "bound": "tensor", "achieved": enc_tflops, "peak": pk["bf16_tflops"],
+                     "unit": "TFLOP/s", "frac": enc_tflops / pk["bf16_tflops"], "traffic": None,
+                     "peak_source": pk["source"] + " (burst cuBLAS bf16, kernels timed alone)", "ms": enc_ms,
+                     "useful_flops": enc_flops},
         "loss": losses[-1] if losses else None,
     }
     if not args.no_cpu_baseline:

@@ -112,6 +112,47 @@ int step_ts_encoder_fwd(const float *series, long long sB, long long sT, long lo
                         void *workspace, size_t workspace_bytes, int chunk_seqs,
                         float drop_p, unsigned long long seed, void *stream);
 
+
+/* ------------------------------------------------------------------------ *
+ * TSFormer encoder, bf16 tensor-core path (tcgen05.mma + TMEM + TMA bulk copies)
+ * Same reference spans as the fp32 path above.  Activations travel between kernels as
+ * "tile images": a [T, K] bf16 matrix stored as [T/128][K/8][128 rows][8] (the UMMA K-major
+ * no-swizzle canonical layout of a 128-row tile), weights as [K/8][Nout][8].
+ * ------------------------------------------------------------------------ */
+typedef struct step_ts_layer_images {
+  const void *in_proj;  /* [12][288][8] bf16 */
+  const void *out_proj; /* [12][96][8]  */
+  const void *lin1;     /* [12][384][8] */
+  const void *lin2;     /* [48][96][8]  */
+} step_ts_layer_images;
+
+/* fp32 W [Nout][K] -> bf16 weight image [K/8][Nout][8] (Nout*K*2 bytes). */
+int step_tc_pack_weight(const float *w, int Nout, int K, void *img, void *stream);
+/* row-major fp32 [T][K] <-> activation tile image (ceil(T/128)*K*256 bytes); test / debug helpers. */
+int step_tc_rows_to_image(const float *x, long long T, int K, void *img, void *stream);
+int step_tc_image_to_rows(const void *img, long long T, int K, float *x, void *stream);
+/* out = epilogue(A W^T + bias) on tcgen05.  K in {96, 384}, Nout in {96, 192, 288, 384}.
+ *   mode 0: out_f32 [T][Nout] row-major;  mode 1: ReLU -> out_img (K' = Nout);
+ *   mode 2 (Nout == 96): LayerNorm(residual image + .) -> out_img and/or out_f32 [T][96]. */
+int step_tc_linear(const void *a_img, const void *w_img, const float *bias, long long T, int K, int Nout, int mode,
+                   const void *res_img, const float *ln_w, const float *ln_b, void *out_img, float *out_f32, void *stream);
+/* Bytes of the per-(sequence, head) attention operand images: which = 0 -> Q, 1 -> K (== V). */
+size_t step_tc_attn_image_bytes(int S, int P, int which);
+/* QKV projection of an X image [S*P, 96] straight into the attention operand images (Q pre-scaled by
+ * log2(e)/sqrt(24)). */
+int step_tc_qkv(const void *x_img, const void *w_img, const float *bias, int S, int P, void *q_img, void *k_img, void *v_img,
+                void *stream);
+/* softmax(Q K^T) V per (sequence, head) on tcgen05 -> O tile image [S*P, 96].  P <= 176. */
+int step_tc_attention(const void *q_img, const void *k_img, const void *v_img, void *o_img, int S, int P, float drop_p,
+                      unsigned long long seed, void *stream);
+size_t step_ts_encoder_bf16_workspace_bytes(int B, int N, int P);
+/* Whole encoder in bf16: series -> hidden [B,N,P,96] fp32 (same contract as step_ts_encoder_fwd). */
+int step_ts_encoder_fwd_bf16(const float *series, long long sB, long long sT, long long sN, int B, int N, int P,
+                             const float *patch_w, const float *patch_b, const float *pos,
+                             const step_ts_layer_weights *h_layers, const step_ts_layer_images *h_images, int n_layers,
+                             const float *final_norm_w, const float *final_norm_b, float *hidden, void *workspace,
+                             size_t workspace_bytes, float drop_p, unsigned long long seed, void *stream);
+
 /* ------------------------------------------------------------------------ *
  * kNN prior graph: cosine-similarity Gram matrix + global top-k select
  *   step/step_arch/similarity.py:6-16,

@@ -1,0 +1,752 @@
+// TSFormer encoder on the 5th-generation tensor cores: tcgen05.mma with TMEM accumulators, operands
+// staged by 1-D TMA bulk copies of UMMA-canonical "tile images", warp-specialised (TMA producer /
+// single-thread MMA issuer / epilogue or softmax warps) and mbarrier-pipelined.  bf16 operands, fp32
+// accumulation, fp32 LayerNorm / softmax statistics.
+//
+// Reference semantics are those of csrc/ts_encoder.cu (same citations); this file is the
+// "bf16 precision" implementation of SURVEY.md section 8 rows T1-T4.
+//
+// Inter-kernel activation format ("tile image", see tc_common.cuh): a [T, K] activation is stored as
+// [T/128 tiles][K/8 chunks][128 rows][8] bf16.  Producers write it with perfectly coalesced 16-byte
+// stores (lane = row), consumers fetch a whole 128 x 96 K-slice (24 KB) with ONE cp.async.bulk.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace stepk {
+using namespace tc;
+
+constexpr int TCL_THREADS = 320;                 // warp 0: TMA, warp 1: MMA, warps 2-5 / 6-9: two epilogue groups
+constexpr int TCL_STAGES = 4;
+constexpr uint32_t SLICE_BYTES = 12 * 2048;      // 128 rows x 96 K, bf16
+constexpr int HD = 24;                           // head dim
+
+enum { TCM_F32 = 0, TCM_RELU_IMG = 1, TCM_RESLN = 2, TCM_QKV = 3 };
+
+// Dropout masks of the tensor-core path: 8 keep/drop decisions (16-bit thresholds) from four 32-bit
+// counter hashes (lowbias32 finaliser: 2 multiplies + 3 xor-shifts each).  ~3x cheaper than Philox4x32-10,
+// which matters because TSFormer draws 3.0 G attention-probability masks per step; still counter-based,
+// so a mask is a pure function of (seed, site, element index).
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ void drop8(float *v, uint64_t idx8, uint32_t thr16, float scale, uint64_t key) {
+  const uint32_t salt = (uint32_t)key ^ ((uint32_t)(key >> 32) * 0x9E3779B9u) ^ ((uint32_t)(idx8 >> 30) * 0x85EBCA6Bu);
+  const uint32_t c = (uint32_t)idx8 << 2;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t w = hash32((c + i) ^ salt);
+    v[2 * i] = ((w & 0xFFFFu) >= thr16) ? v[2 * i] * scale : 0.f;
+    v[2 * i + 1] = ((w >> 16) >= thr16) ? v[2 * i + 1] * scale : 0.f;
+  }
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ===========================================================================
+// weight packing: fp32 W [Nout][K] -> bf16 image [K/8][Nout][8]
+// ===========================================================================
+__global__ void tc_pack_weight_kernel(const float *__restrict__ w, int Nout, int K, uint4 *__restrict__ img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte unit
+  if (idx >= Nout * (K / 8)) return;
+  const int c = idx / Nout, n = idx % Nout;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = w[(size_t)n * K + c * 8 + i];
+  img[idx] = pack8_bf16(v);
+}
+
+// row-major fp32 [T][K] <-> tile image (test / debug helpers)
+__global__ void tc_rows_to_image_kernel(const float *__restrict__ x, long long T, int K, uint4 *__restrict__ img) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int KC = K / 8;
+  const long long MT = (T + 127) / 128;
+  if (idx >= MT * KC * 128) return;
+  const int r = (int)(idx % 128);
+  const int c = (int)((idx / 128) % KC);
+  const long long mt = idx / (128LL * KC);
+  const long long t = mt * 128 + r;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = (t < T) ? x[t * K + c * 8 + i] : 0.f;
+  img[idx] = pack8_bf16(v);
+}
+__global__ void tc_image_to_rows_kernel(const uint4 *__restrict__ img, long long T, int K, float *__restrict__ x) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int KC = K / 8;
+  const long long MT = (T + 127) / 128;
+  if (idx >= MT * KC * 128) return;
+  const int r = (int)(idx % 128);
+  const int c = (int)((idx / 128) % KC);
+  const long long mt = idx / (128LL * KC);
+  const long long t = mt * 128 + r;
+  if (t >= T) return;
+  float v[8];
+  unpack8_bf16(img[idx], v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[t * K + c * 8 + i] = v[i];
+}
+
+// ===========================================================================
+// patch embedding -> X tile image.  block = (32 patches, 16 nodes, b): coalesced node-major reads of the
+// series through smem, coalesced row-major image writes.
+// ===========================================================================
+__global__ void __launch_bounds__(256) tc_embed_kernel(const float *__restrict__ series, long long sB, long long sT,
+                                                       long long sN, int N, int P, const float *__restrict__ w,
+                                                       const float *__restrict__ bias, const float *__restrict__ pos,
+                                                       uint4 *__restrict__ img, uint32_t thr16, float dscale, uint64_t key) {
+  __shared__ float sw[96 * 12];
+  __shared__ float sb[96];
+  __shared__ float sv[16][32 * 12 + 1];   // [node][time]
+  const int b = blockIdx.z, n0 = blockIdx.y * 16, p0 = blockIdx.x * 32, tid = threadIdx.x;
+  for (int i = tid; i < 96 * 12; i += 256) sw[i] = w[i];
+  if (tid < 96) sb[tid] = bias[tid];
+  const int np = min(32, P - p0);
+  for (int i = tid; i < 16 * np * 12; i += 256) {
+    const int nn = i & 15, tt = i >> 4;
+    const int n = n0 + nn;
+    sv[nn][tt] = (n < N) ? series[b * sB + (long long)(p0 * 12 + tt) * sT + n * sN] : 0.f;
+  }
+  __syncthreads();
+  const int pp = tid & 31, ng = tid >> 5;
+  if (pp >= np) return;
+  const int p = p0 + pp;
+  const float scale = sqrtf(96.f);
+  for (int k = 0; k < 2; ++k) {
+    const int nn = ng * 2 + k, n = n0 + nn;
+    if (n >= N) break;
+    float x[12];
+#pragma unroll
+    for (int t = 0; t < 12; ++t) x[t] = sv[nn][pp * 12 + t];
+    const long long token = ((long long)(b * N + n)) * P + p;
+    const long long mt = token >> 7;
+    const int r = (int)(token & 127);
+#pragma unroll 1
+    for (int c = 0; c < 12; ++c) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int f = c * 8 + j;
+        float acc = sb[f] + pos[(size_t)p * 96 + f];
+#pragma unroll
+        for (int t = 0; t < 12; ++t) acc = fmaf(sw[f * 12 + t], x[t], acc);
+        v[j] = acc;
+      }
+      if (thr16) drop8(v, (uint64_t)token * 12 + c, thr16, dscale, key);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= scale;
+      img[(mt * 12 + c) * 128 + r] = pack8_bf16(v);
+    }
+  }
+}
+
+// ===========================================================================
+// token GEMM on tcgen05:  out = epilogue( A[T,K] W^T + b )
+// ===========================================================================
+struct TcLinearArgs {
+  const uint8_t *A;        // tile image [MT][K/8][128][8]
+  const uint8_t *W;        // weight image [K/8][Nout][8]
+  const float *bias;       // [Nout]
+  int MT, K, Nout, mode;
+  long long T;             // valid rows
+  const uint8_t *res;      // residual tile image [MT][12][128][8] (TCM_RESLN)
+  const float *ln_w, *ln_b, *ln2_w, *ln2_b;
+  uint8_t *out_img;        // TCM_RELU_IMG: [MT][Nout/8][128][8]; TCM_RESLN: [MT][12][128][8] (may be null)
+  float *out_f32;          // TCM_F32: [T][Nout]; TCM_RESLN: [T][96] (may be null)
+  uint8_t *q_img, *k_img, *v_img;  // TCM_QKV
+  int P, Pk, RT;
+  float qscale;
+  uint32_t thr16; float dscale; uint64_t key;
+};
+
+__device__ __forceinline__ void layer_norm96(float *v, const float *w, const float *b) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 96; ++c) s += v[c];
+  const float mean = s * (1.f / 96.f);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < 96; ++c) { const float d = v[c] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(q * (1.f / 96.f) + 1e-5f);
+#pragma unroll
+  for (int c = 0; c < 96; ++c) v[c] = (v[c] - mean) * rstd * __ldg(w + c) + __ldg(b + c);
+}
+
+__global__ void __launch_bounds__(TCL_THREADS, 1) tc_linear_kernel(TcLinearArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int KS = a.K / 96, NB = a.Nout / 96;
+  const uint32_t wbytes = (uint32_t)a.K * a.Nout * 2;
+  uint8_t *sW = smem;
+  uint8_t *sA = smem + wbytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sA + TCL_STAGES * SLICE_BYTES);
+  uint64_t *full = bars, *empty = bars + TCL_STAGES, *tfull = bars + 2 * TCL_STAGES, *tempty = tfull + 4, *wbar = tempty + 4;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wbar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TCL_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    mbar_init(wbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      mbar_expect_tx(wbar, wbytes);
+      tma_bulk_g2s(sW, a.W, wbytes, wbar);
+      uint32_t n = 0;
+      for (int mt = blockIdx.x; mt < a.MT; mt += gridDim.x) {
+        for (int ks = 0; ks < KS; ++ks, ++n) {
+          const uint32_t s = n % TCL_STAGES, ph = (n / TCL_STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], SLICE_BYTES);
+          tma_bulk_g2s(sA + s * SLICE_BYTES, a.A + ((size_t)mt * KS + ks) * SLICE_BYTES, SLICE_BYTES, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (one thread) ------------------------------
+    if (lane == 0) {
+      mbar_wait(wbar, 0);
+      const uint32_t idesc = umma_idesc_bf16(128, 96, 0, 0);
+      const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW);
+      const uint32_t w_lbo = (uint32_t)a.Nout * 16;
+      uint32_t n = 0, it = 0;
+      for (int mt = blockIdx.x; mt < a.MT; mt += gridDim.x, ++it) {
+        for (int ks = 0; ks < KS; ++ks, ++n) {
+          const uint32_t s = n % TCL_STAGES, ph = (n / TCL_STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          for (int nb = 0; nb < NB; ++nb) {
+            const uint32_t jj = it * NB + nb, slot = jj & 3, use = jj >> 2;
+            if (ks == 0) {
+              mbar_wait(&tempty[slot], (use & 1) ^ 1);
+              tc_fence_after();
+            }
+#pragma unroll
+            for (int kk = 0; kk < 6; ++kk) {
+              const uint64_t adesc = umma_desc(sA_addr + s * SLICE_BYTES + kk * 2 * 2048, 2048, 128);
+              const uint32_t cidx = ks * 12 + kk * 2;
+              const uint64_t bdesc = umma_desc(sW_addr + cidx * w_lbo + nb * 96 * 16, w_lbo, 128);
+              umma_bf16(tmem + slot * 96, adesc, bdesc, idesc, (ks | kk) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[s]);
+          if (ks == KS - 1) {
+            for (int nb = 0; nb < NB; ++nb) umma_commit(&tfull[(it * NB + nb) & 3]);
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue warps ------------------------------
+    // two groups of four warps take alternate [128 x 96] sub-tiles (accumulator slots 0,2 / 1,3), so that one
+    // group's TMEM loads / LayerNorm / stores overlap the other's
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int grp = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    uint32_t it = 0;
+    for (int mt = blockIdx.x; mt < a.MT; mt += gridDim.x, ++it) {
+      const long long token = (long long)mt * 128 + row;
+      const bool valid = token < a.T;
+      for (int nb = 0; nb < NB; ++nb) {
+        const uint32_t jj = it * NB + nb, slot = jj & 3, use = jj >> 2;
+        if ((int)(jj & 1) != grp) continue;
+        mbar_wait(&tfull[slot], use & 1);
+        tc_fence_after();
+        float v[96];
+        {
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + slot * 96;
+          float t0[32];
+          tmem_ld32(taddr, t0);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] = t0[c];
+          tmem_ld32(taddr + 32, t0);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[32 + c] = t0[c];
+          tmem_ld32(taddr + 64, t0);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[64 + c] = t0[c];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[slot]);
+
+        const float *bias = a.bias + nb * 96;
+#pragma unroll
+        for (int c = 0; c < 96; ++c) v[c] += __ldg(bias + c);
+
+        if (a.mode == TCM_F32) {
+          if (valid) {
+            float *o = a.out_f32 + token * a.Nout + nb * 96;
+#pragma unroll
+            for (int c = 0; c < 96; c += 4) *reinterpret_cast<float4 *>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+          }
+        } else if (a.mode == TCM_RELU_IMG) {
+          uint4 *o = reinterpret_cast<uint4 *>(a.out_img) + ((size_t)mt * (a.Nout / 8) + nb * 12) * 128 + row;
+#pragma unroll
+          for (int cc = 0; cc < 12; ++cc) {
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = fmaxf(v[cc * 8 + j], 0.f);
+            if (a.thr16) drop8(x, ((uint64_t)token * a.Nout + nb * 96) / 8 + cc, a.thr16, a.dscale, a.key);
+            o[cc * 128] = pack8_bf16(x);
+          }
+        } else if (a.mode == TCM_RESLN) {
+          const uint4 *res = reinterpret_cast<const uint4 *>(a.res) + ((size_t)mt * 12) * 128 + row;
+#pragma unroll
+          for (int cc = 0; cc < 12; ++cc) {
+            if (a.thr16) drop8(&v[cc * 8], (uint64_t)token * 12 + cc, a.thr16, a.dscale, a.key);
+            float r8[8];
+            unpack8_bf16(res[cc * 128], r8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[cc * 8 + j] += r8[j];
+          }
+          layer_norm96(v, a.ln_w, a.ln_b);
+          if (a.ln2_w != nullptr) layer_norm96(v, a.ln2_w, a.ln2_b);
+          if (a.out_img != nullptr) {
+            uint4 *o = reinterpret_cast<uint4 *>(a.out_img) + ((size_t)mt * 12) * 128 + row;
+#pragma unroll
+            for (int cc = 0; cc < 12; ++cc) o[cc * 128] = pack8_bf16(&v[cc * 8]);
+          }
+          if (a.out_f32 != nullptr && valid) {
+            float *o = a.out_f32 + token * 96;
+#pragma unroll
+            for (int c = 0; c < 96; c += 4) *reinterpret_cast<float4 *>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+          }
+        } else {  // TCM_QKV: nb 0 -> Q (pre-scaled into the log2 softmax domain), 1 -> K, 2 -> V
+          if (valid) {
+            const long long s = token / a.P;
+            const int p = (int)(token - s * a.P);
+            if (nb == 0) {
+              const int rt = p >> 7, r = p & 127;
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                uint4 *o = reinterpret_cast<uint4 *>(a.q_img) + (((size_t)s * 4 + h) * a.RT + rt) * 3 * 128 + r;
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+                  float x[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) x[j] = v[h * HD + cc * 8 + j] * a.qscale;
+                  o[cc * 128] = pack8_bf16(x);
+                }
+              }
+            } else {
+              uint8_t *base = (nb == 1) ? a.k_img : a.v_img;
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                uint4 *o = reinterpret_cast<uint4 *>(base) + ((size_t)s * 4 + h) * 3 * a.Pk + p;
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) o[(size_t)cc * a.Pk] = pack8_bf16(&v[h * HD + cc * 8]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ===========================================================================
+// attention on tcgen05.  Persistent CTA (one per SM) streaming (sequence, head, row-tile) iterations:
+//   S = Q K^T   (M=128, N=Pk, K=32: head dim 24 padded with a shared zero chunk in smem)
+//   P = softmax rows (fp32 statistics read from TMEM, exp2 domain), written as a bf16 K-major image in smem
+//   O = P V     (M=128, N=32, K=Pk; V is the MN-major B operand)
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 and 6-9 two softmax groups that take
+// alternate iterations with private S/O accumulators in TMEM and private P images (ping-pong): while one
+// group exponentiates, the tensor core computes the other group's S and P.V.
+// ===========================================================================
+struct TcAttnArgs {
+  const uint8_t *q_img, *k_img, *v_img;
+  uint8_t *o_img;
+  int S, P, Pk, RT;
+  uint32_t thr16; float dscale; uint64_t key;
+};
+
+constexpr int TCA_THREADS = 320;
+constexpr int TCA_QBUF = 4, TCA_KVBUF = 3;
+
+__global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int P = a.P, Pk = a.Pk, RT = a.RT;
+  const uint32_t KVB = 3u * Pk * 16;          // bytes of one K (or V) image
+  const uint32_t PB = (uint32_t)(Pk / 8) * 2048;
+  uint8_t *sQ = smem;                          // TCA_QBUF x 6144
+  uint8_t *sK = sQ + TCA_QBUF * 6144;          // TCA_KVBUF x KVB
+  uint8_t *sV = sK + TCA_KVBUF * KVB;          // TCA_KVBUF x KVB
+  uint8_t *sZ = sV + TCA_KVBUF * KVB;          // zero chunk: max(128, Pk) rows x 16 B
+  const uint32_t zrows = Pk > 128 ? Pk : 128;
+  uint8_t *sP = sZ + zrows * 16;               // 2 x [Pk/8][128][16 B]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * PB);
+  uint64_t *q_full = bars, *q_empty = bars + 4, *kv_full = bars + 8, *kv_empty = bars + 11;
+  uint64_t *s_full = bars + 14, *s_empty = bars + 16, *p_ready = bars + 18, *o_full = bars + 20, *o_empty = bars + 22;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TCA_QBUF; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    for (int i = 0; i < TCA_KVBUF; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1); mbar_init(&s_empty[g], 4); mbar_init(&p_ready[g], 4);
+      mbar_init(&o_full[g], 1); mbar_init(&o_empty[g], 4);
+    }
+    fence_barrier_init();
+  }
+  for (uint32_t i = threadIdx.x; i < zrows * 4; i += blockDim.x) reinterpret_cast<uint32_t *>(sZ)[i] = 0u;
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int my_seqs = (a.S - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int per_seq = 4 * RT;
+  const int NIT = my_seqs * per_seq;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < NIT; ++i) {
+        const int seq = blockIdx.x + (i / per_seq) * gridDim.x, w = i % per_seq, h = w / RT, rt = w % RT;
+        if (rt == 0) {
+          const int hi = i / RT, kvb = hi % TCA_KVBUF;
+          mbar_wait(&kv_empty[kvb], ((hi / TCA_KVBUF) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[kvb], 2 * KVB);
+          tma_bulk_g2s(sK + kvb * KVB, a.k_img + ((size_t)seq * 4 + h) * KVB, KVB, &kv_full[kvb]);
+          tma_bulk_g2s(sV + kvb * KVB, a.v_img + ((size_t)seq * 4 + h) * KVB, KVB, &kv_full[kvb]);
+        }
+        const int qb = i & 3;
+        mbar_wait(&q_empty[qb], ((i >> 2) & 1) ^ 1);
+        mbar_expect_tx(&q_full[qb], 6144);
+        tma_bulk_g2s(sQ + qb * 6144, a.q_img + (((size_t)seq * 4 + h) * RT + rt) * 6144, 6144, &q_full[qb]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, Pk, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, 32, 0, 1);
+      const uint32_t zaddr = smem_u32(sZ);
+      for (int j = 0; j <= NIT; ++j) {
+        if (j < NIT) {
+          const int i = j, g = i & 1, u = i >> 1, rt = (i % per_seq) % RT, hi = i / RT, kvb = hi % TCA_KVBUF, qb = i & 3;
+          if (rt == 0) mbar_wait(&kv_full[kvb], (hi / TCA_KVBUF) & 1);
+          mbar_wait(&q_full[qb], (i >> 2) & 1);
+          mbar_wait(&s_empty[g], (u & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t qa = smem_u32(sQ + qb * 6144), ka = smem_u32(sK + kvb * KVB), ts = tmem + g * 256;
+          // k-step 0: head dims 0..15 (chunks 0,1); k-step 1: dims 16..23 + the shared zero chunk
+          umma_bf16(ts, umma_desc(qa, 2048, 128), umma_desc(ka, Pk * 16, 128), idesc_s, 0u);
+          umma_bf16(ts, umma_desc(qa + 2 * 2048, zaddr - (qa + 2 * 2048), 128),
+                    umma_desc(ka + 2 * Pk * 16, zaddr - (ka + 2 * Pk * 16), 128), idesc_s, 1u);
+          umma_commit(&s_full[g]);
+          umma_commit(&q_empty[qb]);
+        }
+        if (j >= 1) {
+          const int i = j - 1, g = i & 1, u = i >> 1, rt = (i % per_seq) % RT, hi = i / RT, kvb = hi % TCA_KVBUF;
+          mbar_wait(&p_ready[g], u & 1);
+          mbar_wait(&o_empty[g], (u & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t pa = smem_u32(sP + g * PB), va = smem_u32(sV + kvb * KVB), to = tmem + g * 256 + 192;
+          for (int kk = 0; kk < Pk / 16; ++kk)
+            umma_bf16(to, umma_desc(pa + kk * 2 * 2048, 2048, 128), umma_desc(va + kk * 256, 128, Pk * 16), idesc_o,
+                      kk != 0 ? 1u : 0u);
+          umma_commit(&o_full[g]);
+          if (rt == RT - 1) umma_commit(&kv_empty[kvb]);
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3, g = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t TM_S = tmem + g * 256, TM_O = tmem + g * 256 + 192;
+    uint8_t *myP = sP + g * PB;
+    for (int i = g; i < NIT; i += 2) {
+      const int u = i >> 1;
+      const int seq = blockIdx.x + (i / per_seq) * gridDim.x, w = i % per_seq, h = w / RT, rt = w % RT;
+      const int rows_valid = min(128, P - rt * 128);
+      const bool warp_active = q * 32 < rows_valid;
+      const bool row_valid = row < rows_valid;
+      mbar_wait(&s_full[g], u & 1);
+      tc_fence_after();
+      // V rows of the padded keys must be finite zeros (P is 0 there, but 0 * NaN = NaN)
+      if (rt == 0 && q == 2) {
+        const int npad = Pk - P, kvb = (i / RT) % TCA_KVBUF;
+        for (int jz = lane; jz < npad * 3; jz += 32) {
+          const int gg = jz / npad, rr = P + jz % npad;
+          *reinterpret_cast<uint4 *>(sV + kvb * KVB + ((size_t)gg * Pk + rr) * 16) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      float m = -INFINITY, l = 0.f;
+      if (warp_active) {
+        // pass 1: row maximum over the P valid columns
+        for (int c0 = 0; c0 < Pk; c0 += 32) {
+          if (c0 + 32 <= Pk) {
+            float t[32];
+            tmem_ld32(TM_S + lane_base + c0, t);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) if (c0 + c < P) m = fmaxf(m, t[c]);
+          } else {
+            float t[16];
+            tmem_ld16(TM_S + lane_base + c0, t);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) if (c0 + c < P) m = fmaxf(m, t[c]);
+          }
+        }
+        // pass 2: p = 2^(s - m), row sum, (dropout), bf16 image
+        const uint64_t drop_base = (((uint64_t)seq * 4 + h) * P + (rt * 128 + row)) * (uint64_t)(Pk / 8);
+        uint4 *prow = reinterpret_cast<uint4 *>(myP) + row;
+        for (int c0 = 0; c0 < Pk; c0 += 32) {
+          float t[32];
+          if (c0 + 32 <= Pk) {
+            tmem_ld32(TM_S + lane_base + c0, t);
+          } else {
+            float t16[16];
+            tmem_ld16(TM_S + lane_base + c0, t16);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) t[c] = t16[c];
+#pragma unroll
+            for (int c = 16; c < 32; ++c) t[c] = -INFINITY;
+          }
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float pv = (c0 + c < P) ? fast_exp2(t[c] - m) : 0.f;
+            l += pv;
+            t[c] = pv;
+          }
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            if (c0 + cc * 8 < Pk) {
+              if (a.thr16) drop8(&t[cc * 8], drop_base + (c0 >> 3) + cc, a.thr16, 1.0f, a.key);
+              prow[(size_t)((c0 >> 3) + cc) * 128] = pack8_bf16(&t[cc * 8]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&s_empty[g]); mbar_arrive(&p_ready[g]); }
+      // epilogue: O / l  -> O tile image (token-tile format of the following out-projection GEMM)
+      mbar_wait(&o_full[g], u & 1);
+      tc_fence_after();
+      float o[32];
+      if (warp_active) tmem_ld32(TM_O + lane_base, o);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[g]);
+      if (row_valid) {
+        const float inv = a.dscale / l;
+        const long long token = (long long)seq * P + rt * 128 + row;
+        const long long mt = token >> 7;
+        const int r = (int)(token & 127);
+        uint4 *dst = reinterpret_cast<uint4 *>(a.o_img) + ((size_t)mt * 12 + 3 * h) * 128 + r;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          float x[8];
+#pragma unroll
+          for (int jx = 0; jx < 8; ++jx) x[jx] = o[cc * 8 + jx] * inv;
+          dst[cc * 128] = pack8_bf16(x);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------
+static size_t tcl_smem_bytes(int K, int Nout) {
+  return (size_t)K * Nout * 2 + TCL_STAGES * SLICE_BYTES + 32 * 8 + 16;
+}
+static size_t tca_smem_bytes(int Pk) {
+  const size_t zrows = Pk > 128 ? Pk : 128;
+  return TCA_QBUF * 6144 + 2 * TCA_KVBUF * (size_t)(3 * Pk * 16) + zrows * 16 + 2 * (size_t)(Pk / 8) * 2048 + 32 * 8 + 16;
+}
+
+static int tc_linear_launch(const TcLinearArgs &a, cudaStream_t st) {
+  if (!((a.K == 96 || a.K == 384) && a.Nout % 96 == 0 && a.Nout >= 96 && a.Nout <= 384))
+    return fail(STEP_EUNSUPPORTED, "tc_linear: unsupported shape K=%lld Nout=%lld", a.K, a.Nout);
+  const size_t smem = tcl_smem_bytes(a.K, a.Nout);
+  int rc = allow_smem(tc_linear_kernel, 227 * 1024);
+  if (rc) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = a.MT < sms ? a.MT : sms;
+  tc_linear_kernel<<<grid, TCL_THREADS, smem, st>>>(a);
+  return check_launch("tc_linear_kernel");
+}
+
+}  // namespace stepk
+
+using namespace stepk;
+
+extern "C" int step_tc_pack_weight(const float *w, int Nout, int K, void *img, void *stream) {
+  STEP_REQUIRE(w && img && Nout > 0 && K > 0 && K % 8 == 0, "tc_pack_weight: bad argument");
+  const int units = Nout * (K / 8);
+  tc_pack_weight_kernel<<<(units + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, Nout, K, reinterpret_cast<uint4 *>(img));
+  return check_launch("tc_pack_weight_kernel");
+}
+
+extern "C" int step_tc_rows_to_image(const float *x, long long T, int K, void *img, void *stream) {
+  STEP_REQUIRE(x && img && T > 0 && K % 8 == 0, "tc_rows_to_image: bad argument");
+  const long long units = ((T + 127) / 128) * (K / 8) * 128;
+  tc_rows_to_image_kernel<<<(unsigned)((units + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, T, K, reinterpret_cast<uint4 *>(img));
+  return check_launch("tc_rows_to_image_kernel");
+}
+
+extern "C" int step_tc_image_to_rows(const void *img, long long T, int K, float *x, void *stream) {
+  STEP_REQUIRE(x && img && T > 0 && K % 8 == 0, "tc_image_to_rows: bad argument");
+  const long long units = ((T + 127) / 128) * (K / 8) * 128;
+  tc_image_to_rows_kernel<<<(unsigned)((units + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4 *>(img), T, K, x);
+  return check_launch("tc_image_to_rows_kernel");
+}
+
+extern "C" int step_tc_linear(const void *a_img, const void *w_img, const float *bias, long long T, int K, int Nout, int mode,
+                              const void *res_img, const float *ln_w, const float *ln_b, void *out_img, float *out_f32,
+                              void *stream) {
+  STEP_REQUIRE(a_img && w_img && bias && T > 0, "tc_linear: bad argument");
+  STEP_REQUIRE(mode == TCM_F32 || mode == TCM_RELU_IMG || mode == TCM_RESLN, "tc_linear: bad mode");
+  if (mode == TCM_RESLN) STEP_REQUIRE(res_img && ln_w && ln_b && Nout == 96, "tc_linear: residual+LN needs its operands");
+  TcLinearArgs a{};
+  a.A = (const uint8_t *)a_img; a.W = (const uint8_t *)w_img; a.bias = bias;
+  a.MT = (int)((T + 127) / 128); a.K = K; a.Nout = Nout; a.mode = mode; a.T = T;
+  a.res = (const uint8_t *)res_img; a.ln_w = ln_w; a.ln_b = ln_b;
+  a.out_img = (uint8_t *)out_img; a.out_f32 = out_f32;
+  a.dscale = 1.f;
+  return tc_linear_launch(a, (cudaStream_t)stream);
+}
+
+extern "C" size_t step_tc_attn_image_bytes(int S, int P, int which) {
+  const int Pk = (P + 15) / 16 * 16, RT = (P + 127) / 128;
+  if (which == 0) return (size_t)S * 4 * RT * 6144;
+  return (size_t)S * 4 * 3 * Pk * 16;
+}
+
+extern "C" int step_tc_qkv(const void *x_img, const void *w_img, const float *bias, int S, int P, void *q_img, void *k_img,
+                           void *v_img, void *stream) {
+  STEP_REQUIRE(x_img && w_img && bias && q_img && k_img && v_img && S > 0 && P > 0, "tc_qkv: bad argument");
+  TcLinearArgs a{};
+  const long long T = (long long)S * P;
+  a.A = (const uint8_t *)x_img; a.W = (const uint8_t *)w_img; a.bias = bias;
+  a.MT = (int)((T + 127) / 128); a.K = 96; a.Nout = 288; a.mode = TCM_QKV; a.T = T;
+  a.q_img = (uint8_t *)q_img; a.k_img = (uint8_t *)k_img; a.v_img = (uint8_t *)v_img;
+  a.P = P; a.Pk = (P + 15) / 16 * 16; a.RT = (P + 127) / 128;
+  a.qscale = 0.20412414523193154f * 1.4426950408889634f;
+  a.dscale = 1.f;
+  return tc_linear_launch(a, (cudaStream_t)stream);
+}
+
+static int tc_attn_launch(const void *q_img, const void *k_img, const void *v_img, void *o_img, int S, int P, float drop_p,
+                          uint64_t seed, uint32_t site, cudaStream_t st) {
+  TcAttnArgs a{};
+  a.q_img = (const uint8_t *)q_img; a.k_img = (const uint8_t *)k_img; a.v_img = (const uint8_t *)v_img; a.o_img = (uint8_t *)o_img;
+  a.S = S; a.P = P; a.Pk = (P + 15) / 16 * 16; a.RT = (P + 127) / 128;
+  if (a.Pk > 176) return fail(STEP_EUNSUPPORTED, "tc_attention: P=%lld > 176 is served by the fp32 path for now", P);
+  if (drop_p > 0.f) { a.thr16 = (uint32_t)(drop_p * 65536.0f); a.dscale = 1.f / (1.f - drop_p); }
+  else { a.thr16 = 0; a.dscale = 1.f; }
+  a.key = rng_key(seed, site);
+  int rc = allow_smem(tc_attn_kernel, 227 * 1024);
+  if (rc) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  tc_attn_kernel<<<S < sms ? S : sms, TCA_THREADS, tca_smem_bytes(a.Pk), st>>>(a);
+  return check_launch("tc_attn_kernel");
+}
+
+extern "C" int step_tc_attention(const void *q_img, const void *k_img, const void *v_img, void *o_img, int S, int P,
+                                 float drop_p, unsigned long long seed, void *stream) {
+  STEP_REQUIRE(q_img && k_img && v_img && o_img && S > 0 && P > 0, "tc_attention: bad argument");
+  return tc_attn_launch(q_img, k_img, v_img, o_img, S, P, drop_p, seed, 0, (cudaStream_t)stream);
+}
+
+// packed weight images of one encoder layer
+extern "C" size_t step_ts_encoder_bf16_workspace_bytes(int B, int N, int P) {
+  const long long S = (long long)B * N, T = S * P, MT = (T + 127) / 128;
+  const int Pk = (P + 15) / 16 * 16, RT = (P + 127) / 128;
+  size_t b = 0;
+  b += 4 * (size_t)MT * SLICE_BYTES;                // X, X1, X2, O images
+  b += (size_t)MT * 4 * SLICE_BYTES;                // H image (K = 384)
+  b += (size_t)S * 4 * RT * 6144;                   // Q
+  b += 2 * (size_t)S * 4 * 3 * Pk * 16;             // K, V
+  return b + 4096;
+}
+
+extern "C" int step_ts_encoder_fwd_bf16(const float *series, long long sB, long long sT, long long sN, int B, int N, int P,
+                                        const float *patch_w, const float *patch_b, const float *pos,
+                                        const step_ts_layer_weights *L, const step_ts_layer_images *I, int n_layers,
+                                        const float *fnw, const float *fnb, float *hidden, void *workspace,
+                                        size_t workspace_bytes, float drop_p, unsigned long long seed, void *stream) {
+  STEP_REQUIRE(series && patch_w && patch_b && pos && L && I && fnw && fnb && hidden && workspace, "ts_encoder_bf16: null pointer");
+  STEP_REQUIRE(n_layers >= 1 && B > 0 && N > 0 && P > 0, "ts_encoder_bf16: bad shape");
+  if (workspace_bytes < step_ts_encoder_bf16_workspace_bytes(B, N, P))
+    return fail(STEP_EWORKSPACE, "ts_encoder_bf16: workspace too small (%lld bytes needed)",
+                (long long)step_ts_encoder_bf16_workspace_bytes(B, N, P));
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long S = (long long)B * N, T = S * P, MT = (T + 127) / 128;
+  const int Pk = (P + 15) / 16 * 16, RT = (P + 127) / 128;
+  uint8_t *ws = reinterpret_cast<uint8_t *>(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  uint8_t *X = ws; ws += (size_t)MT * SLICE_BYTES;
+  uint8_t *X1 = ws; ws += (size_t)MT * SLICE_BYTES;
+  uint8_t *X2 = ws; ws += (size_t)MT * SLICE_BYTES;
+  uint8_t *O = ws; ws += (size_t)MT * SLICE_BYTES;
+  uint8_t *H = ws; ws += (size_t)MT * 4 * SLICE_BYTES;
+  uint8_t *Q = ws; ws += (size_t)S * 4 * RT * 6144;
+  uint8_t *Kimg = ws; ws += (size_t)S * 4 * 3 * Pk * 16;
+  uint8_t *Vimg = ws;
+  uint32_t thr16 = 0; float dscale = 1.f;
+  if (drop_p > 0.f) { thr16 = (uint32_t)(drop_p * 65536.0f); dscale = 1.f / (1.f - drop_p); }
+
+  tc_embed_kernel<<<dim3((P + 31) / 32, (N + 15) / 16, B), 256, 0, st>>>(series, sB, sT, sN, N, P, patch_w, patch_b, pos,
+                                                                        reinterpret_cast<uint4 *>(X), thr16, dscale,
+                                                                        rng_key(seed, 1));
+  STEP_LAUNCH_CHECK("tc_embed_kernel");
+  uint8_t *cur = X, *nxt = X2;
+  int rc;
+  for (int l = 0; l < n_layers; ++l) {
+    const uint32_t site = 16u * (l + 1);
+    TcLinearArgs a{};
+    // QKV projection -> attention operand images
+    a.A = cur; a.W = (const uint8_t *)I[l].in_proj; a.bias = L[l].in_proj_b; a.MT = (int)MT; a.K = 96; a.Nout = 288;
+    a.mode = TCM_QKV; a.T = T; a.q_img = Q; a.k_img = Kimg; a.v_img = Vimg; a.P = P; a.Pk = Pk; a.RT = RT;
+    a.qscale = 0.20412414523193154f * 1.4426950408889634f; a.dscale = 1.f;
+    if ((rc = tc_linear_launch(a, st))) return rc;
+    if ((rc = tc_attn_launch(Q, Kimg, Vimg, O, (int)S, P, drop_p, seed, site + 1, st))) return rc;
+    // X1 = LN1(cur + drop(O Wo^T + bo))
+    a = TcLinearArgs{};
+    a.A = O; a.W = (const uint8_t *)I[l].out_proj; a.bias = L[l].out_proj_b; a.MT = (int)MT; a.K = 96; a.Nout = 96;
+    a.mode = TCM_RESLN; a.T = T; a.res = cur; a.ln_w = L[l].norm1_w; a.ln_b = L[l].norm1_b; a.out_img = X1;
+    a.thr16 = thr16; a.dscale = dscale; a.key = rng_key(seed, site + 2);
+    if ((rc = tc_linear_launch(a, st))) return rc;
+    // H = drop(relu(X1 W1^T + b1))
+    a = TcLinearArgs{};
+    a.A = X1; a.W = (const uint8_t *)I[l].lin1; a.bias = L[l].lin1_b; a.MT = (int)MT; a.K = 96; a.Nout = 384;
+    a.mode = TCM_RELU_IMG; a.T = T; a.out_img = H; a.thr16 = thr16; a.dscale = dscale; a.key = rng_key(seed, site + 3);
+    if ((rc = tc_linear_launch(a, st))) return rc;
+    // X2 = LN2(X1 + drop(H W2^T + b2)); last layer: + encoder_norm, fp32 row-major hidden
+    const bool last = (l == n_layers - 1);
+    a = TcLinearArgs{};
+    a.A = H; a.W = (const uint8_t *)I[l].lin2; a.bias = L[l].lin2_b; a.MT = (int)MT; a.K = 384; a.Nout = 96;
+    a.mode = TCM_RESLN; a.T = T; a.res = X1; a.ln_w = L[l].norm2_w; a.ln_b = L[l].norm2_b;
+    if (last) { a.ln2_w = fnw; a.ln2_b = fnb; a.out_f32 = hidden; a.out_img = nullptr; }
+    else a.out_img = nxt;
+    a.thr16 = thr16; a.dscale = dscale; a.key = rng_key(seed, site + 4);
+    if ((rc = tc_linear_launch(a, st))) return rc;
+    uint8_t *t = cur; cur = nxt; nxt = t;
+  }
+  return STEP_OK;
+}

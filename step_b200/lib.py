@@ -23,6 +23,10 @@ class TsLayerWeights(C.Structure):
         "norm1_w", "norm1_b", "norm2_w", "norm2_b")]
 
 
+class TsLayerImages(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("in_proj", "out_proj", "lin1", "lin2")]
+
+
 class GwLayerParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "filter_w", "filter_b", "gate_w", "gate_b", "skip_w", "skip_b", "mlp_w", "mlp_b", "bn_w", "bn_b")]
@@ -47,6 +51,17 @@ SIGNATURES = {
     "step_ts_encoder_fwd": (C.c_int, [f32p, ll, ll, ll, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p,
                                       C.POINTER(TsLayerWeights), C.c_int, f32p, f32p, f32p, vp, C.c_size_t, C.c_int,
                                       C.c_float, ull, vp]),
+    "step_tc_pack_weight": (C.c_int, [f32p, C.c_int, C.c_int, vp, vp]),
+    "step_tc_rows_to_image": (C.c_int, [f32p, ll, C.c_int, vp, vp]),
+    "step_tc_image_to_rows": (C.c_int, [vp, ll, C.c_int, f32p, vp]),
+    "step_tc_linear": (C.c_int, [vp, vp, f32p, ll, C.c_int, C.c_int, C.c_int, vp, f32p, f32p, vp, f32p, vp]),
+    "step_tc_attn_image_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "step_tc_qkv": (C.c_int, [vp, vp, f32p, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "step_tc_attention": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, ull, vp]),
+    "step_ts_encoder_bf16_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "step_ts_encoder_fwd_bf16": (C.c_int, [f32p, ll, ll, ll, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p,
+                                           C.POINTER(TsLayerWeights), C.POINTER(TsLayerImages), C.c_int, f32p, f32p, f32p, vp,
+                                           C.c_size_t, C.c_float, ull, vp]),
     "step_cosine_gram_f32": (C.c_int, [f32p, C.c_int, C.c_int, ll, f32p, f32p, vp]),
     "step_topk_mask_f32": (C.c_int, [f32p, C.c_int, C.c_int, C.c_int, f32p, vp]),
     "step_edge_logits_fwd": (C.c_int, [f32p, f32p, f32p, f32p, C.c_int, C.c_int, f32p, f32p, vp]),

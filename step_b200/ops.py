@@ -292,3 +292,99 @@ class GWNetStack(torch.autograd.Function):
         n_gcn = sum(1 for i in range(n_layers) if params[i * 10 + 6] is not None)
         launch_counter["kernels"] += 2 * n_layers + n_gcn + (n_layers - 1)
         return (dx0, dP1, dP2, dP3, None, None, None, None, None, *grads)
+
+
+# --------------------------------------------------------------------------- #
+# bf16 tensor-core encoder (tcgen05 / TMEM / TMA bulk)
+# --------------------------------------------------------------------------- #
+def tc_pack_weight(w: Tensor) -> Tensor:
+    """fp32 [Nout, K] -> bf16 weight image (uint8 tensor of Nout*K*2 bytes)."""
+    w = _f32(w, "w")
+    Nout, K = w.shape
+    st = _enter(w)
+    img = torch.empty(Nout * K * 2, device=w.device, dtype=torch.uint8)
+    check(_L().step_tc_pack_weight(w.data_ptr(), Nout, K, img.data_ptr(), st), "step_tc_pack_weight")
+    launch_counter["kernels"] += 1
+    return img
+
+
+def tc_rows_to_image(x: Tensor) -> Tensor:
+    x = _f32(x, "x")
+    T, K = x.shape
+    st = _enter(x)
+    img = torch.empty(((T + 127) // 128) * K * 256, device=x.device, dtype=torch.uint8)
+    check(_L().step_tc_rows_to_image(x.data_ptr(), T, K, img.data_ptr(), st), "step_tc_rows_to_image")
+    return img
+
+
+def tc_image_to_rows(img: Tensor, T: int, K: int) -> Tensor:
+    st = _enter(img)
+    x = torch.empty(T, K, device=img.device, dtype=torch.float32)
+    check(_L().step_tc_image_to_rows(img.data_ptr(), T, K, x.data_ptr(), st), "step_tc_image_to_rows")
+    return x
+
+
+def tc_linear(a_img: Tensor, w_img: Tensor, bias: Tensor, T: int, K: int, Nout: int, mode: int, res_img: Optional[Tensor] = None,
+              ln_w: Optional[Tensor] = None, ln_b: Optional[Tensor] = None, want_f32: bool = False):
+    """mode 0 -> fp32 [T,Nout]; mode 1 -> ReLU image; mode 2 -> residual+LayerNorm image (and fp32 rows if want_f32)."""
+    st = _enter(a_img)
+    MT = (T + 127) // 128
+    out_img = out_f32 = None
+    if mode == 0 or want_f32:
+        out_f32 = torch.empty(T, Nout, device=a_img.device, dtype=torch.float32)
+    if mode in (1, 2):
+        out_img = torch.empty(MT * Nout * 256, device=a_img.device, dtype=torch.uint8)
+    check(_L().step_tc_linear(a_img.data_ptr(), w_img.data_ptr(), _f32(bias, "bias").data_ptr(), T, K, Nout, mode, _p(res_img),
+                              _p(ln_w), _p(ln_b), _p(out_img), _p(out_f32), st), "step_tc_linear")
+    launch_counter["kernels"] += 1
+    return out_img, out_f32
+
+
+def tc_qkv_attention(x_img: Tensor, w_img: Tensor, bias: Tensor, S: int, P: int, drop_p: float = 0.0, seed: int = 0) -> Tensor:
+    """X image [S*P,96] -> O image [S*P,96] (QKV projection + softmax(QK^T)V, both on tcgen05)."""
+    st = _enter(x_img)
+    dev = x_img.device
+    q = torch.empty(_L().step_tc_attn_image_bytes(S, P, 0), device=dev, dtype=torch.uint8)
+    k = torch.empty(_L().step_tc_attn_image_bytes(S, P, 1), device=dev, dtype=torch.uint8)
+    v = torch.empty(_L().step_tc_attn_image_bytes(S, P, 1), device=dev, dtype=torch.uint8)
+    o = torch.empty(((S * P + 127) // 128) * 96 * 256, device=dev, dtype=torch.uint8)
+    check(_L().step_tc_qkv(x_img.data_ptr(), w_img.data_ptr(), _f32(bias, "bias").data_ptr(), S, P, q.data_ptr(), k.data_ptr(),
+                           v.data_ptr(), st), "step_tc_qkv")
+    check(_L().step_tc_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), S, P, float(drop_p), int(seed), st),
+          "step_tc_attention")
+    launch_counter["kernels"] += 2
+    return o
+
+
+def ts_pack_layer_images(layers: Sequence[Dict[str, Tensor]]):
+    """Pack the four weight matrices of every encoder layer into bf16 UMMA images (done once: the TSFormer is frozen)."""
+    return [{"in_proj": tc_pack_weight(lw["in_proj_w"]), "out_proj": tc_pack_weight(lw["out_proj_w"]),
+             "lin1": tc_pack_weight(lw["lin1_w"]), "lin2": tc_pack_weight(lw["lin2_w"])} for lw in layers]
+
+
+def ts_encoder_forward_bf16(series: Tensor, patch_w: Tensor, patch_b: Tensor, pos: Tensor, layers: Sequence[Dict[str, Tensor]],
+                            images, norm_w: Tensor, norm_b: Tensor, drop_p: float = 0.0, seed: int = 0) -> Tensor:
+    """series [B, P*12, N] view -> hidden [B, N, P, 96] fp32, computed on the tensor cores in bf16."""
+    if not series.is_cuda or series.dtype != torch.float32:
+        raise _lib.StepB200Error("ts_encoder_forward_bf16: series must be a float32 CUDA tensor")
+    B, T, N = series.shape
+    if T % 12 != 0:
+        raise _lib.StepB200Error(f"ts_encoder_forward_bf16: history length {T} is not a multiple of the patch size 12")
+    P = T // 12
+    st = _enter(series)
+    hidden = torch.empty(B, N, P, 96, device=series.device, dtype=torch.float32)
+    ws_bytes = _L().step_ts_encoder_bf16_workspace_bytes(B, N, P)
+    ws = torch.empty(ws_bytes, device=series.device, dtype=torch.uint8)
+    arr, keep = ts_layer_struct(layers)
+    iarr = (_lib.TsLayerImages * len(layers))()
+    for i, im in enumerate(images):
+        for name in ("in_proj", "out_proj", "lin1", "lin2"):
+            setattr(iarr[i], name, im[name].data_ptr())
+    pw, pb, ps = _f32(patch_w.reshape(96, 12), "patch_w"), _f32(patch_b, "patch_b"), _f32(pos, "pos")
+    nw, nb = _f32(norm_w, "norm_w"), _f32(norm_b, "norm_b")
+    sB, sT, sN = series.stride()
+    check(_L().step_ts_encoder_fwd_bf16(series.data_ptr(), sB, sT, sN, B, N, P, pw.data_ptr(), pb.data_ptr(), ps.data_ptr(), arr,
+                                        iarr, len(layers), nw.data_ptr(), nb.data_ptr(), hidden.data_ptr(), ws.data_ptr(),
+                                        ws_bytes, float(drop_p), int(seed) & (2**64 - 1), st), "step_ts_encoder_fwd_bf16")
+    launch_counter["kernels"] += 1 + len(layers) * 5
+    return hidden

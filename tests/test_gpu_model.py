@@ -24,6 +24,7 @@ def test_step_forward_backward_matches_reference_golden(name, tmp_path):
     ds, n = fx["dataset"], O.NUM_NODES[fx["dataset"]]
     model, _, _ = build_step_model(tmp_path, ds, fx["seed"], real_ckpt=fx["real_ckpt"])
     model = model.to(DEV).train()
+    model.tsformer.precision = "fp32"       # the 1e-4 parity bar is defined for the fp32 kernels
     model.tsformer.dropout_p = 0.0          # parity suite B (SURVEY Appx D.4): train() everywhere, dropout off
     model.backend.dropout = 0.0
     history, long_history, future, uniform = O.synthetic_batch(ds, fx["batch"], fx["patches"], fx["seed"])
@@ -63,6 +64,7 @@ def test_full_size_properties_metr_la(tmp_path):
     """BASELINE configs[1] shape (N=207, B=32, P=168): size-independent properties of the path."""
     model, _, _ = build_step_model(tmp_path, "METR-LA", 0, real_ckpt=True)
     model = model.to(DEV)
+    model.tsformer.precision = "fp32"
     B, n = 32, 207
     history, long_history, future, _ = O.synthetic_batch("METR-LA", B, 168, 3)
     history, long_history = history.to(DEV), long_history.to(DEV)
@@ -99,3 +101,28 @@ def test_full_size_properties_metr_la(tmp_path):
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
         else:
             assert p.grad is not None and torch.isfinite(p.grad).all(), k
+
+
+@pytest.mark.parametrize("name", ["step_METR-LA_b2.pt"])
+def test_step_bf16_encoder_against_reference_golden(name, tmp_path):
+    """Performance precision: TSFormer on the tensor cores in bf16 (everything downstream fp32).  Stated tolerance
+    for this mode: y_hat MAE <= 5e-3, adj_knn differs in <= 2% of the selected edges (the top-k threshold cuts through
+    near-ties), theta untouched (it does not depend on the encoder)."""
+    fx = torch.load(os.path.join(GOLDEN, name), weights_only=False)
+    ds, n = fx["dataset"], O.NUM_NODES[fx["dataset"]]
+    model, _, _ = build_step_model(tmp_path, ds, fx["seed"], real_ckpt=fx["real_ckpt"])
+    model = model.to(DEV).train()
+    model.tsformer.precision = "bf16"
+    model.tsformer.dropout_p = 0.0
+    model.backend.dropout = 0.0
+    history, long_history, future, uniform = O.synthetic_batch(ds, fx["batch"], fx["patches"], fx["seed"])
+    model.discrete_graph_learning.gumbel_uniform = uniform.to(DEV)
+    y_hat, theta, adj_knn, coeff = model(history_data=history.to(DEV), long_history_data=long_history.to(DEV),
+                                         future_data=None, batch_seen=0, epoch=1)
+    mae = (y_hat.detach().cpu() - fx["y_hat"]).abs().mean().item()
+    ref_knn = unpack(fx["adj_knn_bits"], n)
+    mism = int((adj_knn.cpu() != ref_knn).sum())
+    print(f"bf16 encoder: y_hat MAE {mae:.3e}, adj_knn mismatches {mism} of {int(ref_knn.sum())} edges")
+    assert mae <= 5e-3
+    assert mism <= 0.02 * 2 * float(ref_knn.sum())
+    assert (theta[0].detach().cpu() - fx["theta0"]).abs().max().item() < 1e-5

@@ -1,0 +1,110 @@
+"""GPU tests of the tcgen05 (bf16 tensor-core) encoder kernels.
+
+bf16 operands with fp32 accumulation: the comparison target for a single GEMM is the same product of
+bf16-rounded operands in fp32 (tight), for attention / the whole encoder the fp32 oracle with a bf16-level
+tolerance (stated in each test)."""
+import math
+
+import pytest
+import torch
+
+from oracle import step_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def test_image_roundtrip():
+    from step_b200 import ops
+    x = torch.randn(300, 96)
+    img = ops.tc_rows_to_image(x.to(DEV))
+    back = ops.tc_image_to_rows(img, 300, 96).cpu()
+    assert torch.equal(back, bf(x))
+
+
+@pytest.mark.parametrize("T,K,Nout", [(128, 96, 96), (300, 96, 288), (1000, 96, 384), (515, 384, 96), (40000, 96, 288)])
+def test_tc_linear_f32_out(T, K, Nout):
+    from step_b200 import ops
+    g = torch.Generator().manual_seed(T + K + Nout)
+    x, w, b = torch.randn(T, K, generator=g), torch.randn(Nout, K, generator=g) * 0.1, torch.randn(Nout, generator=g)
+    ref = bf(x) @ bf(w).t() + b
+    _, out = ops.tc_linear(ops.tc_rows_to_image(x.to(DEV)), ops.tc_pack_weight(w.to(DEV)), b.to(DEV), T, K, Nout, 0)
+    err = (out.cpu() - ref).abs().max().item()
+    assert err < 1e-3 * max(1.0, ref.abs().max().item()), err
+
+
+def test_tc_linear_relu_and_resln():
+    from step_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    T = 700
+    x, w1, b1 = torch.randn(T, 96, generator=g), torch.randn(384, 96, generator=g) * 0.1, torch.randn(384, generator=g) * 0.1
+    w2, b2 = torch.randn(96, 384, generator=g) * 0.1, torch.randn(96, generator=g) * 0.1
+    lw, lb = torch.rand(96, generator=g) + 0.5, torch.randn(96, generator=g) * 0.1
+    x_img = ops.tc_rows_to_image(x.to(DEV))
+    h_img, _ = ops.tc_linear(x_img, ops.tc_pack_weight(w1.to(DEV)), b1.to(DEV), T, 96, 384, 1)
+    h_ref = bf(torch.relu(bf(x) @ bf(w1).t() + b1))
+    h = ops.tc_image_to_rows(h_img, T, 384).cpu()
+    assert (h - h_ref).abs().max().item() < 0.02
+    y_img, y = ops.tc_linear(h_img, ops.tc_pack_weight(w2.to(DEV)), b2.to(DEV), T, 384, 96, 2, res_img=x_img, ln_w=lw.to(DEV),
+                             ln_b=lb.to(DEV), want_f32=True)
+    y_ref = O._layer_norm(h @ bf(w2).t() + b2 + bf(x), lw, lb)
+    assert (y.cpu() - y_ref).abs().max().item() < 2e-3
+    assert (ops.tc_image_to_rows(y_img, T, 96).cpu() - bf(y.cpu())).abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("S,P", [(3, 168), (16, 168), (5, 100), (2, 24)])
+def test_tc_qkv_attention(S, P):
+    from step_b200 import ops
+    g = torch.Generator().manual_seed(S * 7 + P)
+    T = S * P
+    x = torch.randn(T, 96, generator=g)
+    w, b = torch.randn(288, 96, generator=g) * 0.15, torch.randn(288, generator=g) * 0.1
+    qkv = bf(x) @ bf(w).t() + b
+    q, k, v = qkv.view(S, P, 288).split(96, -1)
+    sh = lambda t: t.reshape(S, P, 4, 24).transpose(1, 2)
+    att = torch.softmax(sh(q) @ sh(k).transpose(-1, -2) / math.sqrt(24), -1)
+    ref = (att @ sh(v)).transpose(1, 2).reshape(T, 96)
+    o_img = ops.tc_qkv_attention(ops.tc_rows_to_image(x.to(DEV)), ops.tc_pack_weight(w.to(DEV)), b.to(DEV), S, P)
+    out = ops.tc_image_to_rows(o_img, T, 96).cpu()
+    err = (out - ref).abs()
+    # bf16 q/k/v/p: ~2^-8 relative per operand; values are O(1)
+    assert err.max().item() < 4e-2 and err.mean().item() < 4e-3, (err.max().item(), err.mean().item())
+
+
+def _layers(sd):
+    out = []
+    for i in range(4):
+        p = f"encoder.transformer_encoder.layers.{i}."
+        out.append({"in_proj_w": sd[p + "self_attn.in_proj_weight"], "in_proj_b": sd[p + "self_attn.in_proj_bias"],
+                    "out_proj_w": sd[p + "self_attn.out_proj.weight"], "out_proj_b": sd[p + "self_attn.out_proj.bias"],
+                    "lin1_w": sd[p + "linear1.weight"], "lin1_b": sd[p + "linear1.bias"],
+                    "lin2_w": sd[p + "linear2.weight"], "lin2_b": sd[p + "linear2.bias"],
+                    "norm1_w": sd[p + "norm1.weight"], "norm1_b": sd[p + "norm1.bias"],
+                    "norm2_w": sd[p + "norm2.weight"], "norm2_b": sd[p + "norm2.bias"]})
+    return [{k: v.to(DEV) for k, v in l.items()} for l in out]
+
+
+@pytest.mark.parametrize("B,N,P,real", [(2, 9, 168, False), (1, 40, 168, True), (3, 5, 24, False)])
+def test_ts_encoder_bf16_close_to_oracle(B, N, P, real):
+    import os
+    from conftest import GOLDEN
+    from step_b200 import ops
+    sd = torch.load(os.path.join(GOLDEN, "tsformer_METR-LA_state.pt")) if real else O.synthetic_tsformer_params(1)
+    g = torch.Generator().manual_seed(5)
+    long_history = torch.randn(B, P * 12, N, 3, generator=g)
+    ref = O.tsformer_encode(sd, long_history[..., [0]])
+    layers = _layers(sd)
+    images = ops.ts_pack_layer_images(layers)
+    out = ops.ts_encoder_forward_bf16(long_history.to(DEV)[..., 0], sd["patch_embedding.input_embedding.weight"].to(DEV),
+                                      sd["patch_embedding.input_embedding.bias"].to(DEV),
+                                      sd["positional_encoding.position_embedding"].to(DEV), layers, images,
+                                      sd["encoder_norm.weight"].to(DEV), sd["encoder_norm.bias"].to(DEV)).cpu()
+    err = (out - ref).abs()
+    print("bf16 encoder vs fp32 oracle: max", err.max().item(), "mean", err.mean().item(), "ref absmean", ref.abs().mean().item())
+    # 4 post-norm layers in bf16: stated tolerance = 3e-2 mean abs (hidden states are O(0.3-1))
+    assert torch.isfinite(out).all()
+    assert err.mean().item() < 3e-2 and err.max().item() < 0.5
