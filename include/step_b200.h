@@ -197,6 +197,25 @@ int step_gumbel_sample_fwd(const float *logits /*[N,N,2]*/, const float *uniform
 int step_gumbel_sample_bwd(const float *dsampled, const float *y0, int B, int N, float tau, int accumulate,
                            float *dlogits, void *stream);
 
+
+/* ------------------------------------------------------------------------ *
+ * Discrete graph learning: convolutional part of the batch-invariant "global feature" trunk
+ *   step/step_arch/discrete_graph_learning.py:131-133
+ *   x [N, L0] -> Conv1d(1,8,10) -> ReLU -> BN(8) -> Conv1d(8,16,10) -> ReLU -> BN(16) -> y2n [N, 16, L0-18]
+ * y1 is never materialised (recomputed from x wherever needed).  bnK_stats: [4][C] = mean, biased var,
+ * scale, shift - written when training != 0 (batch statistics), read as given when training == 0.
+ * y2: pre-BN2 conv output kept for the backward pass.  scratch: >= 4096 bytes.
+ * ------------------------------------------------------------------------ */
+int step_dgl_conv_fwd(const float *x, int N, int L0, const float *w1, const float *b1, const float *g1, const float *be1,
+                      const float *w2, const float *b2, const float *g2, const float *be2, float eps, int training,
+                      float *bn1_stats, float *bn2_stats, float *y2, float *y2n, void *scratch, void *stream);
+/* Backward of step_dgl_conv_fwd (training mode).  dy2n: [N,16,L0-18].  dy1n_scratch: [N,8,L0-9] floats.
+ * Outputs (overwritten): dw1 [8,1,10], db1 [8], dg1/dbe1 [8], dw2 [16,8,10], db2 [16], dg2/dbe2 [16]. */
+int step_dgl_conv_bwd(const float *dy2n, const float *x, int N, int L0, const float *w1, const float *b1, const float *g1,
+                      const float *w2, const float *g2, float eps, const float *bn1_stats, const float *bn2_stats,
+                      const float *y2, float *dy1n_scratch, float *dw1, float *db1, float *dg1, float *dbe1, float *dw2,
+                      float *db2, float *dg2, float *dbe2, void *scratch, void *stream);
+
 /* ------------------------------------------------------------------------ *
  * Graph WaveNet layer stack (8 x gated dilated conv + skip + diffusion GCN + BN)
  *   step/step_arch/graphwavenet/model.py:169-213 (+ gcn :35-48, nconv :10-16)

@@ -79,14 +79,33 @@ class DiscreteGraphLearning(nn.Module):
         scale = bn.weight * torch.rsqrt(var + bn.eps)
         return x * scale.view(shape) + (bn.bias - mean * scale).view(shape)
 
+    @staticmethod
+    @torch.no_grad()
+    def _update_running(bn, mean, var, count):
+        bn.running_mean.mul_(1 - bn.momentum).add_(mean, alpha=bn.momentum)
+        bn.running_var.mul_(1 - bn.momentum).add_(var, alpha=bn.momentum * count / max(count - 1, 1))
+        bn.num_batches_tracked += 1
+
+    @staticmethod
+    def _eval_stats(bn):
+        scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+        return torch.stack([bn.running_mean, bn.running_var, scale, bn.bias - bn.running_mean * scale]).contiguous()
+
     def _global_feature(self, device):
-        """Batch-invariant node embedding, reference :131-135.  [N, 100]."""
+        """Batch-invariant node embedding, reference :131-135.  [N, 100].  conv1/bn1/conv2/bn2 run in the fused
+        trunk kernels (csrc/trunk.cu); the [N, dim_fc] x [dim_fc, 100] Linear is a plain library GEMM."""
         if self._feats_dev is None or self._feats_dev.device != device:
-            self._feats_dev = self.node_feats.to(device).t().contiguous().unsqueeze(1)     # [N,1,L], uploaded once
+            self._feats_dev = self.node_feats.to(device).t().contiguous()          # [N, L], uploaded once
         t = self.training
-        x = self._batch_norm(F.relu(self.conv1(self._feats_dev)), self.bn1, t)
-        x = self._batch_norm(F.relu(self.conv2(x)), self.bn2, t)
-        x = F.relu(self.fc(x.view(self.num_nodes, -1)))
+        e1 = None if t else self._eval_stats(self.bn1)
+        e2 = None if t else self._eval_stats(self.bn2)
+        y2n, s1, s2 = ops.TrunkConv.apply(self._feats_dev, self.conv1.weight, self.conv1.bias, self.bn1.weight, self.bn1.bias,
+                                          self.conv2.weight, self.conv2.bias, self.bn2.weight, self.bn2.bias, self.bn1.eps, t, e1, e2)
+        if t:
+            n, L0 = self._feats_dev.shape
+            self._update_running(self.bn1, s1[0], s1[1], n * (L0 - 9))
+            self._update_running(self.bn2, s2[0], s2[1], n * (L0 - 18))
+        x = F.relu(self.fc(y2n))
         return self._batch_norm(x, self.bn3, t)
 
     def get_k_nn_neighbor(self, data, k=11 * 207, metric="cosine"):

@@ -1,0 +1,502 @@
+// Discrete-graph-learning "global feature" trunk, convolutional part, fused forward + backward (fp32):
+//   x [N,1,L0] -> Conv1d(1,8,10) -> ReLU -> BatchNorm1d(8) -> Conv1d(8,16,10) -> ReLU -> BatchNorm1d(16) -> [N, 16*L2]
+// Reference: step/step_arch/discrete_graph_learning.py:131-133 (conv1/bn1/conv2/bn2; the module is in train(), so
+// both BatchNorms use batch statistics over the N nodes x L positions).
+//
+// The reference (cuDNN + ATen) materialises y1 = relu(conv1) [N,8,L1] and its normalised copy plus a dozen
+// elementwise temporaries of the 318 MB conv2 output.  Here y1 is never stored: conv1 is 10 MACs per value, so
+// it is recomputed inside every consumer (statistics pass, conv2 forward, conv2 backward, conv1 backward) from the
+// 20 MB input series, and BatchNorm1 is an affine applied on the fly.  Stored tensors: y2 (pre-BN2, needed for the
+// ReLU mask and x-hat in backward) and y2n (the Linear's input).
+#include "common.cuh"
+
+namespace stepk {
+
+constexpr int TK = 10;          // conv kernel width
+constexpr int C1 = 8, C2 = 16;
+constexpr int TL = 512;         // positions per tile
+constexpr int HALO = TK - 1;
+
+struct TrunkDims { int N, L0, L1, L2; };
+
+__device__ __forceinline__ void block_reduce_add_double(float v, double *dst, float *red) {
+  // red: >= 32 floats of smem; all threads call; adds the block sum of v to *dst
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float s = (l < (int)(blockDim.x >> 5)) ? red[l] : 0.f;
+    s = warp_sum(s);
+    if (l == 0) atomicAdd(dst, (double)s);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// F1: batch statistics of y1 = relu(conv1(x)) without storing it.  grid (ceil(L1/1024), N), 256 threads.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) trunk_conv1_stats_kernel(const float *__restrict__ x, TrunkDims d,
+                                                                const float *__restrict__ w1, const float *__restrict__ b1,
+                                                                double *__restrict__ sums /*[2][8]*/) {
+  __shared__ float xs[1024 + HALO];
+  __shared__ float ws[C1 * TK + C1];
+  __shared__ float red[32];
+  const int n = blockIdx.y, t0 = blockIdx.x * 1024, tid = threadIdx.x;
+  const float *xr = x + (size_t)n * d.L0;
+  for (int i = tid; i < 1024 + HALO; i += 256) xs[i] = (t0 + i < d.L0) ? xr[t0 + i] : 0.f;
+  if (tid < C1 * TK) ws[tid] = w1[tid];
+  if (tid < C1) ws[C1 * TK + tid] = b1[tid];
+  __syncthreads();
+  float s[C1], q[C1];
+#pragma unroll
+  for (int c = 0; c < C1; ++c) { s[c] = 0.f; q[c] = 0.f; }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int p = tid + 256 * j;
+    if (t0 + p < d.L1) {
+      float xv[TK];
+#pragma unroll
+      for (int k = 0; k < TK; ++k) xv[k] = xs[p + k];
+#pragma unroll
+      for (int c = 0; c < C1; ++c) {
+        float a = ws[C1 * TK + c];
+#pragma unroll
+        for (int k = 0; k < TK; ++k) a = fmaf(ws[c * TK + k], xv[k], a);
+        a = fmaxf(a, 0.f);
+        s[c] += a;
+        q[c] = fmaf(a, a, q[c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C1; ++c) {
+    block_reduce_add_double(s[c], sums + c, red);
+    block_reduce_add_double(q[c], sums + C1 + c, red);
+  }
+}
+
+// sums [2][C] (double) -> stats [4][C] floats: mean, biased var, scale = gamma*rstd, shift = beta - mean*scale
+__global__ void trunk_bn_finalize_kernel(const double *sums, double count, int C, const float *gamma, const float *beta,
+                                         float eps, float *stats) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[c] / count;
+  double var = sums[C + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  stats[c] = (float)mean;
+  stats[C + c] = (float)var;
+  stats[2 * C + c] = gamma[c] * rstd;
+  stats[3 * C + c] = beta[c] - (float)mean * gamma[c] * rstd;
+}
+
+// ---------------------------------------------------------------------------
+// shared tile helpers
+// ---------------------------------------------------------------------------
+// y1 (raw, post-ReLU) for `count` positions starting at y1-position p0 into dst[c][stride]; positions >= L1 give 0
+__device__ __forceinline__ void compute_y1_tile(const float *xs /* x at [p0, p0+count+HALO) */, const float *w1s,
+                                                const float *b1s, int p0, int count, int L1, float *dst, int stride,
+                                                const float *scale, const float *shift /* null: raw */) {
+  for (int idx = threadIdx.x; idx < C1 * count; idx += blockDim.x) {
+    const int c = idx / count, j = idx - c * count;
+    float a = 0.f;
+    if (p0 + j < L1 && p0 + j >= 0) {
+      a = b1s[c];
+#pragma unroll
+      for (int k = 0; k < TK; ++k) a = fmaf(w1s[c * TK + k], xs[j + k], a);
+      a = fmaxf(a, 0.f);
+      if (scale != nullptr) a = fmaf(a, scale[c], shift[c]);
+    }
+    dst[c * stride + j] = a;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// F2: y2 = relu(conv2(BN1(relu(conv1 x)))) (pre-BN2) + BN2 batch sums.  grid (ceil(L2/512), N), 256 threads.
+// ---------------------------------------------------------------------------
+constexpr int Y1W = TL + HALO;          // 521 y1 positions per tile
+constexpr int Y1S = Y1W + 3;            // smem row stride
+
+__global__ void __launch_bounds__(256) trunk_conv2_fwd_kernel(const float *__restrict__ x, TrunkDims d,
+                                                              const float *__restrict__ w1, const float *__restrict__ b1,
+                                                              const float *__restrict__ bn1 /*[4][8]*/,
+                                                              const float *__restrict__ w2, const float *__restrict__ b2,
+                                                              float *__restrict__ y2, double *__restrict__ sums2 /*[2][16] or null*/) {
+  __shared__ float xs[Y1W + HALO + 2];
+  __shared__ float y1s[C1 * Y1S];
+  __shared__ __align__(16) float w2s[C1 * TK * C2];   // [ci][k][co]
+  __shared__ float w1s[C1 * TK], b1s[C1], sc1[C1], sh1[C1], b2s[C2];
+  __shared__ float red[32];
+  const int n = blockIdx.y, t0 = blockIdx.x * TL, tid = threadIdx.x;
+  const float *xr = x + (size_t)n * d.L0;
+  for (int i = tid; i < Y1W + HALO; i += 256) xs[i] = (t0 + i < d.L0) ? xr[t0 + i] : 0.f;
+  for (int i = tid; i < C2 * C1 * TK; i += 256) {
+    const int co = i / (C1 * TK), r = i - co * (C1 * TK), ci = r / TK, k = r - ci * TK;
+    w2s[(ci * TK + k) * C2 + co] = w2[i];
+  }
+  if (tid < C1 * TK) w1s[tid] = w1[tid];
+  if (tid < C1) { b1s[tid] = b1[tid]; sc1[tid] = bn1[2 * C1 + tid]; sh1[tid] = bn1[3 * C1 + tid]; }
+  if (tid < C2) b2s[tid] = b2[tid];
+  __syncthreads();
+  compute_y1_tile(xs, w1s, b1s, t0, Y1W, d.L1, y1s, Y1S, sc1, sh1);
+  __syncthreads();
+
+  float acc[2][C2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int co = 0; co < C2; ++co) acc[j][co] = b2s[co];
+  const int p0 = tid, p1 = tid + 256;
+#pragma unroll 1
+  for (int ci = 0; ci < C1; ++ci) {
+    const float *yr = y1s + ci * Y1S;
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const float a0 = yr[p0 + k], a1 = yr[p1 + k];
+      const float4 *w = reinterpret_cast<const float4 *>(w2s + (ci * TK + k) * C2);
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 ww = w[c4];
+        acc[0][4 * c4] = fmaf(ww.x, a0, acc[0][4 * c4]); acc[0][4 * c4 + 1] = fmaf(ww.y, a0, acc[0][4 * c4 + 1]);
+        acc[0][4 * c4 + 2] = fmaf(ww.z, a0, acc[0][4 * c4 + 2]); acc[0][4 * c4 + 3] = fmaf(ww.w, a0, acc[0][4 * c4 + 3]);
+        acc[1][4 * c4] = fmaf(ww.x, a1, acc[1][4 * c4]); acc[1][4 * c4 + 1] = fmaf(ww.y, a1, acc[1][4 * c4 + 1]);
+        acc[1][4 * c4 + 2] = fmaf(ww.z, a1, acc[1][4 * c4 + 2]); acc[1][4 * c4 + 3] = fmaf(ww.w, a1, acc[1][4 * c4 + 3]);
+      }
+    }
+  }
+  float s[C2], q[C2];
+  const bool ok0 = t0 + p0 < d.L2, ok1 = t0 + p1 < d.L2;
+  float *yo = y2 + (size_t)n * C2 * d.L2 + t0;
+#pragma unroll
+  for (int co = 0; co < C2; ++co) {
+    const float v0 = fmaxf(acc[0][co], 0.f), v1 = fmaxf(acc[1][co], 0.f);
+    if (ok0) yo[(size_t)co * d.L2 + p0] = v0;
+    if (ok1) yo[(size_t)co * d.L2 + p1] = v1;
+    s[co] = (ok0 ? v0 : 0.f) + (ok1 ? v1 : 0.f);
+    q[co] = (ok0 ? v0 * v0 : 0.f) + (ok1 ? v1 * v1 : 0.f);
+  }
+  if (sums2 != nullptr) {
+#pragma unroll
+    for (int co = 0; co < C2; ++co) {
+      block_reduce_add_double(s[co], sums2 + co, red);
+      block_reduce_add_double(q[co], sums2 + C2 + co, red);
+    }
+  }
+}
+
+// F3: y2n = y2 * scale[c] + shift[c]   ([N][C][L] layout)
+__global__ void trunk_bn_apply_kernel(const float *__restrict__ y, long long total, int C, int L, const float *__restrict__ stats,
+                                      float *__restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)((i / L) % C);
+  out[i] = fmaf(y[i], stats[2 * C + c], stats[3 * C + c]);
+}
+
+// ---------------------------------------------------------------------------
+// B1: BatchNorm backward sums for one channel per blockIdx.x: S1 = sum dy, S2 = sum dy * xhat.
+// grid (C, 64): blockIdx.y strides over the N rows.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) trunk_bn_bwd_stats_kernel(const float *__restrict__ dy, const float *__restrict__ y, int N,
+                                                                 int C, int L, const float *__restrict__ stats, float eps,
+                                                                 double *__restrict__ sums /*[2][C]*/) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  const float mean = stats[c], rstd = 1.0f / sqrtf(stats[C + c] + eps);
+  float s1 = 0.f, s2 = 0.f;
+  for (int n = blockIdx.y; n < N; n += gridDim.y) {
+    const float *dr = dy + ((size_t)n * C + c) * L, *yr = y + ((size_t)n * C + c) * L;
+    for (int l = threadIdx.x; l < L; l += 256) {
+      const float g = dr[l];
+      s1 += g;
+      s2 = fmaf(g, (yr[l] - mean) * rstd, s2);
+    }
+  }
+  block_reduce_add_double(s1, sums + c, red);
+  block_reduce_add_double(s2, sums + C + c, red);
+}
+
+// coefficient table for BN backward: coef [5][C] = gamma*rstd, S1/M, S2/M, mean, rstd; also dgamma = S2, dbeta = S1
+__global__ void trunk_bn_bwd_finalize_kernel(const double *sums, double count, int C, const float *gamma, const float *stats,
+                                             float eps, float *coef, float *dgamma, float *dbeta) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  const float rstd = 1.0f / sqrtf(stats[C + c] + eps);
+  coef[c] = gamma[c] * rstd;
+  coef[C + c] = (float)(sums[c] / count);
+  coef[2 * C + c] = (float)(sums[C + c] / count);
+  coef[3 * C + c] = stats[c];
+  coef[4 * C + c] = rstd;
+  dgamma[c] = (float)sums[C + c];
+  dbeta[c] = (float)sums[c];
+}
+
+// ---------------------------------------------------------------------------
+// B2: backward through BN2 -> ReLU -> conv2: d(y1n) [N,8,L1], dW2, db2, and the BN1 backward sums.
+// grid (ceil(L1/512), N), 256 threads, dynamic smem.
+// ---------------------------------------------------------------------------
+constexpr int DPW = TL + HALO;     // 521 dpre2 positions [t0-9, t0+512)
+constexpr int DPS = DPW + 3;
+
+__global__ void __launch_bounds__(256) trunk_conv2_bwd_kernel(const float *__restrict__ x, TrunkDims d,
+                                                              const float *__restrict__ w1, const float *__restrict__ b1,
+                                                              const float *__restrict__ bn1 /*[4][8]*/, float eps,
+                                                              const float *__restrict__ w2, const float *__restrict__ dy2n,
+                                                              const float *__restrict__ y2, const float *__restrict__ coef2 /*[5][16]*/,
+                                                              float *__restrict__ dy1n, float *__restrict__ dw2,
+                                                              float *__restrict__ db2, double *__restrict__ sums1 /*[2][8]*/) {
+  extern __shared__ __align__(16) float sm[];
+  float *dp_cl = sm;                         // [16][DPS]      dpre2 by channel (for the transposed conv)
+  float *dp_lc = dp_cl + C2 * DPS;           // [DPW][16]      dpre2 by position (broadcast reads for dW2)
+  float *y1s = dp_lc + DPW * C2;             // [8][Y1S]       normalised y1 at [t0, t0+521)
+  float *y1r = y1s + C1 * Y1S;               // [8][TL]        raw y1 at [t0, t0+512) for x-hat
+  float *xs = y1r + C1 * TL;                 // [Y1W + HALO + 2]
+  float *w2t = xs + (Y1W + HALO + 2 + 3) / 4 * 4;   // [co][k][ci]  (8 contiguous ci)
+  float *w1s = w2t + C2 * TK * C1;           // 80
+  float *b1s = w1s + C1 * TK;                // 8
+  float *sc1 = b1s + C1, *sh1 = sc1 + C1;    // 8 + 8
+  float *red = sh1 + C1;                     // 32
+  const int n = blockIdx.y, t0 = blockIdx.x * TL, tid = threadIdx.x;
+  const float *xr = x + (size_t)n * d.L0;
+  for (int i = tid; i < Y1W + HALO; i += 256) xs[i] = (t0 + i < d.L0) ? xr[t0 + i] : 0.f;
+  for (int i = tid; i < C2 * C1 * TK; i += 256) {
+    const int co = i / (C1 * TK), r = i - co * (C1 * TK), ci = r / TK, k = r - ci * TK;
+    w2t[(co * TK + k) * C1 + ci] = w2[i];
+  }
+  if (tid < C1 * TK) w1s[tid] = w1[tid];
+  if (tid < C1) { b1s[tid] = b1[tid]; sc1[tid] = bn1[2 * C1 + tid]; sh1[tid] = bn1[3 * C1 + tid]; }
+  // dpre2 tile: position j <-> l = t0 - 9 + j
+  for (int idx = tid; idx < C2 * DPW; idx += 256) {
+    const int co = idx / DPW, j = idx - co * DPW, l = t0 - HALO + j;
+    float v = 0.f;
+    if (l >= 0 && l < d.L2) {
+      const size_t off = ((size_t)n * C2 + co) * d.L2 + l;
+      const float yv = y2[off];
+      if (yv > 0.f) {
+        const float xhat = (yv - coef2[3 * C2 + co]) * coef2[4 * C2 + co];
+        v = coef2[co] * (dy2n[off] - coef2[C2 + co] - xhat * coef2[2 * C2 + co]);
+      }
+    }
+    dp_cl[co * DPS + j] = v;
+    dp_lc[j * C2 + co] = v;
+  }
+  __syncthreads();
+  compute_y1_tile(xs, w1s, b1s, t0, Y1W, d.L1, y1s, Y1S, sc1, sh1);
+  compute_y1_tile(xs, w1s, b1s, t0, TL, d.L1, y1r, TL, nullptr, nullptr);
+  __syncthreads();
+
+  // ---- d(y1n)[ci][l'] = sum_co sum_k w2[co][ci][k] dpre2[co][l'-k];  l' = t0 + p, dpre2 index j = p - k + 9 ----
+  {
+    float acc[2][C1];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int ci = 0; ci < C1; ++ci) acc[j][ci] = 0.f;
+    const int p0 = tid, p1 = tid + 256;
+#pragma unroll 1
+    for (int co = 0; co < C2; ++co) {
+      const float *dr = dp_cl + co * DPS + HALO;
+#pragma unroll
+      for (int k = 0; k < TK; ++k) {
+        const float a0 = dr[p0 - k], a1 = dr[p1 - k];
+        const float4 *w = reinterpret_cast<const float4 *>(w2t + (co * TK + k) * C1);
+        const float4 wa = w[0], wb = w[1];
+        acc[0][0] = fmaf(wa.x, a0, acc[0][0]); acc[0][1] = fmaf(wa.y, a0, acc[0][1]);
+        acc[0][2] = fmaf(wa.z, a0, acc[0][2]); acc[0][3] = fmaf(wa.w, a0, acc[0][3]);
+        acc[0][4] = fmaf(wb.x, a0, acc[0][4]); acc[0][5] = fmaf(wb.y, a0, acc[0][5]);
+        acc[0][6] = fmaf(wb.z, a0, acc[0][6]); acc[0][7] = fmaf(wb.w, a0, acc[0][7]);
+        acc[1][0] = fmaf(wa.x, a1, acc[1][0]); acc[1][1] = fmaf(wa.y, a1, acc[1][1]);
+        acc[1][2] = fmaf(wa.z, a1, acc[1][2]); acc[1][3] = fmaf(wa.w, a1, acc[1][3]);
+        acc[1][4] = fmaf(wb.x, a1, acc[1][4]); acc[1][5] = fmaf(wb.y, a1, acc[1][5]);
+        acc[1][6] = fmaf(wb.z, a1, acc[1][6]); acc[1][7] = fmaf(wb.w, a1, acc[1][7]);
+      }
+    }
+    const bool ok0 = t0 + p0 < d.L1, ok1 = t0 + p1 < d.L1;
+    float *o = dy1n + (size_t)n * C1 * d.L1 + t0;
+    float s1[C1], s2[C1];
+#pragma unroll
+    for (int ci = 0; ci < C1; ++ci) {
+      const float mean = bn1[ci], rstd = 1.0f / sqrtf(bn1[C1 + ci] + eps);
+      float a = 0.f, b = 0.f;
+      if (ok0) {
+        o[(size_t)ci * d.L1 + p0] = acc[0][ci];
+        a += acc[0][ci];
+        b = fmaf(acc[0][ci], (y1r[ci * TL + p0] - mean) * rstd, b);
+      }
+      if (ok1) {
+        o[(size_t)ci * d.L1 + p1] = acc[1][ci];
+        a += acc[1][ci];
+        b = fmaf(acc[1][ci], (y1r[ci * TL + p1] - mean) * rstd, b);
+      }
+      s1[ci] = a; s2[ci] = b;
+    }
+#pragma unroll
+    for (int ci = 0; ci < C1; ++ci) {
+      block_reduce_add_double(s1[ci], sums1 + ci, red);
+      block_reduce_add_double(s2[ci], sums1 + C1 + ci, red);
+    }
+  }
+
+  // ---- dW2[co][ci][k] += sum_{l in own range} dpre2[co][l] y1n[ci][l+k];  own l = t0 + p, p in [0,512) ----
+  // thread = (ci, k) pair x one of 3 position segments, 16 output channels in registers
+  if (tid < 240) {
+    const int pair = tid % 80, seg = tid / 80, ci = pair / TK, k = pair - ci * TK;
+    const int pbeg = seg * 171, pend = min(TL, pbeg + 171);
+    float acc[C2];
+#pragma unroll
+    for (int co = 0; co < C2; ++co) acc[co] = 0.f;
+    for (int p = pbeg; p < pend; ++p) {
+      const float yv = y1s[ci * Y1S + p + k];
+      const float4 *dpp = reinterpret_cast<const float4 *>(dp_lc + (p + HALO) * C2);
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 g = dpp[c4];
+        acc[4 * c4] = fmaf(g.x, yv, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(g.y, yv, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(g.z, yv, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(g.w, yv, acc[4 * c4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < C2; ++co) atomicAdd(dw2 + (co * C1 + ci) * TK + k, acc[co]);
+  }
+  // ---- db2[co] += sum over own range ----
+  if (tid < C2 * 16) {
+    const int co = tid >> 4, part = tid & 15;
+    float s = 0.f;
+    for (int p = part; p < TL; p += 16) s += dp_cl[co * DPS + HALO + p];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (part == 0) atomicAdd(db2 + co, s);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// B3: backward through BN1 -> ReLU -> conv1: dW1 [8][10], db1 [8].  grid (ceil(L1/1024), N), 256 threads.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) trunk_conv1_bwd_kernel(const float *__restrict__ x, TrunkDims d,
+                                                              const float *__restrict__ w1, const float *__restrict__ b1,
+                                                              const float *__restrict__ dy1n, const float *__restrict__ coef1 /*[5][8]*/,
+                                                              float *__restrict__ dw1, float *__restrict__ db1) {
+  __shared__ float xs[1024 + HALO];
+  __shared__ float ws[C1 * TK + C1];
+  __shared__ float accs[C1 * TK + C1];
+  const int n = blockIdx.y, t0 = blockIdx.x * 1024, tid = threadIdx.x;
+  const float *xr = x + (size_t)n * d.L0;
+  for (int i = tid; i < 1024 + HALO; i += 256) xs[i] = (t0 + i < d.L0) ? xr[t0 + i] : 0.f;
+  if (tid < C1 * TK) ws[tid] = w1[tid];
+  if (tid < C1) ws[C1 * TK + tid] = b1[tid];
+  if (tid < C1 * TK + C1) accs[tid] = 0.f;
+  __syncthreads();
+  // one channel at a time keeps the register footprint small: 10 weight-grad accumulators + 1 bias-grad
+#pragma unroll 1
+  for (int c = 0; c < C1; ++c) {
+    float gw[TK], gb = 0.f;
+#pragma unroll
+    for (int k = 0; k < TK; ++k) gw[k] = 0.f;
+    const float a1 = coef1[c], s1m = coef1[C1 + c], s2m = coef1[2 * C1 + c], mean = coef1[3 * C1 + c], rstd = coef1[4 * C1 + c];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int p = tid + 256 * j;
+      if (t0 + p < d.L1) {
+        float xv[TK];
+#pragma unroll
+        for (int k = 0; k < TK; ++k) xv[k] = xs[p + k];
+        float a = ws[C1 * TK + c];
+#pragma unroll
+        for (int k = 0; k < TK; ++k) a = fmaf(ws[c * TK + k], xv[k], a);
+        if (a > 0.f) {
+          const float xhat = (a - mean) * rstd;
+          const float g = a1 * (dy1n[((size_t)n * C1 + c) * d.L1 + t0 + p] - s1m - xhat * s2m);
+          gb += g;
+#pragma unroll
+          for (int k = 0; k < TK; ++k) gw[k] = fmaf(g, xv[k], gw[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const float v = warp_sum(gw[k]);
+      if ((tid & 31) == 0) atomicAdd(&accs[c * TK + k], v);
+    }
+    gb = warp_sum(gb);
+    if ((tid & 31) == 0) atomicAdd(&accs[C1 * TK + c], gb);
+  }
+  __syncthreads();
+  if (tid < C1 * TK) atomicAdd(dw1 + tid, accs[tid]);
+  else if (tid < C1 * TK + C1) atomicAdd(db1 + (tid - C1 * TK), accs[tid]);
+}
+
+static size_t conv2_bwd_smem() {
+  size_t f = (size_t)C2 * DPS + (size_t)DPW * C2 + (size_t)C1 * Y1S + (size_t)C1 * TL + (Y1W + HALO + 2 + 3) / 4 * 4 +
+             C2 * TK * C1 + C1 * TK + 3 * C1 + 32;
+  return f * sizeof(float);
+}
+
+}  // namespace stepk
+
+using namespace stepk;
+
+// scratch: 2*(2*8) + 2*(2*16) doubles then coefficient tables; the caller provides >= 4096 bytes, zeroed by us
+extern "C" int step_dgl_conv_fwd(const float *x, int N, int L0, const float *w1, const float *b1, const float *g1,
+                                 const float *be1, const float *w2, const float *b2, const float *g2, const float *be2,
+                                 float eps, int training, float *bn1_stats /*[4][8]*/, float *bn2_stats /*[4][16]*/,
+                                 float *y2, float *y2n, void *scratch, void *stream) {
+  STEP_REQUIRE(x && w1 && b1 && g1 && be1 && w2 && b2 && g2 && be2 && bn1_stats && bn2_stats && y2 && y2n && scratch,
+               "dgl_conv_fwd: null pointer");
+  STEP_REQUIRE(N > 0 && N <= 65535 && L0 > 2 * HALO, "dgl_conv_fwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const TrunkDims d{N, L0, L0 - HALO, L0 - 2 * HALO};
+  double *sums = reinterpret_cast<double *>(scratch);   // [0,16): bn1, [16,48): bn2
+  if (training) {
+    cudaError_t e = cudaMemsetAsync(sums, 0, 48 * sizeof(double), st);
+    if (e != cudaSuccess) return fail_msg((int)e, cudaGetErrorString(e));
+    trunk_conv1_stats_kernel<<<dim3((d.L1 + 1023) / 1024, N), 256, 0, st>>>(x, d, w1, b1, sums);
+    STEP_LAUNCH_CHECK("trunk_conv1_stats_kernel");
+    trunk_bn_finalize_kernel<<<1, 32, 0, st>>>(sums, (double)N * d.L1, C1, g1, be1, eps, bn1_stats);
+    STEP_LAUNCH_CHECK("trunk_bn_finalize_kernel");
+  }
+  trunk_conv2_fwd_kernel<<<dim3((d.L2 + TL - 1) / TL, N), 256, 0, st>>>(x, d, w1, b1, bn1_stats, w2, b2, y2,
+                                                                        training ? sums + 16 : nullptr);
+  STEP_LAUNCH_CHECK("trunk_conv2_fwd_kernel");
+  if (training) {
+    trunk_bn_finalize_kernel<<<1, 32, 0, st>>>(sums + 16, (double)N * d.L2, C2, g2, be2, eps, bn2_stats);
+    STEP_LAUNCH_CHECK("trunk_bn_finalize_kernel");
+  }
+  const long long total = (long long)N * C2 * d.L2;
+  trunk_bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(y2, total, C2, d.L2, bn2_stats, y2n);
+  return check_launch("trunk_bn_apply_kernel");
+}
+
+extern "C" int step_dgl_conv_bwd(const float *dy2n, const float *x, int N, int L0, const float *w1, const float *b1,
+                                 const float *g1, const float *w2, const float *g2, float eps, const float *bn1_stats,
+                                 const float *bn2_stats, const float *y2, float *dy1n_scratch, float *dw1, float *db1,
+                                 float *dg1, float *dbe1, float *dw2, float *db2, float *dg2, float *dbe2, void *scratch,
+                                 void *stream) {
+  STEP_REQUIRE(dy2n && x && w1 && b1 && g1 && w2 && g2 && bn1_stats && bn2_stats && y2 && dy1n_scratch && dw1 && db1 && dg1 &&
+                   dbe1 && dw2 && db2 && dg2 && dbe2 && scratch,
+               "dgl_conv_bwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const TrunkDims d{N, L0, L0 - HALO, L0 - 2 * HALO};
+  double *sums = reinterpret_cast<double *>(scratch);          // [0,16): bn1 bwd, [16,48): bn2 bwd
+  float *coef1 = reinterpret_cast<float *>(sums + 48);         // [5][8]
+  float *coef2 = coef1 + 5 * C1;                               // [5][16]
+  cudaError_t e = cudaMemsetAsync(sums, 0, 48 * sizeof(double), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dw1, 0, C1 * TK * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(db1, 0, C1 * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dw2, 0, C2 * C1 * TK * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(db2, 0, C2 * sizeof(float), st);
+  if (e != cudaSuccess) return fail_msg((int)e, cudaGetErrorString(e));
+  trunk_bn_bwd_stats_kernel<<<dim3(C2, 64), 256, 0, st>>>(dy2n, y2, N, C2, d.L2, bn2_stats, eps, sums + 16);
+  STEP_LAUNCH_CHECK("trunk_bn_bwd_stats_kernel");
+  trunk_bn_bwd_finalize_kernel<<<1, 32, 0, st>>>(sums + 16, (double)N * d.L2, C2, g2, bn2_stats, eps, coef2, dg2, dbe2);
+  STEP_LAUNCH_CHECK("trunk_bn_bwd_finalize_kernel");
+  int rc = allow_smem(trunk_conv2_bwd_kernel, conv2_bwd_smem());
+  if (rc) return rc;
+  trunk_conv2_bwd_kernel<<<dim3((d.L1 + TL - 1) / TL, N), 256, conv2_bwd_smem(), st>>>(x, d, w1, b1, bn1_stats, eps, w2, dy2n, y2,
+                                                                                       coef2, dy1n_scratch, dw2, db2, sums);
+  STEP_LAUNCH_CHECK("trunk_conv2_bwd_kernel");
+  trunk_bn_bwd_finalize_kernel<<<1, 32, 0, st>>>(sums, (double)N * d.L1, C1, g1, bn1_stats, eps, coef1, dg1, dbe1);
+  STEP_LAUNCH_CHECK("trunk_bn_bwd_finalize_kernel");
+  trunk_conv1_bwd_kernel<<<dim3((d.L1 + 1023) / 1024, N), 256, 0, st>>>(x, d, w1, b1, dy1n_scratch, coef1, dw1, db1);
+  return check_launch("trunk_conv1_bwd_kernel");
+}

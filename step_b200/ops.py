@@ -388,3 +388,56 @@ def ts_encoder_forward_bf16(series: Tensor, patch_w: Tensor, patch_b: Tensor, po
                                         ws_bytes, float(drop_p), int(seed) & (2**64 - 1), st), "step_ts_encoder_fwd_bf16")
     launch_counter["kernels"] += 1 + len(layers) * 5
     return hidden
+
+
+# --------------------------------------------------------------------------- #
+# discrete graph learning trunk (conv1 -> BN -> conv2 -> BN)
+# --------------------------------------------------------------------------- #
+class TrunkConv(torch.autograd.Function):
+    """x [N, L0] -> (y2n [N, 16*(L0-18)], bn1_stats [4,8], bn2_stats [4,16]).  Parameters: conv1.w/b, bn1.w/b, conv2.w/b, bn2.w/b."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, g1, be1, w2, b2, g2, be2, eps, training, eval_stats1, eval_stats2):
+        x = _f32(x, "x")
+        prm = [_f32(t, "trunk param") for t in (w1, b1, g1, be1, w2, b2, g2, be2)]
+        N, L0 = x.shape
+        L2 = L0 - 18
+        st = _enter(x)
+        dev = x.device
+        if training:
+            s1 = torch.empty(4, 8, device=dev, dtype=torch.float32)
+            s2 = torch.empty(4, 16, device=dev, dtype=torch.float32)
+        else:
+            s1, s2 = _f32(eval_stats1, "eval_stats1"), _f32(eval_stats2, "eval_stats2")
+        y2 = torch.empty(N, 16, L2, device=dev, dtype=torch.float32)
+        y2n = torch.empty(N, 16, L2, device=dev, dtype=torch.float32)
+        scratch = torch.empty(4096, device=dev, dtype=torch.uint8)
+        check(_L().step_dgl_conv_fwd(x.data_ptr(), N, L0, *[t.data_ptr() for t in prm], float(eps), 1 if training else 0,
+                                     s1.data_ptr(), s2.data_ptr(), y2.data_ptr(), y2n.data_ptr(), scratch.data_ptr(), st),
+              "step_dgl_conv_fwd")
+        launch_counter["kernels"] += 5 if training else 2
+        ctx.save_for_backward(x, y2, s1, s2, *prm)
+        ctx.eps, ctx.training = float(eps), bool(training)
+        ctx.mark_non_differentiable(s1, s2)
+        return y2n.view(N, 16 * L2), s1, s2
+
+    @staticmethod
+    def backward(ctx, dy2n, _d1, _d2):
+        if not ctx.training:
+            raise _lib.StepB200Error("TrunkConv: backward is only defined in training mode (batch statistics)")
+        x, y2, s1, s2, w1, b1, g1, be1, w2, b2, g2, be2 = ctx.saved_tensors
+        N, L0 = x.shape
+        dy2n = _f32(dy2n, "dy2n")
+        st = _enter(x)
+        dev = x.device
+        grads = [torch.empty_like(t) for t in (w1, b1, g1, be1, w2, b2, g2, be2)]
+        dy1n = torch.empty(N, 8, L0 - 9, device=dev, dtype=torch.float32)
+        scratch = torch.empty(4096, device=dev, dtype=torch.uint8)
+        dw1, db1, dg1, dbe1, dw2, db2, dg2, dbe2 = grads
+        check(_L().step_dgl_conv_bwd(dy2n.data_ptr(), x.data_ptr(), N, L0, w1.data_ptr(), b1.data_ptr(), g1.data_ptr(),
+                                     w2.data_ptr(), g2.data_ptr(), ctx.eps, s1.data_ptr(), s2.data_ptr(), y2.data_ptr(),
+                                     dy1n.data_ptr(), dw1.data_ptr(), db1.data_ptr(), dg1.data_ptr(), dbe1.data_ptr(),
+                                     dw2.data_ptr(), db2.data_ptr(), dg2.data_ptr(), dbe2.data_ptr(), scratch.data_ptr(), st),
+              "step_dgl_conv_bwd")
+        launch_counter["kernels"] += 5
+        return (None, *grads, None, None, None, None)

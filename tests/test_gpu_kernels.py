@@ -300,3 +300,54 @@ def test_gwnet_eval_mode_and_dropout():
     c = model(history.to(DEV), hidden_last.to(DEV), adj.to(DEV)).detach()
     assert not torch.equal(a, c)
     assert torch.isfinite(a).all()
+
+
+# --------------------------------------------------------------------------- DGL trunk (conv1/bn1/conv2/bn2)
+@pytest.mark.parametrize("N,L0", [(5, 700), (7, 2100), (33, 1543)])
+def test_trunk_conv_fwd_bwd(N, L0):
+    from step_b200 import ops
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(N + L0)
+    x = torch.randn(N, L0, generator=g)
+    prm = {"w1": torch.randn(8, 1, 10, generator=g) * 0.3, "b1": torch.randn(8, generator=g) * 0.1,
+           "g1": torch.rand(8, generator=g) + 0.5, "be1": torch.randn(8, generator=g) * 0.1,
+           "w2": torch.randn(16, 8, 10, generator=g) * 0.1, "b2": torch.randn(16, generator=g) * 0.1,
+           "g2": torch.rand(16, generator=g) + 0.5, "be2": torch.randn(16, generator=g) * 0.1}
+    sd = {"discrete_graph_learning." + k: v for k, v in
+          {"conv1.weight": prm["w1"], "conv1.bias": prm["b1"], "bn1.weight": prm["g1"], "bn1.bias": prm["be1"],
+           "conv2.weight": prm["w2"], "conv2.bias": prm["b2"], "bn2.weight": prm["g2"], "bn2.bias": prm["be2"]}.items()}
+    leaves = {k: v.clone().double().requires_grad_(True) for k, v in sd.items()}    # fp64 oracle arithmetic
+    p = "discrete_graph_learning."
+    xx = x.double().unsqueeze(1)
+    y = O._bn(leaves, p + "bn1.", torch.relu(F.conv1d(xx, leaves[p + "conv1.weight"], leaves[p + "conv1.bias"])), True)
+    y = O._bn(leaves, p + "bn2.", torch.relu(F.conv1d(y, leaves[p + "conv2.weight"], leaves[p + "conv2.bias"])), True)
+    ref = y.reshape(N, -1)
+    wgt = torch.randn(ref.shape, generator=g).double()
+    (ref * wgt).sum().backward()
+    d = {k: v.to(DEV).requires_grad_(True) for k, v in prm.items()}
+    out, s1, s2 = ops.TrunkConv.apply(x.to(DEV), d["w1"], d["b1"], d["g1"], d["be1"], d["w2"], d["b2"], d["g2"], d["be2"],
+                                      1e-5, True, None, None)
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() < 2e-4
+    (out * wgt.float().to(DEV)).sum().backward()
+    names = {"w1": "conv1.weight", "b1": "conv1.bias", "g1": "bn1.weight", "be1": "bn1.bias",
+             "w2": "conv2.weight", "b2": "conv2.bias", "g2": "bn2.weight", "be2": "bn2.bias"}
+    gmax = max(float(v.grad.abs().max()) for v in leaves.values())
+    for k, nme in names.items():
+        rg = leaves[p + nme].grad
+        err = (d[k].grad.cpu().double() - rg).abs().max().item() / max(float(rg.abs().max()), 1e-4 * gmax)
+        # conv biases in front of a train-mode BatchNorm have an (almost) zero gradient: cancellation noise
+        assert err < (5e-2 if k in ("b1", "b2") else 3e-3), (k, err)
+    # eval mode with given running statistics
+    st1 = torch.stack([torch.randn(8, generator=g) * 0.1, torch.rand(8, generator=g) + 0.5, torch.zeros(8), torch.zeros(8)])
+    st2 = torch.stack([torch.randn(16, generator=g) * 0.1, torch.rand(16, generator=g) + 0.5, torch.zeros(16), torch.zeros(16)])
+    for st, gm, be in ((st1, prm["g1"], prm["be1"]), (st2, prm["g2"], prm["be2"])):
+        st[2] = gm / torch.sqrt(st[1] + 1e-5)
+        st[3] = be - st[0] * st[2]
+    ev = dict(sd)
+    ev.update({p + "bn1.running_mean": st1[0], p + "bn1.running_var": st1[1], p + "bn2.running_mean": st2[0], p + "bn2.running_var": st2[1]})
+    y = O._bn(ev, p + "bn1.", torch.relu(F.conv1d(x.unsqueeze(1), prm["w1"], prm["b1"])), False)
+    y = O._bn(ev, p + "bn2.", torch.relu(F.conv1d(y, prm["w2"], prm["b2"])), False)
+    with torch.no_grad():
+        out_e, _, _ = ops.TrunkConv.apply(x.to(DEV), *[prm[k].to(DEV) for k in ("w1", "b1", "g1", "be1", "w2", "b2", "g2", "be2")],
+                                          1e-5, False, st1.to(DEV), st2.to(DEV))
+    assert (out_e.cpu() - y.reshape(N, -1)).abs().max().item() < 2e-4
