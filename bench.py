@@ -170,10 +170,10 @@ def main():
         raise SystemExit("bench.py: no CUDA device - the B200-native path has no CPU fallback "
                          "(use --impl reference for the CPU comparator)")
     import torch.distributed as dist
+    from step_b200 import parallel
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    parallel.init_from_env("nccl")
 
     from oracle import step_oracle as O          # only for the deterministic synthetic tensors + the CPU leg
     from step.step_arch import STEP
@@ -200,7 +200,7 @@ def main():
     if args.no_dropout:
         model.tsformer.dropout_p = 0.0
         model.backend.dropout = 0.0
-    trainable = [p for p in model.parameters() if p.requires_grad]
+    reducer = parallel.FlatGradReducer(model.parameters(), world)    # all trainable grads in one flat buffer
 
     torch.manual_seed(1234 + rank)
     n_host = 4                                    # rotate a few distinct host batches (inputs differ step to step)
@@ -215,13 +215,9 @@ def main():
         y_hat, theta, adj_knn, coeff = model(history_data=history, long_history_data=long_history, future_data=None,
                                              batch_seen=0, epoch=1)
         loss = step_loss(y_hat[..., [0]], future[..., [0]], theta, adj_knn, coeff, null_val=0.0)
-        for p in trainable:
-            p.grad = None
+        reducer.zero()
         loss.backward()
-        if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in trainable if p.grad is not None])
-            dist.all_reduce(flat)
-            flat.div_(world)
+        reducer.reduce()                          # one NCCL all-reduce of the flat gradient buffer when world > 1
         return loss
 
     def barrier():

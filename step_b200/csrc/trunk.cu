@@ -257,15 +257,26 @@ __global__ void __launch_bounds__(256) trunk_conv2_bwd_kernel(const float *__res
   float *b1s = w1s + C1 * TK;                // 8
   float *sc1 = b1s + C1, *sh1 = sc1 + C1;    // 8 + 8
   float *red = sh1 + C1;                     // 32
-  const int n = blockIdx.y, t0 = blockIdx.x * TL, tid = threadIdx.x;
+  const int n = blockIdx.y, tid = threadIdx.x;
   const float *xr = x + (size_t)n * d.L0;
-  for (int i = tid; i < Y1W + HALO; i += 256) xs[i] = (t0 + i < d.L0) ? xr[t0 + i] : 0.f;
   for (int i = tid; i < C2 * C1 * TK; i += 256) {
     const int co = i / (C1 * TK), r = i - co * (C1 * TK), ci = r / TK, k = r - ci * TK;
     w2t[(co * TK + k) * C1 + ci] = w2[i];
   }
   if (tid < C1 * TK) w1s[tid] = w1[tid];
   if (tid < C1) { b1s[tid] = b1[tid]; sc1[tid] = bn1[2 * C1 + tid]; sh1[tid] = bn1[3 * C1 + tid]; }
+  // weight / bias gradient partials stay in registers across the tiles of this CTA (one atomic flush at the end:
+  // per-tile atomics to the 1280 dW2 addresses serialise in L2)
+  float accw[C2], accb = 0.f, s1acc[C1], s2acc[C1];
+#pragma unroll
+  for (int co = 0; co < C2; ++co) accw[co] = 0.f;
+#pragma unroll
+  for (int ci = 0; ci < C1; ++ci) { s1acc[ci] = 0.f; s2acc[ci] = 0.f; }
+  const int ntiles = (d.L1 + TL - 1) / TL;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const int t0 = tile * TL;
+  __syncthreads();
+  for (int i = tid; i < Y1W + HALO; i += 256) xs[i] = (t0 + i < d.L0) ? xr[t0 + i] : 0.f;
   // dpre2 tile: position j <-> l = t0 - 9 + j
   for (int idx = tid; idx < C2 * DPW; idx += 256) {
     const int co = idx / DPW, j = idx - co * DPW, l = t0 - HALO + j;
@@ -314,7 +325,6 @@ __global__ void __launch_bounds__(256) trunk_conv2_bwd_kernel(const float *__res
     }
     const bool ok0 = t0 + p0 < d.L1, ok1 = t0 + p1 < d.L1;
     float *o = dy1n + (size_t)n * C1 * d.L1 + t0;
-    float s1[C1], s2[C1];
 #pragma unroll
     for (int ci = 0; ci < C1; ++ci) {
       const float mean = bn1[ci], rstd = 1.0f / sqrtf(bn1[C1 + ci] + eps);
@@ -329,12 +339,7 @@ __global__ void __launch_bounds__(256) trunk_conv2_bwd_kernel(const float *__res
         a += acc[1][ci];
         b = fmaf(acc[1][ci], (y1r[ci * TL + p1] - mean) * rstd, b);
       }
-      s1[ci] = a; s2[ci] = b;
-    }
-#pragma unroll
-    for (int ci = 0; ci < C1; ++ci) {
-      block_reduce_add_double(s1[ci], sums1 + ci, red);
-      block_reduce_add_double(s2[ci], sums1 + C1 + ci, red);
+      s1acc[ci] += a; s2acc[ci] += b;
     }
   }
 
@@ -343,30 +348,39 @@ __global__ void __launch_bounds__(256) trunk_conv2_bwd_kernel(const float *__res
   if (tid < 240) {
     const int pair = tid % 80, seg = tid / 80, ci = pair / TK, k = pair - ci * TK;
     const int pbeg = seg * 171, pend = min(TL, pbeg + 171);
-    float acc[C2];
-#pragma unroll
-    for (int co = 0; co < C2; ++co) acc[co] = 0.f;
     for (int p = pbeg; p < pend; ++p) {
       const float yv = y1s[ci * Y1S + p + k];
       const float4 *dpp = reinterpret_cast<const float4 *>(dp_lc + (p + HALO) * C2);
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
         const float4 g = dpp[c4];
-        acc[4 * c4] = fmaf(g.x, yv, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(g.y, yv, acc[4 * c4 + 1]);
-        acc[4 * c4 + 2] = fmaf(g.z, yv, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(g.w, yv, acc[4 * c4 + 3]);
+        accw[4 * c4] = fmaf(g.x, yv, accw[4 * c4]); accw[4 * c4 + 1] = fmaf(g.y, yv, accw[4 * c4 + 1]);
+        accw[4 * c4 + 2] = fmaf(g.z, yv, accw[4 * c4 + 2]); accw[4 * c4 + 3] = fmaf(g.w, yv, accw[4 * c4 + 3]);
       }
     }
-#pragma unroll
-    for (int co = 0; co < C2; ++co) atomicAdd(dw2 + (co * C1 + ci) * TK + k, acc[co]);
   }
-  // ---- db2[co] += sum over own range ----
-  if (tid < C2 * 16) {
+  // ---- db2[co] partial over own range: thread = (co, 16-way position split) ----
+  {
     const int co = tid >> 4, part = tid & 15;
-    float s = 0.f;
-    for (int p = part; p < TL; p += 16) s += dp_cl[co * DPS + HALO + p];
+    for (int p = part; p < TL; p += 16) accb += dp_cl[co * DPS + HALO + p];
+  }
+  }  // tile loop
+
+  if (tid < 240) {
+    const int pair = tid % 80, ci = pair / TK, k = pair - ci * TK;
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (part == 0) atomicAdd(db2 + co, s);
+    for (int co = 0; co < C2; ++co) atomicAdd(dw2 + (co * C1 + ci) * TK + k, accw[co]);
+  }
+  {
+    const int co = tid >> 4, part = tid & 15;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) accb += __shfl_xor_sync(0xffffffffu, accb, o);
+    if (part == 0) atomicAdd(db2 + co, accb);
+  }
+#pragma unroll
+  for (int ci = 0; ci < C1; ++ci) {
+    block_reduce_add_double(s1acc[ci], sums1 + ci, red);
+    block_reduce_add_double(s2acc[ci], sums1 + C1 + ci, red);
   }
 }
 
@@ -492,7 +506,7 @@ extern "C" int step_dgl_conv_bwd(const float *dy2n, const float *x, int N, int L
   STEP_LAUNCH_CHECK("trunk_bn_bwd_finalize_kernel");
   int rc = allow_smem(trunk_conv2_bwd_kernel, conv2_bwd_smem());
   if (rc) return rc;
-  trunk_conv2_bwd_kernel<<<dim3((d.L1 + TL - 1) / TL, N), 256, conv2_bwd_smem(), st>>>(x, d, w1, b1, bn1_stats, eps, w2, dy2n, y2,
+  trunk_conv2_bwd_kernel<<<dim3(6, N), 256, conv2_bwd_smem(), st>>>(x, d, w1, b1, bn1_stats, eps, w2, dy2n, y2,
                                                                                        coef2, dy1n_scratch, dw2, db2, sums);
   STEP_LAUNCH_CHECK("trunk_conv2_bwd_kernel");
   trunk_bn_bwd_finalize_kernel<<<1, 32, 0, st>>>(sums, (double)N * d.L1, C1, g1, bn1_stats, eps, coef1, dg1, dbe1);

@@ -1,0 +1,70 @@
+"""Batch-parallel training plumbing: one process per GPU, NCCL over NVLink (gloo on CPU for tests).
+
+Reference behaviour being reproduced: easytorch wraps the model in
+DistributedDataParallel(find_unused_parameters=True) - every rank holds all parameters, runs its own batch
+(batch size is per process), BatchNorm statistics stay per rank, and the gradients of the trainable parameters
+are averaged across ranks once per step.  Parameters that receive no gradient (residual_convs.*, bn.7.*,
+gconv.7.mlp.*, fc_mean.*) contribute zeros.
+
+Implementation: all trainable gradients live in ONE flat buffer (each ``param.grad`` is a view into it), so the
+collective is a single all-reduce of ~162 MB (METR-LA) with no gather/scatter copies; NVSwitch makes its cost
+(~0.4 ms at the measured 725 GB/s bus bandwidth) small against the 30 ms step, so it is issued after backward
+rather than bucketed."""
+from __future__ import annotations
+
+import os
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: Optional[str] = None) -> tuple:
+    """Initialise torch.distributed from RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun). Returns (rank, world, local_rank)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kwargs = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            kwargs["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend, **kwargs)
+    return rank, world, local_rank
+
+
+def shard_batch(global_batch: int, rank: int, world: int) -> slice:
+    """Contiguous slice of a global batch owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(global_batch, world)
+    start = rank * base + min(rank, rem)
+    return slice(start, start + base + (1 if rank < rem else 0))
+
+
+class FlatGradReducer:
+    """Keeps every trainable gradient in one flat buffer and averages it across ranks with a single all-reduce."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], world: Optional[int] = None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatGradReducer: no trainable parameters")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, device=dev, dtype=dt)
+        self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self) -> None:
+        """Call before backward: gradients accumulate into the views (parameters without a gradient stay zero)."""
+        self.flat.zero_()
+
+    def reduce(self) -> torch.Tensor:
+        """Average the gradients over all ranks (no-op for a single process)."""
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(self.world)
+        return self.flat

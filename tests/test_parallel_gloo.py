@@ -1,0 +1,72 @@
+"""CPU, world_size 2 over gloo: the N>1 host logic (flat-gradient all-reduce, batch sharding)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from step_b200 import parallel
+    r, w, _ = parallel.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    unused = torch.nn.Parameter(torch.ones(5))          # never receives a gradient (like fc_mean.* in STEP)
+    frozen = torch.nn.Parameter(torch.ones(2), requires_grad=False)
+    red = parallel.FlatGradReducer(list(model.parameters()) + [unused, frozen])
+    assert red.numel == sum(p.numel() for p in model.parameters()) + 5
+    x = torch.arange(8, dtype=torch.float32).view(2, 4) + 10.0 * rank      # different data per rank
+    for _ in range(2):                                                       # second pass checks zero()
+        red.zero()
+        model(x).square().sum().backward()
+        flat = red.reduce().clone()
+    # reference: average of the two ranks' gradients computed locally
+    grads = []
+    for rr in range(world):
+        m2 = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+        m2.load_state_dict(model.state_dict())
+        xx = torch.arange(8, dtype=torch.float32).view(2, 4) + 10.0 * rr
+        m2(xx).square().sum().backward()
+        grads.append(torch.cat([p.grad.reshape(-1) for p in m2.parameters()]))
+    want = torch.cat([(grads[0] + grads[1]) / 2, torch.zeros(5)])
+    ok = torch.allclose(flat, want, rtol=1e-5, atol=1e-5) and unused.grad.abs().sum().item() == 0.0
+    # views: param.grad aliases the flat buffer
+    ok = ok and model[0].weight.grad.data_ptr() == red.flat.data_ptr()
+    out.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_grad_reducer_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_shard_batch():
+    from step_b200.parallel import shard_batch
+    for gb, w in ((32, 8), (33, 8), (4, 8), (7, 2)):
+        parts = [shard_batch(gb, r, w) for r in range(w)]
+        assert parts[0].start == 0 and parts[-1].stop == gb
+        assert all(a.stop == b.start for a, b in zip(parts, parts[1:]))
+        sizes = [p.stop - p.start for p in parts]
+        assert max(sizes) - min(sizes) <= 1
