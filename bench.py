@@ -148,6 +148,8 @@ def cpu_reference_run(steps, warmup, batch, dropout=True):
 # --------------------------------------------------------------------------------------------- our arm
 def main():
     args = parse()
+    if not os.environ.get("STEP_B200_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"       # NCCL's version banner goes to stdout and would precede the JSON line
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -255,14 +257,39 @@ def main():
             print(json.dumps({"only_resident": True, "ms_per_step": ms_res / args.steps, "gpu_launches": launches}))
         return
 
-    # ---- end-to-end: pinned host batch -> H2D copies -> step -> loss read back, all inside the timed region ----
+    # ---- end-to-end: pinned host batch -> H2D copies -> step -> loss read back, all inside the timed region.
+    # The copies of step i+1 are issued on a side stream while step i computes (double-buffered device
+    # staging), the way a prefetching data loader feeds the runner; every byte is still copied inside the
+    # timed region and every step's loss is read back to the host.
     losses = []
+    copy_stream = torch.cuda.Stream(dev)
+    staging = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def issue_copy(i):
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])            # the step that last used this slot is done with it
+            for dst, src in zip(staging[slot], host[i % n_host]):
+                dst.copy_(src, non_blocking=True)
+            ready[slot].record(copy_stream)
 
     def e2e_step(i):
-        h, lh, f = host[i % n_host]
-        loss = train_step(h.to(dev, non_blocking=True), lh.to(dev, non_blocking=True), f.to(dev, non_blocking=True))
-        losses.append(loss.item())                # D2H read of the step's result
+        if i == 0:
+            issue_copy(0)
+        issue_copy(i + 1)                                       # prefetch the next batch during this step
+        slot = i % 2
+        torch.cuda.current_stream(dev).wait_event(ready[slot])
+        loss = train_step(*staging[slot])
+        consumed[slot].record(torch.cuda.current_stream(dev))
+        losses.append(loss.item())                              # D2H read of the step's result
+    for ev in consumed:
+        ev.record(torch.cuda.current_stream(dev))
     e2e_step(0)
+    torch.cuda.synchronize(dev)
+    for ev in consumed:
+        ev.record(torch.cuda.current_stream(dev))
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
