@@ -150,8 +150,15 @@ size_t step_ts_encoder_bf16_workspace_bytes(int B, int N, int P);
 int step_ts_encoder_fwd_bf16(const float *series, long long sB, long long sT, long long sN, int B, int N, int P,
                              const float *patch_w, const float *patch_b, const float *pos,
                              const step_ts_layer_weights *h_layers, const step_ts_layer_images *h_images, int n_layers,
-                             const float *final_norm_w, const float *final_norm_b, float *hidden, void *workspace,
-                             size_t workspace_bytes, float drop_p, unsigned long long seed, void *stream);
+                             const float *final_norm_w, const float *final_norm_b, float *hidden, void *seq_img,
+                             void *workspace, size_t workspace_bytes, float drop_p, unsigned long long seed, void *stream);
+/* seq_img (optional output of step_ts_encoder_fwd_bf16, may be NULL): the hidden states once more as a per-sample
+ * K-major bf16 image [B][P*12 chunks][R = round_up(N,128)][8] (row = node, K = (patch, feature)) - the operand of the
+ * tensor-core Gram GEMM below. */
+size_t step_tc_seq_image_bytes(int B, int N, int P);
+/* Cosine-similarity Gram matrix from the sequence image on tcgen05 (similarity.py:6-16; norms = sqrt of the Gram
+ * diagonal).  gram_scratch, sim: [B,N,N] fp32. */
+int step_tc_cosine_gram(const void *seq_img, int B, int N, int P, float *gram_scratch, float *sim, void *stream);
 
 /* ------------------------------------------------------------------------ *
  * kNN prior graph: cosine-similarity Gram matrix + global top-k select

@@ -128,5 +128,12 @@ class DiscreteGraphLearning(nn.Module):
         self._calls += 1
         seed = (torch.initial_seed() + 0xC2B2AE35 * self._calls) & (2 ** 63 - 1)
         sampled_adj = ops.GumbelSample.apply(logits, self.gumbel_uniform, batch_size, 0.5, seed)
-        adj_knn = ops.knn_prior(hidden_states, self.k * self.num_nodes)
+        seq_img = getattr(tsformer, "seq_image", None)
+        if seq_img is not None:
+            # bf16 mode: the encoder also emitted its output as the K-major operand image of the Gram GEMM (tcgen05)
+            with torch.no_grad():
+                sim = ops.tc_cosine_gram(seq_img, batch_size, num_nodes, hidden_states.shape[2])
+                adj_knn = ops.topk_mask(sim, self.k * self.num_nodes)
+        else:
+            adj_knn = ops.knn_prior(hidden_states, self.k * self.num_nodes)
         return bernoulli_unnorm, hidden_states, adj_knn, sampled_adj

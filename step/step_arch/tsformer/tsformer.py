@@ -119,6 +119,7 @@ class TSFormer(nn.Module):
         self.precision = os.environ.get("STEP_B200_PRECISION", "bf16")
         self._tc_images = None
         self._tc_key = None
+        self.seq_image = None        # bf16 Gram operand of the last bf16 forward ([B][P*12][R][8]); None in fp32 mode
         self._calls = 0
         self.initialize_weights()
 
@@ -147,11 +148,12 @@ class TSFormer(nn.Module):
             if self._tc_key != key:           # frozen weights: packed into UMMA images once
                 self._tc_images = ops.ts_pack_layer_images(layers)
                 self._tc_key = key
-            hidden = ops.ts_encoder_forward_bf16(series, emb.weight, emb.bias, self.positional_encoding.position_embedding,
-                                                 layers, self._tc_images, self.encoder_norm.weight, self.encoder_norm.bias,
-                                                 drop_p=drop, seed=seed)
+            hidden, self.seq_image = ops.ts_encoder_forward_bf16(
+                series, emb.weight, emb.bias, self.positional_encoding.position_embedding, layers, self._tc_images,
+                self.encoder_norm.weight, self.encoder_norm.bias, drop_p=drop, seed=seed, want_seq_image=True)
         else:
             # fp32 kernels (also serves P > 176 until the tensor-core attention handles two key blocks)
+            self.seq_image = None
             hidden = ops.ts_encoder_forward(series, emb.weight, emb.bias, self.positional_encoding.position_embedding, layers,
                                             self.encoder_norm.weight, self.encoder_norm.bias, drop_p=drop, seed=seed,
                                             chunk_seqs=self.chunk_seqs)

@@ -156,6 +156,8 @@ struct TcLinearArgs {
   const float *ln_w, *ln_b, *ln2_w, *ln2_b;
   uint8_t *out_img;        // TCM_RELU_IMG: [MT][Nout/8][128][8]; TCM_RESLN: [MT][12][128][8] (may be null)
   float *out_f32;          // TCM_F32: [T][Nout]; TCM_RESLN: [T][96] (may be null)
+  uint8_t *seq_img;        // TCM_RESLN: per-sample K-major image [B][P*12 chunks][seq_rows][8] of the output (Gram operand)
+  int seq_nodes, seq_rows; // nodes per sample, padded rows per chunk
   uint8_t *q_img, *k_img, *v_img;  // TCM_QKV
   int P, Pk, RT;
   float qscale;
@@ -172,7 +174,7 @@ __device__ __forceinline__ void layer_norm96(float *v, const float *w, const flo
   for (int c = 0; c < 96; ++c) { const float d = v[c] - mean; q = fmaf(d, d, q); }
   const float rstd = rsqrtf(q * (1.f / 96.f) + 1e-5f);
 #pragma unroll
-  for (int c = 0; c < 96; ++c) v[c] = (v[c] - mean) * rstd * __ldg(w + c) + __ldg(b + c);
+  for (int c = 0; c < 96; ++c) v[c] = (v[c] - mean) * rstd * w[c] + b[c];
 }
 
 __global__ void __launch_bounds__(TCL_THREADS, 1) tc_linear_kernel(TcLinearArgs a) {
@@ -184,7 +186,16 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_linear_kernel(TcLinearArgs 
   uint64_t *bars = reinterpret_cast<uint64_t *>(sA + TCL_STAGES * SLICE_BYTES);
   uint64_t *full = bars, *empty = bars + TCL_STAGES, *tfull = bars + 2 * TCL_STAGES, *tempty = tfull + 4, *wbar = tempty + 4;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wbar + 1);
+  float *sBias = reinterpret_cast<float *>(bars + 32);     // [Nout] bias, then 4 x [96] LayerNorm vectors
+  float *sLn = sBias + 384;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < a.Nout; i += blockDim.x) sBias[i] = a.bias[i];
+  if (a.mode == TCM_RESLN) {
+    for (int i = threadIdx.x; i < 96; i += blockDim.x) {
+      sLn[i] = a.ln_w[i]; sLn[96 + i] = a.ln_b[i];
+      sLn[192 + i] = a.ln2_w ? a.ln2_w[i] : 1.f; sLn[288 + i] = a.ln2_b ? a.ln2_b[i] : 0.f;
+    }
+  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TCL_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -281,9 +292,14 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_linear_kernel(TcLinearArgs 
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[slot]);
 
-        const float *bias = a.bias + nb * 96;
+        {
+          const float4 *bias4 = reinterpret_cast<const float4 *>(sBias + nb * 96);
 #pragma unroll
-        for (int c = 0; c < 96; ++c) v[c] += __ldg(bias + c);
+          for (int c4 = 0; c4 < 24; ++c4) {
+            const float4 bb = bias4[c4];
+            v[4 * c4] += bb.x; v[4 * c4 + 1] += bb.y; v[4 * c4 + 2] += bb.z; v[4 * c4 + 3] += bb.w;
+          }
+        }
 
         if (a.mode == TCM_F32) {
           if (valid) {
@@ -311,8 +327,8 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_linear_kernel(TcLinearArgs 
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[cc * 8 + j] += r8[j];
           }
-          layer_norm96(v, a.ln_w, a.ln_b);
-          if (a.ln2_w != nullptr) layer_norm96(v, a.ln2_w, a.ln2_b);
+          layer_norm96(v, sLn, sLn + 96);
+          if (a.ln2_w != nullptr) layer_norm96(v, sLn + 192, sLn + 288);
           if (a.out_img != nullptr) {
             uint4 *o = reinterpret_cast<uint4 *>(a.out_img) + ((size_t)mt * 12) * 128 + row;
 #pragma unroll
@@ -322,6 +338,16 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_linear_kernel(TcLinearArgs 
             float *o = a.out_f32 + token * 96;
 #pragma unroll
             for (int c = 0; c < 96; c += 4) *reinterpret_cast<float4 *>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+          }
+          if (a.seq_img != nullptr && valid) {
+            // row = node, K index = (patch, feature): the operand layout of the cosine-similarity Gram GEMM
+            const long long sq = token / a.P;
+            const int pp = (int)(token - sq * a.P);
+            const long long bb = sq / a.seq_nodes;
+            const int nn = (int)(sq - bb * a.seq_nodes);
+            uint4 *o = reinterpret_cast<uint4 *>(a.seq_img) + ((size_t)bb * a.P * 12 + (size_t)pp * 12) * a.seq_rows + nn;
+#pragma unroll
+            for (int cc = 0; cc < 12; ++cc) o[(size_t)cc * a.seq_rows] = pack8_bf16(&v[cc * 8]);
           }
         } else {  // TCM_QKV: nb 0 -> Q (pre-scaled into the log2 softmax domain), 1 -> K, 2 -> V
           if (valid) {
@@ -490,49 +516,82 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       }
       float m = -INFINITY, l = 0.f;
       if (warp_active) {
-        // pass 1: row maximum over the P valid columns
-        for (int c0 = 0; c0 < Pk; c0 += 32) {
-          if (c0 + 32 <= Pk) {
-            float t[32];
-            tmem_ld32(TM_S + lane_base + c0, t);
+        // Full 32-column blocks run unpredicated with four independent max / sum chains; only the tail block
+        // (columns [c_tail, P), then zero fill up to Pk) carries per-element predicates.
+        const int c_tail = (P / 32) * 32;
+        const bool tail32 = c_tail + 32 <= Pk;          // else the tail is one 16-column load (Pk is a multiple of 16)
+        // ---- pass 1: row maximum ----
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        for (int c0 = 0; c0 < c_tail; c0 += 32) {
+          float t[32];
+          tmem_ld32(TM_S + lane_base + c0, t);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) if (c0 + c < P) m = fmaxf(m, t[c]);
-          } else {
-            float t[16];
-            tmem_ld16(TM_S + lane_base + c0, t);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) if (c0 + c < P) m = fmaxf(m, t[c]);
+          for (int c = 0; c < 32; c += 4) {
+            m0 = fmaxf(m0, t[c]); m1 = fmaxf(m1, t[c + 1]); m2 = fmaxf(m2, t[c + 2]); m3 = fmaxf(m3, t[c + 3]);
           }
         }
-        // pass 2: p = 2^(s - m), row sum, (dropout), bf16 image
-        const uint64_t drop_base = (((uint64_t)seq * 4 + h) * P + (rt * 128 + row)) * (uint64_t)(Pk / 8);
-        uint4 *prow = reinterpret_cast<uint4 *>(myP) + row;
-        for (int c0 = 0; c0 < Pk; c0 += 32) {
+        if (c_tail < P) {
           float t[32];
-          if (c0 + 32 <= Pk) {
-            tmem_ld32(TM_S + lane_base + c0, t);
+          if (tail32) {
+            tmem_ld32(TM_S + lane_base + c_tail, t);
           } else {
             float t16[16];
-            tmem_ld16(TM_S + lane_base + c0, t16);
+            tmem_ld16(TM_S + lane_base + c_tail, t16);
 #pragma unroll
             for (int c = 0; c < 16; ++c) t[c] = t16[c];
 #pragma unroll
             for (int c = 16; c < 32; ++c) t[c] = -INFINITY;
           }
 #pragma unroll
+          for (int c = 0; c < 32; ++c) if (c_tail + c < P) m0 = fmaxf(m0, t[c]);
+        }
+        m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        // ---- pass 2: p = 2^(s - m), row sum, (dropout), bf16 image ----
+        const uint64_t drop_base = (((uint64_t)seq * 4 + h) * P + (rt * 128 + row)) * (uint64_t)(Pk / 8);
+        uint4 *prow = reinterpret_cast<uint4 *>(myP) + row;
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        for (int c0 = 0; c0 < c_tail; c0 += 32) {
+          float t[32];
+          tmem_ld32(TM_S + lane_base + c0, t);
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            t[c] = fast_exp2(t[c] - m); t[c + 1] = fast_exp2(t[c + 1] - m);
+            t[c + 2] = fast_exp2(t[c + 2] - m); t[c + 3] = fast_exp2(t[c + 3] - m);
+            l0 += t[c]; l1 += t[c + 1]; l2 += t[c + 2]; l3 += t[c + 3];
+          }
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            if (a.thr16) drop8(&t[cc * 8], drop_base + (c0 >> 3) + cc, a.thr16, 1.0f, a.key);
+            prow[(size_t)((c0 >> 3) + cc) * 128] = pack8_bf16(&t[cc * 8]);
+          }
+        }
+        if (c_tail < Pk) {
+          float t[32];
+          if (tail32) {
+            tmem_ld32(TM_S + lane_base + c_tail, t);
+          } else {
+            float t16[16];
+            tmem_ld16(TM_S + lane_base + c_tail, t16);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) t[c] = t16[c];
+#pragma unroll
+            for (int c = 16; c < 32; ++c) t[c] = 0.f;
+          }
+#pragma unroll
           for (int c = 0; c < 32; ++c) {
-            const float pv = (c0 + c < P) ? fast_exp2(t[c] - m) : 0.f;
-            l += pv;
+            const float pv = (c_tail + c < P) ? fast_exp2(t[c] - m) : 0.f;
+            l0 += pv;
             t[c] = pv;
           }
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
-            if (c0 + cc * 8 < Pk) {
-              if (a.thr16) drop8(&t[cc * 8], drop_base + (c0 >> 3) + cc, a.thr16, 1.0f, a.key);
-              prow[(size_t)((c0 >> 3) + cc) * 128] = pack8_bf16(&t[cc * 8]);
+            if (c_tail + cc * 8 < Pk) {
+              if (a.thr16) drop8(&t[cc * 8], drop_base + (c_tail >> 3) + cc, a.thr16, 1.0f, a.key);
+              prow[(size_t)((c_tail >> 3) + cc) * 128] = pack8_bf16(&t[cc * 8]);
             }
           }
         }
+        l = (l0 + l1) + (l2 + l3);
       }
       tc_fence_before();
       fence_proxy_async();
@@ -567,9 +626,117 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+// ===========================================================================
+// Gram matrix of the hidden states on tcgen05: G[b] = X[b] X[b]^T, X[b] = [N nodes, K = P*96] read from the
+// sequence-major bf16 image [B][K/8][R][8] the encoder's last epilogue emits.  One CTA per
+// (sample, 128-row tile, 256-column block); the K dimension streams through a 4-stage TMA ring, both MMA
+// operands are row ranges of the same image.  fp32 accumulation in TMEM over the whole K = 16128.
+// ===========================================================================
+constexpr int TG_KC = 8;          // chunks (64 K elements) per pipeline stage
+constexpr int TG_STAGES = 4;
+
+struct TcGramArgs {
+  const uint8_t *img;
+  float *gram;              // [B][N][N] raw dot products
+  int N, R, KC;             // nodes, padded rows per chunk, chunks per sample (multiple of TG_KC)
+};
+
+__global__ void __launch_bounds__(192, 1) tc_gram_kernel(TcGramArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int b = blockIdx.z, mt = blockIdx.y, nblk = blockIdx.x;
+  const int col0 = nblk * 256;
+  const int Rb = min(256, a.R - col0);                         // B rows staged per chunk
+  const int Ncols = min(256, ((a.N - col0) + 15) / 16 * 16);   // MMA N
+  const uint32_t a_stage = TG_KC * 2048, b_stage = (uint32_t)TG_KC * Rb * 16;
+  uint8_t *sA = smem;
+  uint8_t *sB = smem + TG_STAGES * a_stage;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TG_STAGES * b_stage);
+  uint64_t *full = bars, *empty = bars + TG_STAGES, *done = bars + 2 * TG_STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int nslices = a.KC / TG_KC;
+  const uint8_t *base = a.img + (size_t)b * a.KC * a.R * 16;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nslices; ++i) {
+        const int s = i % TG_STAGES, ph = (i / TG_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], a_stage + b_stage);
+        for (int c = 0; c < TG_KC; ++c) {
+          const uint8_t *chunk = base + ((size_t)(i * TG_KC + c) * a.R) * 16;
+          tma_bulk_g2s(sA + s * a_stage + c * 2048, chunk + (size_t)mt * 128 * 16, 2048, &full[s]);
+          tma_bulk_g2s(sB + s * b_stage + (size_t)c * Rb * 16, chunk + (size_t)col0 * 16, (uint32_t)Rb * 16, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, Ncols, 0, 0);
+      for (int i = 0; i < nslices; ++i) {
+        const int s = i % TG_STAGES, ph = (i / TG_STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t aa = smem_u32(sA + s * a_stage), ba = smem_u32(sB + s * b_stage);
+#pragma unroll
+        for (int kk = 0; kk < TG_KC / 2; ++kk)
+          umma_bf16(tmem, umma_desc(aa + kk * 2 * 2048, 2048, 128), umma_desc(ba + kk * 2 * Rb * 16, Rb * 16, 128), idesc,
+                    (i | kk) != 0 ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(done);
+    }
+  } else {
+    const int q = warp & 3, row = mt * 128 + q * 32 + lane;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    float *out = a.gram + ((size_t)b * a.N + row) * a.N + col0;
+    for (int c0 = 0; c0 < Ncols; c0 += 32) {
+      float t[32];
+      if (c0 + 32 <= Ncols) {
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, t);
+      } else {
+        float t16[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, t16);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) t[c] = t16[c];
+      }
+      if (row < a.N) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c0 + c < Ncols && col0 + c0 + c < a.N) out[c0 + c] = t[c];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// sim = G / ((sqrt(G_ii) + 1e-7)(sqrt(G_jj) + 1e-7))   (similarity.py:8-14; the norms are the Gram diagonal)
+__global__ void gram_normalize_kernel(const float *__restrict__ g, int N, float *__restrict__ sim) {
+  const int b = blockIdx.y;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)N * N) return;
+  const int i = (int)(e / N), j = (int)(e - (long long)i * N);
+  const float *gb = g + (size_t)b * N * N;
+  const float ni = sqrtf(fmaxf(gb[(size_t)i * N + i], 0.f)) + 1e-7f, nj = sqrtf(fmaxf(gb[(size_t)j * N + j], 0.f)) + 1e-7f;
+  sim[(size_t)b * N * N + e] = gb[e] / (ni * nj);
+}
+
 // ---------------------------------------------------------------------------
 static size_t tcl_smem_bytes(int K, int Nout) {
-  return (size_t)K * Nout * 2 + TCL_STAGES * SLICE_BYTES + 32 * 8 + 16;
+  return (size_t)K * Nout * 2 + TCL_STAGES * SLICE_BYTES + 32 * 8 + (384 + 4 * 96) * 4 + 16;
 }
 static size_t tca_smem_bytes(int Pk) {
   const size_t zrows = Pk > 128 ? Pk : 128;
@@ -674,6 +841,29 @@ extern "C" int step_tc_attention(const void *q_img, const void *k_img, const voi
   return tc_attn_launch(q_img, k_img, v_img, o_img, S, P, drop_p, seed, 0, (cudaStream_t)stream);
 }
 
+extern "C" size_t step_tc_seq_image_bytes(int B, int N, int P) {
+  const size_t R = (size_t)(N + 127) / 128 * 128;
+  return (size_t)B * P * 12 * R * 16;
+}
+
+extern "C" int step_tc_cosine_gram(const void *seq_img, int B, int N, int P, float *gram_scratch, float *sim, void *stream) {
+  STEP_REQUIRE(seq_img && gram_scratch && sim && B > 0 && N > 0 && P > 0, "tc_cosine_gram: bad argument");
+  if ((P * 12) % TG_KC != 0) return fail(STEP_EUNSUPPORTED, "tc_cosine_gram: P*12 = %lld must be a multiple of 8", (long long)P * 12);
+  cudaStream_t st = (cudaStream_t)stream;
+  TcGramArgs a{};
+  a.img = (const uint8_t *)seq_img; a.gram = gram_scratch; a.N = N; a.R = (N + 127) / 128 * 128; a.KC = P * 12;
+  const int nblk = (N + 255) / 256;
+  const int Rb = a.R < 256 ? a.R : 256;
+  const size_t smem = TG_STAGES * (size_t)(TG_KC * 2048 + TG_KC * Rb * 16) + 16 * 8 + 16;
+  int rc = allow_smem(tc_gram_kernel, 227 * 1024);
+  if (rc) return rc;
+  tc_gram_kernel<<<dim3(nblk, a.R / 128, B), 192, smem, st>>>(a);
+  STEP_LAUNCH_CHECK("tc_gram_kernel");
+  const long long per = (long long)N * N;
+  gram_normalize_kernel<<<dim3((unsigned)((per + 255) / 256), B), 256, 0, st>>>(gram_scratch, N, sim);
+  return check_launch("gram_normalize_kernel");
+}
+
 // packed weight images of one encoder layer
 extern "C" size_t step_ts_encoder_bf16_workspace_bytes(int B, int N, int P) {
   const long long S = (long long)B * N, T = S * P, MT = (T + 127) / 128;
@@ -689,7 +879,7 @@ extern "C" size_t step_ts_encoder_bf16_workspace_bytes(int B, int N, int P) {
 extern "C" int step_ts_encoder_fwd_bf16(const float *series, long long sB, long long sT, long long sN, int B, int N, int P,
                                         const float *patch_w, const float *patch_b, const float *pos,
                                         const step_ts_layer_weights *L, const step_ts_layer_images *I, int n_layers,
-                                        const float *fnw, const float *fnb, float *hidden, void *workspace,
+                                        const float *fnw, const float *fnb, float *hidden, void *seq_img, void *workspace,
                                         size_t workspace_bytes, float drop_p, unsigned long long seed, void *stream) {
   STEP_REQUIRE(series && patch_w && patch_b && pos && L && I && fnw && fnb && hidden && workspace, "ts_encoder_bf16: null pointer");
   STEP_REQUIRE(n_layers >= 1 && B > 0 && N > 0 && P > 0, "ts_encoder_bf16: bad shape");
@@ -742,7 +932,10 @@ extern "C" int step_ts_encoder_fwd_bf16(const float *series, long long sB, long 
     a = TcLinearArgs{};
     a.A = H; a.W = (const uint8_t *)I[l].lin2; a.bias = L[l].lin2_b; a.MT = (int)MT; a.K = 384; a.Nout = 96;
     a.mode = TCM_RESLN; a.T = T; a.res = X1; a.ln_w = L[l].norm2_w; a.ln_b = L[l].norm2_b;
-    if (last) { a.ln2_w = fnw; a.ln2_b = fnb; a.out_f32 = hidden; a.out_img = nullptr; }
+    if (last) {
+      a.ln2_w = fnw; a.ln2_b = fnb; a.out_f32 = hidden; a.out_img = nullptr;
+      a.seq_img = (uint8_t *)seq_img; a.seq_nodes = N; a.seq_rows = (N + 127) / 128 * 128; a.P = P;
+    }
     else a.out_img = nxt;
     a.thr16 = thr16; a.dscale = dscale; a.key = rng_key(seed, site + 4);
     if ((rc = tc_linear_launch(a, st))) return rc;

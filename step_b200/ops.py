@@ -363,8 +363,9 @@ def ts_pack_layer_images(layers: Sequence[Dict[str, Tensor]]):
 
 
 def ts_encoder_forward_bf16(series: Tensor, patch_w: Tensor, patch_b: Tensor, pos: Tensor, layers: Sequence[Dict[str, Tensor]],
-                            images, norm_w: Tensor, norm_b: Tensor, drop_p: float = 0.0, seed: int = 0) -> Tensor:
-    """series [B, P*12, N] view -> hidden [B, N, P, 96] fp32, computed on the tensor cores in bf16."""
+                            images, norm_w: Tensor, norm_b: Tensor, drop_p: float = 0.0, seed: int = 0, want_seq_image: bool = False):
+    """series [B, P*12, N] view -> hidden [B, N, P, 96] fp32, computed on the tensor cores in bf16.
+    want_seq_image: also return the bf16 sequence-major image of the hidden states (Gram operand)."""
     if not series.is_cuda or series.dtype != torch.float32:
         raise _lib.StepB200Error("ts_encoder_forward_bf16: series must be a float32 CUDA tensor")
     B, T, N = series.shape
@@ -375,6 +376,9 @@ def ts_encoder_forward_bf16(series: Tensor, patch_w: Tensor, patch_b: Tensor, po
     hidden = torch.empty(B, N, P, 96, device=series.device, dtype=torch.float32)
     ws_bytes = _L().step_ts_encoder_bf16_workspace_bytes(B, N, P)
     ws = torch.empty(ws_bytes, device=series.device, dtype=torch.uint8)
+    seq_img = None
+    if want_seq_image and (P * 12) % 8 == 0:
+        seq_img = torch.empty(_L().step_tc_seq_image_bytes(B, N, P), device=series.device, dtype=torch.uint8)
     arr, keep = ts_layer_struct(layers)
     iarr = (_lib.TsLayerImages * len(layers))()
     for i, im in enumerate(images):
@@ -384,10 +388,21 @@ def ts_encoder_forward_bf16(series: Tensor, patch_w: Tensor, patch_b: Tensor, po
     nw, nb = _f32(norm_w, "norm_w"), _f32(norm_b, "norm_b")
     sB, sT, sN = series.stride()
     check(_L().step_ts_encoder_fwd_bf16(series.data_ptr(), sB, sT, sN, B, N, P, pw.data_ptr(), pb.data_ptr(), ps.data_ptr(), arr,
-                                        iarr, len(layers), nw.data_ptr(), nb.data_ptr(), hidden.data_ptr(), ws.data_ptr(),
-                                        ws_bytes, float(drop_p), int(seed) & (2**64 - 1), st), "step_ts_encoder_fwd_bf16")
+                                        iarr, len(layers), nw.data_ptr(), nb.data_ptr(), hidden.data_ptr(), _p(seq_img),
+                                        ws.data_ptr(), ws_bytes, float(drop_p), int(seed) & (2**64 - 1), st),
+          "step_ts_encoder_fwd_bf16")
     launch_counter["kernels"] += 1 + len(layers) * 5
-    return hidden
+    return (hidden, seq_img) if want_seq_image else hidden
+
+
+def tc_cosine_gram(seq_img: Tensor, B: int, N: int, P: int) -> Tensor:
+    """Cosine-similarity Gram matrix [B,N,N] from the encoder's bf16 sequence image (tcgen05)."""
+    st = _enter(seq_img)
+    scratch = torch.empty(B, N, N, device=seq_img.device, dtype=torch.float32)
+    sim = torch.empty(B, N, N, device=seq_img.device, dtype=torch.float32)
+    check(_L().step_tc_cosine_gram(seq_img.data_ptr(), B, N, P, scratch.data_ptr(), sim.data_ptr(), st), "step_tc_cosine_gram")
+    launch_counter["kernels"] += 2
+    return sim
 
 
 # --------------------------------------------------------------------------- #

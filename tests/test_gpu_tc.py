@@ -108,3 +108,23 @@ def test_ts_encoder_bf16_close_to_oracle(B, N, P, real):
     # 4 post-norm layers in bf16: stated tolerance = 3e-2 mean abs (hidden states are O(0.3-1))
     assert torch.isfinite(out).all()
     assert err.mean().item() < 3e-2 and err.max().item() < 0.5
+
+
+@pytest.mark.parametrize("B,N,P", [(2, 50, 24), (2, 207, 168), (1, 300, 24)])
+def test_tc_cosine_gram_from_encoder_image(B, N, P):
+    from step_b200 import ops
+    sd = O.synthetic_tsformer_params(2)
+    g = torch.Generator().manual_seed(B + N + P)
+    long_history = torch.randn(B, P * 12, N, 1, generator=g)
+    layers = _layers(sd)
+    images = ops.ts_pack_layer_images(layers)
+    hidden, img = ops.ts_encoder_forward_bf16(long_history.to(DEV)[..., 0], sd["patch_embedding.input_embedding.weight"].to(DEV),
+                                              sd["patch_embedding.input_embedding.bias"].to(DEV),
+                                              sd["positional_encoding.position_embedding"].to(DEV), layers, images,
+                                              sd["encoder_norm.weight"].to(DEV), sd["encoder_norm.bias"].to(DEV),
+                                              want_seq_image=True)
+    sim = ops.tc_cosine_gram(img, B, N, P).cpu()
+    x = bf(hidden.cpu()).reshape(B, N, -1)                 # the image holds the bf16-rounded hidden states
+    ref = O.cosine_similarity_gram(x.double()).float()
+    assert (sim - ref).abs().max().item() < 2e-4
+    assert (sim.diagonal(dim1=1, dim2=2) - 1).abs().max().item() < 1e-5
