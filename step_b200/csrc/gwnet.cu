@@ -14,7 +14,10 @@
 // which needs the same 6 node-mixes per layer but only 32-channel operands.  BatchNorm of layer i is
 // applied on load by layer i+1 (scale/shift from the batch statistics), the 256-channel skip conv is
 // evaluated only at the last time step (the only column that survives `skip[..., -T:]`).
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tc_mix.cuh"
 
 namespace stepk {
 
@@ -32,6 +35,8 @@ struct GwPlan {
   size_t off_z[GW_MAX_LAYERS], off_f[GW_MAX_LAYERS], off_g[GW_MAX_LAYERS], off_q[GW_MAX_LAYERS][3];
   size_t off_U, off_M, off_H;       // forward scratch, [B,12,N,32]
   size_t off_DH, off_DZC, off_DQ[3], off_A[3], off_DA, off_DU, off_DPF, off_DPG, off_DR[2];
+  size_t off_M3[3], off_O3[3], off_DA3[3];   // tensor-core mix path: per-support mix outputs
+  size_t off_img[3];                          // bf16 split images of P1, P2 (per sample) and P3
   size_t total;
 };
 
@@ -63,6 +68,11 @@ static GwPlan make_plan(int B, int N, int L) {
   p.off_DA = take(big); p.off_DU = take(big); p.off_DPF = take(big); p.off_DPG = take(big);
   p.off_DR[0] = take((size_t)B * 13 * p.col);
   p.off_DR[1] = take((size_t)B * 13 * p.col);
+  for (int s = 0; s < 3; ++s) { p.off_M3[s] = take(big); p.off_O3[s] = take(big); p.off_DA3[s] = take(big); }
+  const size_t img_floats = (mix_images_bytes(N) + 3) / 4;
+  p.off_img[0] = take(img_floats * B);
+  p.off_img[1] = take(img_floats * B);
+  p.off_img[2] = take(img_floats);
   p.total = o;
   return p;
 }
@@ -198,23 +208,23 @@ __device__ __forceinline__ void column_sums_to(const float *Y, int N, float *red
 // dst[co*ldd + ci] += sum_n X[n][co] * U[n][ci]   (X, U: [N][32] in global, CTA-local data)
 // tiles: smem scratch of 2*64*33 floats.
 __device__ __forceinline__ void outer_acc(const float *X, const float *U, int N, float *tiles, float *dst, int ldd) {
-  float *T1 = tiles, *T2 = tiles + 64 * 33;
+  float *T1 = tiles, *T2 = tiles + 64 * 32;          // [64 nodes][32] each, 16-byte aligned rows
   const int co = threadIdx.x >> 3, ci4 = (threadIdx.x & 7) * 4;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   for (int n0 = 0; n0 < N; n0 += 64) {
     __syncthreads();
-    for (int i = threadIdx.x; i < 64 * GC; i += GW_THREADS) {
-      const int n = i >> 5, c = i & 31;
+    for (int i = threadIdx.x; i < 64 * (GC / 4); i += GW_THREADS) {
+      const int n = i >> 3, c4 = (i & 7) * 4;
       const bool ok = (n0 + n) < N;
-      T1[n * 33 + c] = ok ? X[(size_t)(n0 + n) * GC + c] : 0.f;
-      T2[n * 33 + c] = ok ? U[(size_t)(n0 + n) * GC + c] : 0.f;
+      st4(T1 + n * GC + c4, ok ? ld4(X + (size_t)(n0 + n) * GC + c4) : make_float4(0, 0, 0, 0));
+      st4(T2 + n * GC + c4, ok ? ld4(U + (size_t)(n0 + n) * GC + c4) : make_float4(0, 0, 0, 0));
     }
     __syncthreads();
 #pragma unroll 8
     for (int n = 0; n < 64; ++n) {
-      const float x = T1[n * 33 + co];
-      a0 = fmaf(x, T2[n * 33 + ci4], a0); a1 = fmaf(x, T2[n * 33 + ci4 + 1], a1);
-      a2 = fmaf(x, T2[n * 33 + ci4 + 2], a2); a3 = fmaf(x, T2[n * 33 + ci4 + 3], a3);
+      const float x = T1[n * GC + co];                 // 4 distinct words per warp: broadcast
+      const float4 u = ld4(T2 + n * GC + ci4);         // 8 distinct 16-byte words per warp: conflict-free
+      a0 = fmaf(x, u.x, a0); a1 = fmaf(x, u.y, a1); a2 = fmaf(x, u.z, a2); a3 = fmaf(x, u.w, a3);
     }
   }
   float *d = dst + (size_t)co * ldd + ci4;
@@ -250,6 +260,9 @@ struct GwFwdArgs {
   const float *P[3]; long long pstride[3];  // supports, per-sample stride (0 for the shared adaptive one)
   step_gw_layer_params w;
   float *f, *g, *q[3], *U, *M, *H, *skip;
+  int stage;                              // 0: fused CUDA-core layer; 1: conv + skip + a_s; 2: q_s; 3: output (tensor-core mixes in between)
+  float *Aout[3];                         // stage 1: a_s = W_s2 u
+  const float *Min[3], *Oin[3];           // stage 2 / 3: tensor-core mix results
   double *sums;                           // [2][32]
   uint32_t drop_thr; float drop_scale; uint64_t key;
 };
@@ -265,6 +278,7 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
   const size_t ocol = ((size_t)b * a.Tout + t) * col;
   float *U = a.U + ocol, *Mb = a.M + ocol, *Hb = a.H + ocol;
 
+  if (a.stage <= 1) {
   for (int i = tid; i < 1024; i += GW_THREADS) {
     Wb[i] = a.w.filter_w[2 * i]; Wb[1024 + i] = a.w.filter_w[2 * i + 1];
     Wb[2048 + i] = a.w.gate_w[2 * i]; Wb[3072 + i] = a.w.gate_w[2 * i + 1];
@@ -342,6 +356,7 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
     }
     __syncthreads();
   }
+  }  // stage <= 1
   if (!a.has_gcn) return;
 
   // ---- stage the 7 [32x32] blocks of the gcn 1x1 conv: Wb[k][co][ci] = mlp_w[co][k*32+ci] ----
@@ -351,8 +366,38 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
   }
   __syncthreads();
 
+  if (a.stage == 1) {
+    // a_s = W_s2 u for the three supports -> global; the node mixes run on the tensor cores (tc_mix_kernel)
+    for (int s = 0; s < 3; ++s) {
+      const float *W2 = Wb + (2 + 2 * s) * 1024;
+      float *ao = a.Aout[s] + ocol;
+      for (int n = tid; n < N; n += GW_THREADS) {
+        float u[GC];
+        load_row(U + (size_t)n * GC, u);
+        float *ar = ao + (size_t)n * GC;
+        matvec_chunks(W2, u, [&](int cg, float4 v) { st4(ar + 4 * cg, v); });
+      }
+    }
+    return;
+  }
+  if (a.stage == 2) {
+    // q_s = W_s1 u + (P_s^T a_s)
+    for (int s = 0; s < 3; ++s) {
+      const float *W1 = Wb + (1 + 2 * s) * 1024;
+      float *qs = a.q[s] + ocol;
+      const float *ms = a.Min[s] + ocol;
+      for (int n = tid; n < N; n += GW_THREADS) {
+        float u[GC];
+        load_row(U + (size_t)n * GC, u);
+        float *qr = qs + (size_t)n * GC;
+        const float *mr = ms + (size_t)n * GC;
+        matvec_chunks(W1, u, [&](int cg, float4 v) { st4(qr + 4 * cg, add4(v, ld4(mr + 4 * cg))); });
+      }
+    }
+    return;
+  }
   // ---- phase M: diffusion, Horner form per support ----
-  for (int s = 0; s < 3; ++s) {
+  for (int s = 0; s < 3 && a.stage == 0; ++s) {
     const float *Ps = a.P[s] + (size_t)b * a.pstride[s];
     const float *W1 = Wb + (1 + 2 * s) * 1024, *W2 = Wb + (2 + 2 * s) * 1024;
     // a = W_s2 u  -> Y
@@ -400,10 +445,12 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
     float u[GC];
     load_row(U + (size_t)n * GC, u);
     const float *hr = Hb + (size_t)n * GC, *zr = z1 + (size_t)n * GC;
+    const float *o0 = a.Oin[0] + ocol + (size_t)n * GC, *o1 = a.Oin[1] + ocol + (size_t)n * GC, *o2 = a.Oin[2] + ocol + (size_t)n * GC;
     float *yr = Y + (size_t)n * GC, *zo = a.zout + ocol + (size_t)n * GC;
     const uint64_t elem0 = (uint64_t)(ocol + (size_t)n * GC);
     matvec_chunks(Wb, u, [&](int cg, float4 v) {
-      v = add4(add4(v, ld4(hr + 4 * cg)), ld4(a.w.mlp_b + 4 * cg));
+      const float4 hsum = (a.stage == 0) ? ld4(hr + 4 * cg) : add4(add4(ld4(o0 + 4 * cg), ld4(o1 + 4 * cg)), ld4(o2 + 4 * cg));
+      v = add4(add4(v, hsum), ld4(a.w.mlp_b + 4 * cg));
       if (a.drop_thr) v = dropout4(v, elem0, cg, a.drop_thr, a.drop_scale, a.key);
       float4 r = ld4(zr + 4 * cg);
       if (a.has_in_bn) {
@@ -448,6 +495,8 @@ struct GwBwdArgs {
   const float *f, *g;
   const float *dskip;       // [B,N,256]
   float *U, *DH, *DZC, *DQ[3], *A[3], *DA, *DU, *DPF, *DPG;
+  int stage;                // 0: fused CUDA-core layer; 1: up to dh/du0 (before the tensor-core mixes); 2: after them
+  const float *DA3[3];      // stage 2: da_s = P_s dq_s from the tensor-core mix
   uint32_t drop_thr; float drop_scale; uint64_t key;
 };
 
@@ -471,6 +520,7 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
   __syncthreads();
 
   // ---- phase 0: u, dz (through BatchNorm), dh (through dropout), du = W0^T dh ----
+  if (a.stage != 2) {
   for (int n = tid; n < N; n += GW_THREADS) {
     {
       float fv[GC], gv[GC];
@@ -504,8 +554,9 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
     store_row(DU + (size_t)n * GC, du);
   }
   __syncthreads();
+  }  // stage != 2
 
-  if (a.has_gcn) {
+  if (a.has_gcn && a.stage != 2) {
     // d mlp bias = column sums of dh
     {
       const int c = tid & 31, grp = tid >> 5;
@@ -522,7 +573,32 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
       __syncthreads();
     }
     outer_acc(DH, U, N, tiles, a.gr.mlp_w, 224);  // block 0: dW0[co][ci] += dh[n][co] u[n][ci]
-
+  }
+  if (a.stage == 1) return;
+  if (a.has_gcn && a.stage == 2) {
+    // dq_s = P_s dh and da_s = P_s dq_s were produced by tc_mix_kernel
+    for (int s = 0; s < 3; ++s) {
+      const float *W1 = Wb + (1 + 2 * s) * 1024, *W2 = Wb + (2 + 2 * s) * 1024;
+      const float *DQ = a.DQ[s] + ocol, *DAs = a.DA3[s] + ocol;
+      float *As = a.A[s] + ocol;
+      for (int n = tid; n < N; n += GW_THREADS) {
+        {
+          float u[GC];
+          load_row(U + (size_t)n * GC, u);
+          float *ar = As + (size_t)n * GC;
+          matvec_chunks(W2, u, [&](int cg, float4 v) { st4(ar + 4 * cg, v); });
+        }
+        float du[GC];
+        load_row(DU + (size_t)n * GC, du);
+        matvec_t_acc(W1, DQ + (size_t)n * GC, du);
+        matvec_t_acc(W2, DAs + (size_t)n * GC, du);
+        store_row(DU + (size_t)n * GC, du);
+      }
+      outer_acc(DQ, U, N, tiles, a.gr.mlp_w + (1 + 2 * s) * 32, 224);
+      outer_acc(DAs, U, N, tiles, a.gr.mlp_w + (2 + 2 * s) * 32, 224);
+    }
+  }
+  if (a.has_gcn && a.stage == 0) {
     for (int s = 0; s < 3; ++s) {
       const float *Pts = a.Pt[s] + (size_t)b * a.pstride[s];
       const float *W1 = Wb + (1 + 2 * s) * 1024, *W2 = Wb + (2 + 2 * s) * 1024;
@@ -835,6 +911,13 @@ extern "C" size_t step_gwnet_stash_floats(int B, int N, int n_layers) {
   return make_plan(B, N, n_layers).total;
 }
 
+// Node mixes on the tensor cores (tc_mix_kernel, split-bf16 = fp32-level accuracy) unless STEP_B200_GW_MIX=simt
+static bool gw_use_tc(int N) {
+  const char *e = getenv("STEP_B200_GW_MIX");
+  if (e != nullptr && strcmp(e, "simt") == 0) return false;
+  return mix_smem_bytes(mix_geom(N)) <= 227 * 1024;
+}
+
 static size_t fwd_smem_bytes(int N) { return ((size_t)N * GC + 7 * 1024) * sizeof(float); }
 static size_t bwd_smem_bytes(int N) { return ((size_t)N * GC + 7 * 1024 + 2 * 64 * 33) * sizeof(float); }
 static size_t bwd_in_smem_bytes(int N) { return ((size_t)N * GC + 4 * 1024 + 2 * 64 * 33 + 128) * sizeof(float); }
@@ -862,6 +945,15 @@ extern "C" int step_gwnet_stack_fwd(const float *x0, const float *P1, const floa
   cudaError_t e = cudaMemsetAsync(skip_out, 0, (size_t)B * N * GSKIP * sizeof(float), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(stash + p.off_sums_fwd, 0, (size_t)n_layers * 2 * 32 * sizeof(double), st);
   if (e != cudaSuccess) return fail_msg((int)e, cudaGetErrorString(e));
+  const bool use_tc = gw_use_tc(N);
+  const MixGeom geom = mix_geom(N);
+  const size_t img_floats = (mix_images_bytes(N) + 3) / 4;
+  if (use_tc) {
+    // bf16 hi/lo operand images of P and P^T for the three supports (kept in the stash for the backward pass)
+    if ((rc = tc_support_images_launch(P1, B, geom, reinterpret_cast<uint8_t *>(stash + p.off_img[0]), (long long)img_floats * 4, st))) return rc;
+    if ((rc = tc_support_images_launch(P2, B, geom, reinterpret_cast<uint8_t *>(stash + p.off_img[1]), (long long)img_floats * 4, st))) return rc;
+    if ((rc = tc_support_images_launch(P3, 1, geom, reinterpret_cast<uint8_t *>(stash + p.off_img[2]), 0, st))) return rc;
+  }
   for (int i = 0; i < n_layers; ++i) {
     GwFwdArgs a{};
     a.zin = (i == 0) ? x0 : stash + p.off_z[i - 1];
@@ -882,8 +974,34 @@ extern "C" int step_gwnet_stack_fwd(const float *x0, const float *P1, const floa
     if (training && drop_p > 0.f) { a.drop_thr = drop_threshold(drop_p); a.drop_scale = 1.f / (1.f - drop_p); }
     else { a.drop_thr = 0; a.drop_scale = 1.f; }
     a.key = rng_key(seed, 0x100u + i);
-    gw_layer_fwd_kernel<<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
-    STEP_LAUNCH_CHECK("gw_layer_fwd_kernel");
+    if (!use_tc || !a.has_gcn) {
+      a.stage = a.has_gcn ? 0 : 1;
+      gw_layer_fwd_kernel<<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
+      STEP_LAUNCH_CHECK("gw_layer_fwd_kernel");
+    } else {
+      TcMixArgs m{};
+      m.g = geom; m.B = B; m.T = a.Tout; m.nsup = 3; m.transposed_type = 1;
+      for (int s = 0; s < 3; ++s) {
+        m.img[s] = reinterpret_cast<const uint8_t *>(stash + p.off_img[s]);
+        m.img_bstride[s] = (s < 2) ? (long long)img_floats * 4 : 0;
+        a.Aout[s] = stash + p.off_A[s];
+        a.Min[s] = stash + p.off_M3[s];
+        a.Oin[s] = stash + p.off_O3[s];
+      }
+      a.stage = 1;
+      gw_layer_fwd_kernel<<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
+      STEP_LAUNCH_CHECK("gw_layer_fwd_kernel[conv]");
+      for (int s = 0; s < 3; ++s) { m.Y[s] = stash + p.off_A[s]; m.out[s] = stash + p.off_M3[s]; }
+      if ((rc = tc_mix_launch(m, st))) return rc;
+      a.stage = 2;
+      gw_layer_fwd_kernel<<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
+      STEP_LAUNCH_CHECK("gw_layer_fwd_kernel[q]");
+      for (int s = 0; s < 3; ++s) { m.Y[s] = a.q[s]; m.out[s] = stash + p.off_O3[s]; }
+      if ((rc = tc_mix_launch(m, st))) return rc;
+      a.stage = 3;
+      gw_layer_fwd_kernel<<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
+      STEP_LAUNCH_CHECK("gw_layer_fwd_kernel[out]");
+    }
     if (a.has_gcn && training) {
       bn_finalize_kernel<<<1, 32, 0, st>>>(a.sums, (double)B * a.Tout * N, Lp[i].bn_w, Lp[i].bn_b, bn_stats + (size_t)i * 128);
       STEP_LAUNCH_CHECK("bn_finalize_kernel");
@@ -930,6 +1048,9 @@ extern "C" int step_gwnet_stack_bwd(const float *dskip, const float *x0, const f
   if (drop_p > 0.f) { thr = drop_threshold(drop_p); dscale = 1.f / (1.f - drop_p); }
   float *coef = stash + p.off_coef;
   double *bsums = reinterpret_cast<double *>(stash + p.off_sums_bwd);
+  const bool use_tc = gw_use_tc(N);
+  const MixGeom geom = mix_geom(N);
+  const size_t img_floats = (mix_images_bytes(N) + 3) / 4;
 
   for (int i = n_layers - 1; i >= 0; --i) {
     const bool has_gcn = (Lp[i].mlp_w != nullptr);
@@ -948,8 +1069,29 @@ extern "C" int step_gwnet_stack_bwd(const float *dskip, const float *x0, const f
     for (int s = 0; s < 3; ++s) { a.DQ[s] = stash + p.off_DQ[s]; a.A[s] = stash + p.off_A[s]; }
     a.DA = stash + p.off_DA; a.DU = stash + p.off_DU; a.DPF = stash + p.off_DPF; a.DPG = stash + p.off_DPG;
     a.drop_thr = thr; a.drop_scale = dscale; a.key = rng_key(seed, 0x100u + i);
-    gw_layer_bwd_kernel<<<dim3(a.Tout, B), GW_THREADS, bwd_smem_bytes(N), st>>>(a);
-    STEP_LAUNCH_CHECK("gw_layer_bwd_kernel");
+    if (!use_tc || !has_gcn) {
+      a.stage = 0;
+      gw_layer_bwd_kernel<<<dim3(a.Tout, B), GW_THREADS, bwd_smem_bytes(N), st>>>(a);
+      STEP_LAUNCH_CHECK("gw_layer_bwd_kernel");
+    } else {
+      TcMixArgs m{};
+      m.g = geom; m.B = B; m.T = a.Tout; m.nsup = 3; m.transposed_type = 0;
+      for (int s = 0; s < 3; ++s) {
+        m.img[s] = reinterpret_cast<const uint8_t *>(stash + p.off_img[s]);
+        m.img_bstride[s] = (s < 2) ? (long long)img_floats * 4 : 0;
+        a.DA3[s] = stash + p.off_DA3[s];
+      }
+      a.stage = 1;
+      gw_layer_bwd_kernel<<<dim3(a.Tout, B), GW_THREADS, bwd_smem_bytes(N), st>>>(a);
+      STEP_LAUNCH_CHECK("gw_layer_bwd_kernel[pre]");
+      for (int s = 0; s < 3; ++s) { m.Y[s] = stash + p.off_DH; m.out[s] = stash + p.off_DQ[s]; }
+      if ((rc = tc_mix_launch(m, st))) return rc;
+      for (int s = 0; s < 3; ++s) { m.Y[s] = stash + p.off_DQ[s]; m.out[s] = stash + p.off_DA3[s]; }
+      if ((rc = tc_mix_launch(m, st))) return rc;
+      a.stage = 2;
+      gw_layer_bwd_kernel<<<dim3(a.Tout, B), GW_THREADS, bwd_smem_bytes(N), st>>>(a);
+      STEP_LAUNCH_CHECK("gw_layer_bwd_kernel[post]");
+    }
 
     if (has_gcn) {
       GwDpArgs d{};
