@@ -156,6 +156,8 @@ int step_ts_encoder_fwd_bf16(const float *series, long long sB, long long sT, lo
  * K-major bf16 image [B][P*12 chunks][R = round_up(N,128)][8] (row = node, K = (patch, feature)) - the operand of the
  * tensor-core Gram GEMM below. */
 size_t step_tc_seq_image_bytes(int B, int N, int P);
+/* Build the same image from fp32 hidden states [B,N,P,96] (node-sharded mode: after the all-gather). */
+int step_tc_hidden_to_seq_image(const float *hidden, int B, int N, int P, void *seq_img, void *stream);
 /* Cosine-similarity Gram matrix from the sequence image on tcgen05 (similarity.py:6-16; norms = sqrt of the Gram
  * diagonal).  gram_scratch, sim: [B,N,N] fp32. */
 int step_tc_cosine_gram(const void *seq_img, int B, int N, int P, float *gram_scratch, float *sim, void *stream);

@@ -120,6 +120,9 @@ class TSFormer(nn.Module):
         self._tc_images = None
         self._tc_key = None
         self.seq_image = None        # bf16 Gram operand of the last bf16 forward ([B][P*12][R][8]); None in fp32 mode
+        # node-sharded mode (STEP_PEMS07 on several GPUs): (rank, world) -> this rank encodes only its node range and
+        # the hidden states are assembled with one NCCL all-gather (step_b200.parallel.all_gather_nodes)
+        self.node_shard = None
         self._calls = 0
         self.initialize_weights()
 
@@ -136,6 +139,12 @@ class TSFormer(nn.Module):
         if mask:
             raise NotImplementedError("masked pre-training encoder is listed as 'next' in DESIGN.md (SURVEY section 8(f).3)")
         series = long_term_history[:, :, 0, :].permute(0, 2, 1)      # [B, P*L, N] view, no copy
+        num_nodes = series.shape[2]
+        if self.node_shard is not None:
+            from step_b200 import parallel
+            rank, world = self.node_shard
+            n0, n1 = parallel.node_shard_bounds(num_nodes, rank, world)
+            series = series[:, :, n0:n1]
         drop = self.dropout_p if self.training else 0.0
         seed = self._next_seed() if drop > 0 else 0
         emb = self.patch_embedding.input_embedding
@@ -157,6 +166,11 @@ class TSFormer(nn.Module):
             hidden = ops.ts_encoder_forward(series, emb.weight, emb.bias, self.positional_encoding.position_embedding, layers,
                                             self.encoder_norm.weight, self.encoder_norm.bias, drop_p=drop, seed=seed,
                                             chunk_seqs=self.chunk_seqs)
+        if self.node_shard is not None:
+            from step_b200 import parallel
+            rank, world = self.node_shard
+            hidden = parallel.all_gather_nodes(hidden, num_nodes, rank, world)
+            self.seq_image = ops.tc_hidden_to_seq_image(hidden) if self.precision == "bf16" and hidden.shape[2] * 12 % 8 == 0 else None
         return hidden, None, None
 
     def forward(self, history_data: torch.Tensor, future_data: torch.Tensor = None, batch_seen: int = None,

@@ -1100,8 +1100,17 @@ extern "C" int step_gwnet_stack_bwd(const float *dskip, const float *x0, const f
       d.DH = stash + p.off_DH;
       d.dP[0] = dP1; d.dP[1] = dP2; d.dP[2] = dP3;
       d.pstride[0] = (long long)nn; d.pstride[1] = (long long)nn; d.pstride[2] = 0;
-      gw_dP_kernel<<<dim3((N + 63) / 64, (N + 63) / 64, 3 * B), 256, 0, st>>>(d);
-      STEP_LAUNCH_CHECK("gw_dP_kernel");
+      if (use_tc && tc_dP_supported(N)) {
+        TcDpArgs td{};
+        for (int s = 0; s < 3; ++s) {
+          td.Q[s] = d.Q[s]; td.A[s] = d.A[s]; td.DQ[s] = d.DQ[s]; td.dP[s] = d.dP[s]; td.pstride[s] = d.pstride[s];
+        }
+        td.DH = d.DH; td.B = B; td.T = d.T; td.N = N;
+        if ((rc = tc_dP_launch(td, st))) return rc;
+      } else {
+        gw_dP_kernel<<<dim3((N + 63) / 64, (N + 63) / 64, 3 * B), 256, 0, st>>>(d);
+        STEP_LAUNCH_CHECK("gw_dP_kernel");
+      }
     }
 
     GwBwdInArgs c{};

@@ -90,6 +90,23 @@ __global__ void tc_image_to_rows_kernel(const uint4 *__restrict__ img, long long
   for (int i = 0; i < 8; ++i) x[t * K + c * 8 + i] = v[i];
 }
 
+// fp32 hidden states [B,N,P,96] -> sequence-major bf16 image [B][P*12][R][8] (Gram operand); used when the
+// hidden states were assembled by an all-gather of node shards
+__global__ void tc_hidden_to_seq_image_kernel(const float *__restrict__ h, int B, int N, int P, int R, uint4 *__restrict__ img) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;    // (b, kc, n) with n fastest
+  const long long KC = (long long)P * 12;
+  if (idx >= (long long)B * KC * N) return;
+  const int n = (int)(idx % N);
+  const long long kc = (idx / N) % KC;
+  const long long b = idx / ((long long)N * KC);
+  const int p = (int)(kc / 12), cc = (int)(kc % 12);
+  const float *src = h + (((size_t)b * N + n) * P + p) * 96 + cc * 8;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = src[j];
+  img[((size_t)b * KC + kc) * R + n] = pack8_bf16(v);
+}
+
 // ===========================================================================
 // patch embedding -> X tile image.  block = (32 patches, 16 nodes, b): coalesced node-major reads of the
 // series through smem, coalesced row-major image writes.
@@ -844,6 +861,14 @@ extern "C" int step_tc_attention(const void *q_img, const void *k_img, const voi
 extern "C" size_t step_tc_seq_image_bytes(int B, int N, int P) {
   const size_t R = (size_t)(N + 127) / 128 * 128;
   return (size_t)B * P * 12 * R * 16;
+}
+
+extern "C" int step_tc_hidden_to_seq_image(const float *hidden, int B, int N, int P, void *seq_img, void *stream) {
+  STEP_REQUIRE(hidden && seq_img && B > 0 && N > 0 && P > 0, "tc_hidden_to_seq_image: bad argument");
+  const long long units = (long long)B * P * 12 * N;
+  tc_hidden_to_seq_image_kernel<<<(unsigned)((units + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      hidden, B, N, P, (N + 127) / 128 * 128, reinterpret_cast<uint4 *>(seq_img));
+  return check_launch("tc_hidden_to_seq_image_kernel");
 }
 
 extern "C" int step_tc_cosine_gram(const void *seq_img, int B, int N, int P, float *gram_scratch, float *sim, void *stream) {

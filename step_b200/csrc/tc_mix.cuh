@@ -228,4 +228,157 @@ inline int tc_support_images_launch(const float *P, int nb, const MixGeom &g, ui
   return check_launch("tc_support_images_kernel");
 }
 
+
+// ===========================================================================
+// Dense support gradient on tcgen05 (the straight-through estimator needs dL/dP for EVERY edge):
+//   dP_s[b][v][w] += sum_t sum_c ( q_s[b,t,v,c] dh[b,t,w,c] + a_s[b,t,v,c] dq_s[b,t,w,c] )
+// an "NT" GEMM with K = 2*T*32 per (sample, support).  Operands are fp32 activations in [B,T,N,32]; the CTA
+// splits them into bf16 hi/lo K-major images in shared memory itself (double buffered over t) and issues
+// hi*hi + hi*lo + lo*hi.  One CTA = (128-row tile of v, support x sample).
+// ===========================================================================
+struct TcDpArgs {
+  const float *Q[3], *A[3], *DQ[3], *DH;
+  float *dP[3];
+  long long pstride[3];       // 0: shared across the batch (adaptive adjacency) -> atomic accumulation
+  int B, T, N;
+};
+constexpr int DP_THREADS = 320;
+
+__global__ void __launch_bounds__(DP_THREADS, 1) tc_dP_kernel(TcDpArgs a) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t dp_smem[];
+  const int mt = blockIdx.x, sb = blockIdx.y, s = sb / a.B, b = sb - s * a.B;
+  const int N = a.N, Nb = (N + 15) / 16 * 16;
+  const uint32_t a_img = 8 * 128 * 16, b_img = 8u * Nb * 16;      // 8 chunks (2 pairs x 32 channels) per time step
+  const uint32_t stage_bytes = 2 * a_img + 2 * b_img;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(dp_smem + 2 * stage_bytes);
+  uint64_t *built = bars, *consumed = bars + 2, *d_full = bars + 4;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&built[i], 8); mbar_init(&consumed[i], 1); }
+    mbar_init(d_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const size_t col = (size_t)N * 32;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, Nb, 0, 0);
+      for (int t = 0; t < a.T; ++t) {
+        const int st = t & 1;
+        mbar_wait(&built[st], (t >> 1) & 1);
+        tc_fence_after();
+        const uint32_t ah = smem_u32(dp_smem + st * stage_bytes), al = ah + a_img, bh = al + a_img, bl = bh + b_img;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t dah = umma_desc(ah + kk * 2 * 2048, 2048, 128), dal = umma_desc(al + kk * 2 * 2048, 2048, 128);
+          const uint64_t dbh = umma_desc(bh + kk * 2 * Nb * 16, Nb * 16, 128), dbl = umma_desc(bl + kk * 2 * Nb * 16, Nb * 16, 128);
+          umma_bf16(tmem, dah, dbh, idesc, (t | kk) != 0 ? 1u : 0u);
+          umma_bf16(tmem, dah, dbl, idesc, 1u);
+          umma_bf16(tmem, dal, dbh, idesc, 1u);
+        }
+        umma_commit(&consumed[st]);
+      }
+      umma_commit(d_full);
+    }
+  } else if (warp >= 2) {
+    const int wt = threadIdx.x - 64;       // 0..255
+    for (int t = 0; t < a.T; ++t) {
+      const int st = t & 1;
+      mbar_wait(&consumed[st], ((t >> 1) & 1) ^ 1);
+      uint8_t *base = dp_smem + st * stage_bytes;
+      uint4 *Ah = reinterpret_cast<uint4 *>(base), *Al = reinterpret_cast<uint4 *>(base + a_img);
+      uint4 *Bh = reinterpret_cast<uint4 *>(base + 2 * a_img), *Bl = reinterpret_cast<uint4 *>(base + 2 * a_img + b_img);
+      const size_t toff = ((size_t)b * a.T + t) * col;
+      // A: rows v = mt*128 + r; chunk = pair*4 + cg
+      for (int u = wt; u < 8 * 128; u += 256) {
+        const int chunk = u >> 7, r = u & 127, pair = chunk >> 2, cg = chunk & 3, v = mt * 128 + r;
+        float hi[8], lo[8];
+        if (v < N) {
+          const float *src = (pair ? a.A[s] : a.Q[s]) + toff + (size_t)v * 32 + cg * 8;
+          const float4 x0 = reinterpret_cast<const float4 *>(src)[0], x1 = reinterpret_cast<const float4 *>(src)[1];
+          const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float h = __bfloat162float(__float2bfloat16_rn(x[j])); hi[j] = h; lo[j] = x[j] - h; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { hi[j] = 0.f; lo[j] = 0.f; }
+        }
+        Ah[u] = pack8_bf16(hi);
+        Al[u] = pack8_bf16(lo);
+      }
+      // B: rows w; chunk = pair*4 + cg
+      for (int u = wt; u < 8 * Nb; u += 256) {
+        const int chunk = u / Nb, w = u - chunk * Nb, pair = chunk >> 2, cg = chunk & 3;
+        float hi[8], lo[8];
+        if (w < N) {
+          const float *src = (pair ? a.DQ[s] : a.DH) + toff + (size_t)w * 32 + cg * 8;
+          const float4 x0 = reinterpret_cast<const float4 *>(src)[0], x1 = reinterpret_cast<const float4 *>(src)[1];
+          const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float h = __bfloat162float(__float2bfloat16_rn(x[j])); hi[j] = h; lo[j] = x[j] - h; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { hi[j] = 0.f; lo[j] = 0.f; }
+        }
+        Bh[u] = pack8_bf16(hi);
+        Bl[u] = pack8_bf16(lo);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&built[st]);
+    }
+    // epilogue (warps 2-5): dP[v][w] += D
+    if (warp < 6) {
+      const int q = warp & 3, v = mt * 128 + q * 32 + lane;
+      mbar_wait(d_full, 0);
+      tc_fence_after();
+      float *dst = a.dP[s] + (size_t)b * a.pstride[s] + (size_t)v * N;
+      const bool shared = a.pstride[s] == 0;
+      for (int c0 = 0; c0 < Nb; c0 += 32) {
+        float tv[32];
+        if (c0 + 32 <= Nb) {
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, tv);
+        } else {
+          float t16[16];
+          tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, t16);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) tv[c] = t16[c];
+#pragma unroll
+          for (int c = 16; c < 32; ++c) tv[c] = 0.f;
+        }
+        if (v < N) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (c0 + c < N) {
+              if (shared) atomicAdd(dst + c0 + c, tv[c]);
+              else dst[c0 + c] += tv[c];
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+inline bool tc_dP_supported(int N) { return (N + 15) / 16 * 16 <= 256; }
+
+inline int tc_dP_launch(const TcDpArgs &a, cudaStream_t st) {
+  int rc = allow_smem(tc_dP_kernel, 227 * 1024);
+  if (rc) return rc;
+  const int Nb = (a.N + 15) / 16 * 16;
+  const size_t smem = 2 * (size_t)(2 * 8 * 128 * 16 + 2 * 8 * Nb * 16) + 8 * 8 + 16;
+  tc_dP_kernel<<<dim3((a.N + 127) / 128, 3 * a.B), DP_THREADS, smem, st>>>(a);
+  return check_launch("tc_dP_kernel");
+}
+
 }  // namespace stepk

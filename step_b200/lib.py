@@ -63,6 +63,7 @@ SIGNATURES = {
                                            C.POINTER(TsLayerWeights), C.POINTER(TsLayerImages), C.c_int, f32p, f32p, f32p, vp, vp,
                                            C.c_size_t, C.c_float, ull, vp]),
     "step_tc_seq_image_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "step_tc_hidden_to_seq_image": (C.c_int, [f32p, C.c_int, C.c_int, C.c_int, vp, vp]),
     "step_tc_cosine_gram": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, f32p, f32p, vp]),
     "step_cosine_gram_f32": (C.c_int, [f32p, C.c_int, C.c_int, ll, f32p, f32p, vp]),
     "step_topk_mask_f32": (C.c_int, [f32p, C.c_int, C.c_int, C.c_int, f32p, vp]),

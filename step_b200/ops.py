@@ -395,6 +395,17 @@ def ts_encoder_forward_bf16(series: Tensor, patch_w: Tensor, patch_b: Tensor, po
     return (hidden, seq_img) if want_seq_image else hidden
 
 
+def tc_hidden_to_seq_image(hidden: Tensor) -> Tensor:
+    """fp32 hidden [B,N,P,96] -> bf16 sequence image (Gram operand)."""
+    hidden = _f32(hidden, "hidden")
+    B, N, P, _ = hidden.shape
+    st = _enter(hidden)
+    img = torch.empty(_L().step_tc_seq_image_bytes(B, N, P), device=hidden.device, dtype=torch.uint8)
+    check(_L().step_tc_hidden_to_seq_image(hidden.data_ptr(), B, N, P, img.data_ptr(), st), "step_tc_hidden_to_seq_image")
+    launch_counter["kernels"] += 1
+    return img
+
+
 def tc_cosine_gram(seq_img: Tensor, B: int, N: int, P: int) -> Tensor:
     """Cosine-similarity Gram matrix [B,N,N] from the encoder's bf16 sequence image (tcgen05)."""
     st = _enter(seq_img)

@@ -68,3 +68,30 @@ class FlatGradReducer:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.div_(self.world)
         return self.flat
+
+
+def node_shard_bounds(num_nodes: int, rank: int, world: int) -> tuple:
+    """[n0, n1) of the nodes whose TSFormer sequences `rank` encodes in node-sharded mode."""
+    sl = shard_batch(num_nodes, rank, world)
+    return sl.start, sl.stop
+
+
+def all_gather_nodes(local: torch.Tensor, num_nodes: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """Node-sharded mode (STEP_PEMS07): every rank encoded the sequences of its own node
+    range; ONE all-gather over NVLink assembles the full hidden states [B, N, P, d] before the N x N similarity.
+    `local`: [B, n1-n0, P, d].  Shards may differ by one node, so they travel padded to the largest shard."""
+    if world == 1:
+        return local
+    B, nloc, P, d = local.shape
+    nmax = (num_nodes + world - 1) // world
+    send = local
+    if nloc < nmax:
+        send = torch.zeros(B, nmax, P, d, device=local.device, dtype=local.dtype)
+        send[:, :nloc] = local
+    gathered = torch.empty(world, B, nmax, P, d, device=local.device, dtype=local.dtype)
+    dist.all_gather_into_tensor(gathered.view(world * B, nmax, P, d), send.contiguous(), group=group)
+    full = torch.empty(B, num_nodes, P, d, device=local.device, dtype=local.dtype)
+    for r in range(world):
+        n0, n1 = node_shard_bounds(num_nodes, r, world)
+        full[:, n0:n1] = gathered[r, :, : n1 - n0]
+    return full

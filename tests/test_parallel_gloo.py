@@ -70,3 +70,30 @@ def test_shard_batch():
         assert all(a.stop == b.start for a, b in zip(parts, parts[1:]))
         sizes = [p.stop - p.start for p in parts]
         assert max(sizes) - min(sizes) <= 1
+
+
+def _gather_worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from step_b200 import parallel
+    parallel.init_from_env("gloo")
+    B, N, P, d = 2, 7, 3, 4                        # 7 nodes over 2 ranks: shards of 4 and 3
+    full = torch.arange(B * N * P * d, dtype=torch.float32).view(B, N, P, d)
+    n0, n1 = parallel.node_shard_bounds(N, rank, world)
+    got = parallel.all_gather_nodes(full[:, n0:n1].contiguous(), N, rank, world)
+    out.put((rank, bool(torch.equal(got, full)), (n0, n1)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_all_gather_nodes_world2_uneven():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(out.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True, (0, 4)), (1, True, (4, 7))]
