@@ -182,19 +182,26 @@ struct TcLinearArgs {
 };
 
 __device__ __forceinline__ void layer_norm96(float *v, const float *w, const float *b) {
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-  for (int c = 0; c < 96; ++c) s += v[c];
-  const float mean = s * (1.f / 96.f);
-  float q = 0.f;
+  for (int c = 0; c < 96; c += 4) { s0 += v[c]; s1 += v[c + 1]; s2 += v[c + 2]; s3 += v[c + 3]; }
+  const float mean = ((s0 + s1) + (s2 + s3)) * (1.f / 96.f);
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
-  for (int c = 0; c < 96; ++c) { const float d = v[c] - mean; q = fmaf(d, d, q); }
-  const float rstd = rsqrtf(q * (1.f / 96.f) + 1e-5f);
+  for (int c = 0; c < 96; c += 4) {
+    const float d0 = v[c] - mean, d1 = v[c + 1] - mean, d2 = v[c + 2] - mean, d3 = v[c + 3] - mean;
+    q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+  }
+  const float rstd = rsqrtf(((q0 + q1) + (q2 + q3)) * (1.f / 96.f) + 1e-5f);
 #pragma unroll
   for (int c = 0; c < 96; ++c) v[c] = (v[c] - mean) * rstd * w[c] + b[c];
 }
 
+// MODE: epilogue (compile-time so that each variant gets its own register allocation);
+// FINAL: last encoder layer (second LayerNorm, fp32 row-major hidden states, optional Gram operand image)
+template <int MODE, bool FINAL>
 __global__ void __launch_bounds__(TCL_THREADS, 1) tc_linear_kernel(TcLinearArgs a) {
+  constexpr int mode = MODE;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int KS = a.K / 96, NB = a.Nout / 96;
   const uint32_t wbytes = (uint32_t)a.K * a.Nout * 2;
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_linear_kernel(TcLinearArgs 
   float *sLn = sBias + 384;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < a.Nout; i += blockDim.x) sBias[i] = a.bias[i];
-  if (a.mode == TCM_RESLN) {
+  if (mode == TCM_RESLN) {
     for (int i = threadIdx.x; i < 96; i += blockDim.x) {
       sLn[i] = a.ln_w[i]; sLn[96 + i] = a.ln_b[i];
       sLn[192 + i] = a.ln2_w ? a.ln2_w[i] : 1.f; sLn[288 + i] = a.ln2_b ? a.ln2_b[i] : 0.f;
@@ -318,13 +325,13 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_linear_kernel(TcLinearArgs 
           }
         }
 
-        if (a.mode == TCM_F32) {
+        if (mode == TCM_F32) {
           if (valid) {
             float *o = a.out_f32 + token * a.Nout + nb * 96;
 #pragma unroll
             for (int c = 0; c < 96; c += 4) *reinterpret_cast<float4 *>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
           }
-        } else if (a.mode == TCM_RELU_IMG) {
+        } else if (mode == TCM_RELU_IMG) {
           uint4 *o = reinterpret_cast<uint4 *>(a.out_img) + ((size_t)mt * (a.Nout / 8) + nb * 12) * 128 + row;
 #pragma unroll
           for (int cc = 0; cc < 12; ++cc) {
@@ -334,7 +341,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_linear_kernel(TcLinearArgs 
             if (a.thr16) drop8(x, ((uint64_t)token * a.Nout + nb * 96) / 8 + cc, a.thr16, a.dscale, a.key);
             o[cc * 128] = pack8_bf16(x);
           }
-        } else if (a.mode == TCM_RESLN) {
+        } else if (mode == TCM_RESLN) {
           const uint4 *res = reinterpret_cast<const uint4 *>(a.res) + ((size_t)mt * 12) * 128 + row;
 #pragma unroll
           for (int cc = 0; cc < 12; ++cc) {
@@ -345,18 +352,18 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_linear_kernel(TcLinearArgs 
             for (int j = 0; j < 8; ++j) v[cc * 8 + j] += r8[j];
           }
           layer_norm96(v, sLn, sLn + 96);
-          if (a.ln2_w != nullptr) layer_norm96(v, sLn + 192, sLn + 288);
-          if (a.out_img != nullptr) {
+          if (FINAL && a.ln2_w != nullptr) layer_norm96(v, sLn + 192, sLn + 288);
+          if (!FINAL || a.out_img != nullptr) {
             uint4 *o = reinterpret_cast<uint4 *>(a.out_img) + ((size_t)mt * 12) * 128 + row;
 #pragma unroll
             for (int cc = 0; cc < 12; ++cc) o[cc * 128] = pack8_bf16(&v[cc * 8]);
           }
-          if (a.out_f32 != nullptr && valid) {
+          if (FINAL && a.out_f32 != nullptr && valid) {
             float *o = a.out_f32 + token * 96;
 #pragma unroll
             for (int c = 0; c < 96; c += 4) *reinterpret_cast<float4 *>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
           }
-          if (a.seq_img != nullptr && valid) {
+          if (FINAL && a.seq_img != nullptr && valid) {
             // row = node, K index = (patch, feature): the operand layout of the cosine-similarity Gram GEMM
             const long long sq = token / a.P;
             const int pp = (int)(token - sq * a.P);
@@ -764,13 +771,26 @@ static int tc_linear_launch(const TcLinearArgs &a, cudaStream_t st) {
   if (!((a.K == 96 || a.K == 384) && a.Nout % 96 == 0 && a.Nout >= 96 && a.Nout <= 384))
     return fail(STEP_EUNSUPPORTED, "tc_linear: unsupported shape K=%lld Nout=%lld", a.K, a.Nout);
   const size_t smem = tcl_smem_bytes(a.K, a.Nout);
-  int rc = allow_smem(tc_linear_kernel, 227 * 1024);
-  if (rc) return rc;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = a.MT < sms ? a.MT : sms;
-  tc_linear_kernel<<<grid, TCL_THREADS, smem, st>>>(a);
+  const bool fin = (a.mode == TCM_RESLN) && (a.ln2_w != nullptr || a.out_f32 != nullptr || a.seq_img != nullptr);
+  int rc;
+#define TCL_LAUNCH(M, F)                                                        \
+  do {                                                                          \
+    if ((rc = allow_smem(tc_linear_kernel<M, F>, 227 * 1024))) return rc;       \
+    tc_linear_kernel<M, F><<<grid, TCL_THREADS, smem, st>>>(a);                 \
+  } while (0)
+  switch (a.mode) {
+    case TCM_F32: TCL_LAUNCH(TCM_F32, false); break;
+    case TCM_RELU_IMG: TCL_LAUNCH(TCM_RELU_IMG, false); break;
+    case TCM_QKV: TCL_LAUNCH(TCM_QKV, false); break;
+    default:
+      if (fin) TCL_LAUNCH(TCM_RESLN, true);
+      else TCL_LAUNCH(TCM_RESLN, false);
+  }
+#undef TCL_LAUNCH
   return check_launch("tc_linear_kernel");
 }
 
