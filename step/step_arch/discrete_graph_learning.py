@@ -31,6 +31,26 @@ def _load_pkl(path):
             return pickle.load(f, encoding="latin1")
 
 
+class _Tf32Linear(torch.autograd.Function):
+    """y = x W^T + b with TF32 tensor-core GEMMs in forward AND backward (the flag is re-applied in backward
+    because autograd runs it outside the forward's scope)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return torch.addmm(b, x, w.t())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            return g @ w, g.t() @ x, g.sum(0)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+
+
 class DiscreteGraphLearning(nn.Module):
     """Dynamic graph learning module."""
 
@@ -91,7 +111,7 @@ class DiscreteGraphLearning(nn.Module):
         scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
         return torch.stack([bn.running_mean, bn.running_var, scale, bn.bias - bn.running_mean * scale]).contiguous()
 
-    def _global_feature(self, device):
+    def _global_feature(self, device, tf32_fc=False):
         """Batch-invariant node embedding, reference :131-135.  [N, 100].  conv1/bn1/conv2/bn2 run in the fused
         trunk kernels (csrc/trunk.cu); the [N, dim_fc] x [dim_fc, 100] Linear is a plain library GEMM."""
         if self._feats_dev is None or self._feats_dev.device != device:
@@ -105,7 +125,18 @@ class DiscreteGraphLearning(nn.Module):
             n, L0 = self._feats_dev.shape
             self._update_running(self.bn1, s1[0], s1[1], n * (L0 - 9))
             self._update_running(self.bn2, s2[0], s2[1], n * (L0 - 18))
-        x = F.relu(self.fc(y2n))
+        if tf32_fc:
+            # performance precision: the [N, dim_fc] x [dim_fc, 100] Linear (and its two backward GEMMs) on the tensor
+            # cores in TF32 (fp32 accumulate); the fp32 parity mode keeps the exact fp32 GEMM
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = True
+            try:
+                x = _Tf32Linear.apply(y2n, self.fc.weight, self.fc.bias)
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
+            x = F.relu(x)
+        else:
+            x = F.relu(self.fc(y2n))
         return self._batch_norm(x, self.bn3, t)
 
     def get_k_nn_neighbor(self, data, k=11 * 207, metric="cosine"):
@@ -117,7 +148,7 @@ class DiscreteGraphLearning(nn.Module):
     def forward(self, long_term_history, tsformer):
         """long_term_history [B, P*L, N, C] -> (bernoulli_unnorm [B,N*N,2], hidden [B,N,P,d], adj_knn, sampled_adj)."""
         batch_size, _, num_nodes, _ = long_term_history.shape
-        feat = self._global_feature(long_term_history.device)
+        feat = self._global_feature(long_term_history.device, tf32_fc=getattr(tsformer, "precision", "fp32") == "bf16")
         hidden_states = tsformer(long_term_history[..., [0]])
         half = self.embedding_dim
         ut = self.fc_out.weight[:, :half] @ feat.t()                          # [100, N]  sender half (index j)

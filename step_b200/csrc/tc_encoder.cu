@@ -428,9 +428,12 @@ struct TcAttnArgs {
 constexpr int TCA_THREADS = 320;
 constexpr int TCA_QBUF = 4, TCA_KVBUF = 3;
 
+// PF > 0: sequence length known at compile time (168 for every 2016-step STEP config) -> unrolled column loops
+// without bounds predicates; DROP: attention-probability dropout compiled in or out.
+template <int PF, bool DROP>
 __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int P = a.P, Pk = a.Pk, RT = a.RT;
+  const int P = PF > 0 ? PF : a.P, Pk = PF > 0 ? (PF + 15) / 16 * 16 : a.Pk, RT = PF > 0 ? (PF + 127) / 128 : a.RT;
   const uint32_t KVB = 3u * Pk * 16;          // bytes of one K (or V) image
   const uint32_t PB = (uint32_t)(Pk / 8) * 2048;
   uint8_t *sQ = smem;                          // TCA_QBUF x 6144
@@ -585,7 +588,7 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
           }
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
-            if (a.thr16) drop8(&t[cc * 8], drop_base + (c0 >> 3) + cc, a.thr16, 1.0f, a.key);
+            if (DROP) drop8(&t[cc * 8], drop_base + (c0 >> 3) + cc, a.thr16, 1.0f, a.key);
             prow[(size_t)((c0 >> 3) + cc) * 128] = pack8_bf16(&t[cc * 8]);
           }
         }
@@ -610,7 +613,7 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             if (c_tail + cc * 8 < Pk) {
-              if (a.thr16) drop8(&t[cc * 8], drop_base + (c_tail >> 3) + cc, a.thr16, 1.0f, a.key);
+              if (DROP) drop8(&t[cc * 8], drop_base + (c_tail >> 3) + cc, a.thr16, 1.0f, a.key);
               prow[(size_t)((c_tail >> 3) + cc) * 128] = pack8_bf16(&t[cc * 8]);
             }
           }
@@ -863,12 +866,19 @@ static int tc_attn_launch(const void *q_img, const void *k_img, const void *v_im
   if (drop_p > 0.f) { a.thr16 = (uint32_t)(drop_p * 65536.0f); a.dscale = 1.f / (1.f - drop_p); }
   else { a.thr16 = 0; a.dscale = 1.f; }
   a.key = rng_key(seed, site);
-  int rc = allow_smem(tc_attn_kernel, 227 * 1024);
-  if (rc) return rc;
-  int dev = 0, sms = 148;
+  int dev = 0, sms = 148, rc;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  tc_attn_kernel<<<S < sms ? S : sms, TCA_THREADS, tca_smem_bytes(a.Pk), st>>>(a);
+  const int grid = S < sms ? S : sms;
+  const size_t smem = tca_smem_bytes(a.Pk);
+#define TCA_LAUNCH(PF, DR)                                                   \
+  do {                                                                       \
+    if ((rc = allow_smem(tc_attn_kernel<PF, DR>, 227 * 1024))) return rc;    \
+    tc_attn_kernel<PF, DR><<<grid, TCA_THREADS, smem, st>>>(a);              \
+  } while (0)
+  if (P == 168) { if (a.thr16) TCA_LAUNCH(168, true); else TCA_LAUNCH(168, false); }
+  else { if (a.thr16) TCA_LAUNCH(0, true); else TCA_LAUNCH(0, false); }
+#undef TCA_LAUNCH
   return check_launch("tc_attn_kernel");
 }
 
