@@ -267,6 +267,7 @@ struct GwFwdArgs {
   uint32_t drop_thr; float drop_scale; uint64_t key;
 };
 
+template <int STAGE>
 __global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int N = a.N, tid = threadIdx.x, t = blockIdx.x, b = blockIdx.y;
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
   const size_t ocol = ((size_t)b * a.Tout + t) * col;
   float *U = a.U + ocol, *Mb = a.M + ocol, *Hb = a.H + ocol;
 
-  if (a.stage <= 1) {
+  if (STAGE <= 1) {
   for (int i = tid; i < 1024; i += GW_THREADS) {
     Wb[i] = a.w.filter_w[2 * i]; Wb[1024 + i] = a.w.filter_w[2 * i + 1];
     Wb[2048 + i] = a.w.gate_w[2 * i]; Wb[3072 + i] = a.w.gate_w[2 * i + 1];
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
   }
   __syncthreads();
 
-  if (a.stage == 1) {
+  if (STAGE == 1) {
     // a_s = W_s2 u for the three supports -> global; the node mixes run on the tensor cores (tc_mix_kernel)
     for (int s = 0; s < 3; ++s) {
       const float *W2 = Wb + (2 + 2 * s) * 1024;
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
     }
     return;
   }
-  if (a.stage == 2) {
+  if (STAGE == 2) {
     // q_s = W_s1 u + (P_s^T a_s)
     for (int s = 0; s < 3; ++s) {
       const float *W1 = Wb + (1 + 2 * s) * 1024;
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
     return;
   }
   // ---- phase M: diffusion, Horner form per support ----
-  for (int s = 0; s < 3 && a.stage == 0; ++s) {
+  for (int s = 0; s < 3 && STAGE == 0; ++s) {
     const float *Ps = a.P[s] + (size_t)b * a.pstride[s];
     const float *W1 = Wb + (1 + 2 * s) * 1024, *W2 = Wb + (2 + 2 * s) * 1024;
     // a = W_s2 u  -> Y
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
     float *yr = Y + (size_t)n * GC, *zo = a.zout + ocol + (size_t)n * GC;
     const uint64_t elem0 = (uint64_t)(ocol + (size_t)n * GC);
     matvec_chunks(Wb, u, [&](int cg, float4 v) {
-      const float4 hsum = (a.stage == 0) ? ld4(hr + 4 * cg) : add4(add4(ld4(o0 + 4 * cg), ld4(o1 + 4 * cg)), ld4(o2 + 4 * cg));
+      const float4 hsum = (STAGE == 0) ? ld4(hr + 4 * cg) : add4(add4(ld4(o0 + 4 * cg), ld4(o1 + 4 * cg)), ld4(o2 + 4 * cg));
       v = add4(add4(v, hsum), ld4(a.w.mlp_b + 4 * cg));
       if (a.drop_thr) v = dropout4(v, elem0, cg, a.drop_thr, a.drop_scale, a.key);
       float4 r = ld4(zr + 4 * cg);
@@ -500,6 +501,7 @@ struct GwBwdArgs {
   uint32_t drop_thr; float drop_scale; uint64_t key;
 };
 
+template <int STAGE>
 __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int N = a.N, tid = threadIdx.x, t = blockIdx.x, b = blockIdx.y;
@@ -520,7 +522,7 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
   __syncthreads();
 
   // ---- phase 0: u, dz (through BatchNorm), dh (through dropout), du = W0^T dh ----
-  if (a.stage != 2) {
+  if (STAGE != 2) {
   for (int n = tid; n < N; n += GW_THREADS) {
     {
       float fv[GC], gv[GC];
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
   __syncthreads();
   }  // stage != 2
 
-  if (a.has_gcn && a.stage != 2) {
+  if (a.has_gcn && STAGE != 2) {
     // d mlp bias = column sums of dh
     {
       const int c = tid & 31, grp = tid >> 5;
@@ -574,8 +576,8 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
     }
     outer_acc(DH, U, N, tiles, a.gr.mlp_w, 224);  // block 0: dW0[co][ci] += dh[n][co] u[n][ci]
   }
-  if (a.stage == 1) return;
-  if (a.has_gcn && a.stage == 2) {
+  if (STAGE == 1) return;
+  if (a.has_gcn && STAGE == 2) {
     // dq_s = P_s dh and da_s = P_s dq_s were produced by tc_mix_kernel
     for (int s = 0; s < 3; ++s) {
       const float *W1 = Wb + (1 + 2 * s) * 1024, *W2 = Wb + (2 + 2 * s) * 1024;
@@ -598,7 +600,7 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
       outer_acc(DAs, U, N, tiles, a.gr.mlp_w + (2 + 2 * s) * 32, 224);
     }
   }
-  if (a.has_gcn && a.stage == 0) {
+  if (a.has_gcn && STAGE == 0) {
     for (int s = 0; s < 3; ++s) {
       const float *Pts = a.Pt[s] + (size_t)b * a.pstride[s];
       const float *W1 = Wb + (1 + 2 * s) * 1024, *W2 = Wb + (2 + 2 * s) * 1024;
@@ -926,8 +928,13 @@ static int gw_prepare(int N) {
   if (bwd_smem_bytes(N) > 227 * 1024)
     return fail(STEP_EUNSUPPORTED, "gwnet: N=%lld needs more shared memory than one SM has", N);
   int rc;
-  if ((rc = allow_smem(gw_layer_fwd_kernel, 227 * 1024))) return rc;
-  if ((rc = allow_smem(gw_layer_bwd_kernel, 227 * 1024))) return rc;
+  if ((rc = allow_smem(gw_layer_fwd_kernel<0>, 227 * 1024))) return rc;
+  if ((rc = allow_smem(gw_layer_fwd_kernel<1>, 227 * 1024))) return rc;
+  if ((rc = allow_smem(gw_layer_fwd_kernel<2>, 227 * 1024))) return rc;
+  if ((rc = allow_smem(gw_layer_fwd_kernel<3>, 227 * 1024))) return rc;
+  if ((rc = allow_smem(gw_layer_bwd_kernel<0>, 227 * 1024))) return rc;
+  if ((rc = allow_smem(gw_layer_bwd_kernel<1>, 227 * 1024))) return rc;
+  if ((rc = allow_smem(gw_layer_bwd_kernel<2>, 227 * 1024))) return rc;
   if ((rc = allow_smem(gw_layer_bwd_in_kernel, 227 * 1024))) return rc;
   return STEP_OK;
 }
@@ -975,8 +982,8 @@ extern "C" int step_gwnet_stack_fwd(const float *x0, const float *P1, const floa
     else { a.drop_thr = 0; a.drop_scale = 1.f; }
     a.key = rng_key(seed, 0x100u + i);
     if (!use_tc || !a.has_gcn) {
-      a.stage = a.has_gcn ? 0 : 1;
-      gw_layer_fwd_kernel<<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
+      if (a.has_gcn) gw_layer_fwd_kernel<0><<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
+      else gw_layer_fwd_kernel<1><<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
       STEP_LAUNCH_CHECK("gw_layer_fwd_kernel");
     } else {
       TcMixArgs m{};
@@ -988,18 +995,15 @@ extern "C" int step_gwnet_stack_fwd(const float *x0, const float *P1, const floa
         a.Min[s] = stash + p.off_M3[s];
         a.Oin[s] = stash + p.off_O3[s];
       }
-      a.stage = 1;
-      gw_layer_fwd_kernel<<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
+      gw_layer_fwd_kernel<1><<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
       STEP_LAUNCH_CHECK("gw_layer_fwd_kernel[conv]");
       for (int s = 0; s < 3; ++s) { m.Y[s] = stash + p.off_A[s]; m.out[s] = stash + p.off_M3[s]; }
       if ((rc = tc_mix_launch(m, st))) return rc;
-      a.stage = 2;
-      gw_layer_fwd_kernel<<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
+      gw_layer_fwd_kernel<2><<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
       STEP_LAUNCH_CHECK("gw_layer_fwd_kernel[q]");
       for (int s = 0; s < 3; ++s) { m.Y[s] = a.q[s]; m.out[s] = stash + p.off_O3[s]; }
       if ((rc = tc_mix_launch(m, st))) return rc;
-      a.stage = 3;
-      gw_layer_fwd_kernel<<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
+      gw_layer_fwd_kernel<3><<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
       STEP_LAUNCH_CHECK("gw_layer_fwd_kernel[out]");
     }
     if (a.has_gcn && training) {
@@ -1070,8 +1074,7 @@ extern "C" int step_gwnet_stack_bwd(const float *dskip, const float *x0, const f
     a.DA = stash + p.off_DA; a.DU = stash + p.off_DU; a.DPF = stash + p.off_DPF; a.DPG = stash + p.off_DPG;
     a.drop_thr = thr; a.drop_scale = dscale; a.key = rng_key(seed, 0x100u + i);
     if (!use_tc || !has_gcn) {
-      a.stage = 0;
-      gw_layer_bwd_kernel<<<dim3(a.Tout, B), GW_THREADS, bwd_smem_bytes(N), st>>>(a);
+      gw_layer_bwd_kernel<0><<<dim3(a.Tout, B), GW_THREADS, bwd_smem_bytes(N), st>>>(a);
       STEP_LAUNCH_CHECK("gw_layer_bwd_kernel");
     } else {
       TcMixArgs m{};
@@ -1081,15 +1084,13 @@ extern "C" int step_gwnet_stack_bwd(const float *dskip, const float *x0, const f
         m.img_bstride[s] = (s < 2) ? (long long)img_floats * 4 : 0;
         a.DA3[s] = stash + p.off_DA3[s];
       }
-      a.stage = 1;
-      gw_layer_bwd_kernel<<<dim3(a.Tout, B), GW_THREADS, bwd_smem_bytes(N), st>>>(a);
+      gw_layer_bwd_kernel<1><<<dim3(a.Tout, B), GW_THREADS, bwd_smem_bytes(N), st>>>(a);
       STEP_LAUNCH_CHECK("gw_layer_bwd_kernel[pre]");
       for (int s = 0; s < 3; ++s) { m.Y[s] = stash + p.off_DH; m.out[s] = stash + p.off_DQ[s]; }
       if ((rc = tc_mix_launch(m, st))) return rc;
       for (int s = 0; s < 3; ++s) { m.Y[s] = stash + p.off_DQ[s]; m.out[s] = stash + p.off_DA3[s]; }
       if ((rc = tc_mix_launch(m, st))) return rc;
-      a.stage = 2;
-      gw_layer_bwd_kernel<<<dim3(a.Tout, B), GW_THREADS, bwd_smem_bytes(N), st>>>(a);
+      gw_layer_bwd_kernel<2><<<dim3(a.Tout, B), GW_THREADS, bwd_smem_bytes(N), st>>>(a);
       STEP_LAUNCH_CHECK("gw_layer_bwd_kernel[post]");
     }
 
