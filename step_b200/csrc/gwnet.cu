@@ -232,6 +232,46 @@ __device__ __forceinline__ void outer_acc(const float *X, const float *U, int N,
   __syncthreads();
 }
 
+// dst[(blk)*32 + co*ldd + ci] += sum_n X_blk[n][co] * U[n][ci] for NB blocks sharing the U operand: one staging of
+// each 64-node U tile serves all blocks (tiles: (NB + 1) * 64 * 32 floats).
+template <int NB>
+__device__ __forceinline__ void outer_acc_multi(const float *const (&X)[NB], const float *U, int N, float *tiles,
+                                                float *const (&dst)[NB], int ldd) {
+  float *TU = tiles;
+  const int co = threadIdx.x >> 3, ci4 = (threadIdx.x & 7) * 4;
+  float acc[NB][4];
+#pragma unroll
+  for (int k = 0; k < NB; ++k) { acc[k][0] = 0.f; acc[k][1] = 0.f; acc[k][2] = 0.f; acc[k][3] = 0.f; }
+  for (int n0 = 0; n0 < N; n0 += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * (GC / 4); i += GW_THREADS) {
+      const int n = i >> 3, c4 = (i & 7) * 4;
+      const bool ok = (n0 + n) < N;
+      st4(TU + n * GC + c4, ok ? ld4(U + (size_t)(n0 + n) * GC + c4) : make_float4(0, 0, 0, 0));
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        st4(tiles + (k + 1) * 64 * GC + n * GC + c4, ok ? ld4(X[k] + (size_t)(n0 + n) * GC + c4) : make_float4(0, 0, 0, 0));
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int n = 0; n < 64; ++n) {
+      const float4 u = ld4(TU + n * GC + ci4);
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        const float x = tiles[(k + 1) * 64 * GC + n * GC + co];
+        acc[k][0] = fmaf(x, u.x, acc[k][0]); acc[k][1] = fmaf(x, u.y, acc[k][1]);
+        acc[k][2] = fmaf(x, u.z, acc[k][2]); acc[k][3] = fmaf(x, u.w, acc[k][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    float *d = dst[k] + (size_t)co * ldd + ci4;
+    atomicAdd(d, acc[k][0]); atomicAdd(d + 1, acc[k][1]); atomicAdd(d + 2, acc[k][2]); atomicAdd(d + 3, acc[k][3]);
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ void dropout_row(float (&h)[GC], uint64_t elem0, uint32_t thr, float scale, uint64_t key) {
   // elem0: flat index of channel 0 of this row (multiple of 32)
 #pragma unroll
@@ -596,8 +636,12 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
         matvec_t_acc(W2, DAs + (size_t)n * GC, du);
         store_row(DU + (size_t)n * GC, du);
       }
-      outer_acc(DQ, U, N, tiles, a.gr.mlp_w + (1 + 2 * s) * 32, 224);
-      outer_acc(DAs, U, N, tiles, a.gr.mlp_w + (2 + 2 * s) * 32, 224);
+    }
+    {
+      const float *const Xs[6] = {a.DQ[0] + ocol, a.DA3[0] + ocol, a.DQ[1] + ocol, a.DA3[1] + ocol, a.DQ[2] + ocol, a.DA3[2] + ocol};
+      float *const Ds[6] = {a.gr.mlp_w + 1 * 32, a.gr.mlp_w + 2 * 32, a.gr.mlp_w + 3 * 32,
+                            a.gr.mlp_w + 4 * 32, a.gr.mlp_w + 5 * 32, a.gr.mlp_w + 6 * 32};
+      outer_acc_multi<6>(Xs, U, N, tiles, Ds, 224);
     }
   }
   if (a.has_gcn && STAGE == 0) {
@@ -921,7 +965,7 @@ static bool gw_use_tc(int N) {
 }
 
 static size_t fwd_smem_bytes(int N) { return ((size_t)N * GC + 7 * 1024) * sizeof(float); }
-static size_t bwd_smem_bytes(int N) { return ((size_t)N * GC + 7 * 1024 + 2 * 64 * 33) * sizeof(float); }
+static size_t bwd_smem_bytes(int N) { return ((size_t)N * GC + 7 * 1024 + 7 * 64 * 32) * sizeof(float); }
 static size_t bwd_in_smem_bytes(int N) { return ((size_t)N * GC + 4 * 1024 + 2 * 64 * 33 + 128) * sizeof(float); }
 
 static int gw_prepare(int N) {

@@ -334,13 +334,14 @@ __global__ void __launch_bounds__(DP_THREADS, 1) tc_dP_kernel(TcDpArgs a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&built[st]);
     }
-    // epilogue (warps 2-5): dP[v][w] += D
+    // epilogue: TMEM -> smem tile [128][Nb+1] (warps 2-5, lane = row) -> coalesced read-modify-write of dP by all
+    // eight warps (one warp per row, consecutive lanes = consecutive columns)
+    float *tile = reinterpret_cast<float *>(dp_smem);       // the operand stages are dead once d_full has fired
+    const int ldt = Nb + 1;
+    mbar_wait(d_full, 0);
+    tc_fence_after();
     if (warp < 6) {
-      const int q = warp & 3, v = mt * 128 + q * 32 + lane;
-      mbar_wait(d_full, 0);
-      tc_fence_after();
-      float *dst = a.dP[s] + (size_t)b * a.pstride[s] + (size_t)v * N;
-      const bool shared = a.pstride[s] == 0;
+      const int q = warp & 3, r = q * 32 + lane;
       for (int c0 = 0; c0 < Nb; c0 += 32) {
         float tv[32];
         if (c0 + 32 <= Nb) {
@@ -353,14 +354,23 @@ __global__ void __launch_bounds__(DP_THREADS, 1) tc_dP_kernel(TcDpArgs a) {
 #pragma unroll
           for (int c = 16; c < 32; ++c) tv[c] = 0.f;
         }
-        if (v < N) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            if (c0 + c < N) {
-              if (shared) atomicAdd(dst + c0 + c, tv[c]);
-              else dst[c0 + c] += tv[c];
-            }
-          }
+        for (int c = 0; c < 32; ++c) if (c0 + c < Nb) tile[r * ldt + c0 + c] = tv[c];
+      }
+    }
+    // named barrier over the 8 builder/epilogue warps (256 threads); warps 0/1 do not take part
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    {
+      const bool shared = a.pstride[s] == 0;
+      float *dstb = a.dP[s] + (size_t)b * a.pstride[s];
+      for (int r = warp - 2; r < 128; r += 8) {
+        const int v = mt * 128 + r;
+        if (v >= N) break;
+        float *dst = dstb + (size_t)v * N;
+        for (int c = lane; c < N; c += 32) {
+          const float x = tile[r * ldt + c];
+          if (shared) atomicAdd(dst + c, x);
+          else dst[c] += x;
         }
       }
     }
