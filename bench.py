@@ -293,33 +293,74 @@ def main():
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline of the dominant kernel group, timed alone with CUDA events on the launching stream ----
+    # ---- rooflines: kernels timed alone with CUDA events on the launching stream (after warm-up) ----
     pk = peaks()
-    tokens = B * NODES * PATCHES
+    S_seq = B * NODES
+    tokens = S_seq * PATCHES
     enc_flops = B * NODES * (4 * (PATCHES * (2 * 96 * 288 + 2 * 96 * 96 + 4 * 96 * 384) + 4 * 4 * PATCHES * PATCHES * 24)
                              + 2 * PATCHES * 12 * 96)
     lh = resident[0][1]
 
+    def time_ms(fn, reps=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
     def enc_once():
         with torch.no_grad():
             return model.tsformer(lh[..., [0]])
-    for _ in range(3):
-        enc_once()
-    reps = 10
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        enc_once()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    enc_ms = e0.elapsed_time(e1) / reps
+    enc_ms = time_ms(enc_once)
     enc_tflops = enc_flops / (enc_ms * 1e-3) / 1e12
+    drop = 0.0 if args.no_dropout else 0.1
+    roofline_other = [{"kernel": "TSFormer encoder, 21 launches (tc_embed + 4 x [QKV, attention, out+LN1, FFN1, FFN2+LN2])"
+                       if args.precision == "bf16" else "TSFormer encoder, fp32 CUDA-core kernels",
+                       "bound": "tensor", "achieved": enc_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                       "frac": enc_tflops / pk["bf16_tflops"], "ms": enc_ms, "useful_flops": enc_flops}]
     if args.precision == "bf16":
-        roof_name = ("TSFormer encoder, 21 launches: tc_embed + 4 x (tc_linear[QKV] + tc_attn + tc_linear[out+LN1] + "
-                     "tc_linear[FFN1] + tc_linear[FFN2+LN2]) on tcgen05, %d tokens" % tokens)
+        L = ops._L()
+        x_img = ops.tc_rows_to_image(torch.randn(tokens, 96, device=dev))
+        w_in = ops.tc_pack_weight(torch.randn(288, 96, device=dev) * 0.15)
+        b_in = torch.zeros(288, device=dev)
+        q = torch.empty(L.step_tc_attn_image_bytes(S_seq, PATCHES, 0), device=dev, dtype=torch.uint8)
+        k = torch.empty(L.step_tc_attn_image_bytes(S_seq, PATCHES, 1), device=dev, dtype=torch.uint8)
+        v = torch.empty(L.step_tc_attn_image_bytes(S_seq, PATCHES, 1), device=dev, dtype=torch.uint8)
+        o = torch.empty(((tokens + 127) // 128) * 96 * 256, device=dev, dtype=torch.uint8)
+        st = ops._enter(x_img)
+        ops.check(L.step_tc_qkv(x_img.data_ptr(), w_in.data_ptr(), b_in.data_ptr(), S_seq, PATCHES, q.data_ptr(), k.data_ptr(),
+                                v.data_ptr(), st), "step_tc_qkv")
+        att_ms = time_ms(lambda: ops.check(L.step_tc_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), S_seq,
+                                                              PATCHES, drop, 1, st), "step_tc_attention"))
+        att_flops = 4.0 * S_seq * 4 * PATCHES * PATCHES * 24            # useful (unpadded) QK^T + PV flops of one layer
+        att_tflops = att_flops / (att_ms * 1e-3) / 1e12
+        w1 = ops.tc_pack_weight(torch.randn(384, 96, device=dev) * 0.1)
+        b1 = torch.zeros(384, device=dev)
+        ffn_ms = time_ms(lambda: ops.tc_linear(x_img, w1, b1, tokens, 96, 384, 1))
+        ffn_bytes = tokens * (96 + 384) * 2.0                            # bf16 activations in + out (weights stay in smem)
+        ffn_gbs = ffn_bytes / (ffn_ms * 1e-3) / 1e9
+        roofline = {"kernel": "tc_attn_kernel<168,%d> (one TSFormer layer: S=QK^T, softmax, PV on tcgen05; %d sequences x 4 heads, "
+                              "P=168, head dim 24)" % (1 if drop > 0 else 0, S_seq),
+                    "bound": "tensor", "achieved": att_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": att_tflops / pk["bf16_tflops"], "ms": att_ms, "useful_flops": att_flops,
+                    "traffic": 970.5e6, "traffic_source": "profiles/r01_ncu_full_attn.txt (dram read+write per launch)",
+                    "peak_source": pk["source"] + " (burst cuBLAS bf16, kernel timed alone)",
+                    "note": "head dim 24 makes this kernel exp/issue-bound, not MMA-bound (SURVEY section 7): the XU pipe is at 27% "
+                            "and the tensor pipe at 8% in the ncu capture"}
+        roofline_other.append({"kernel": "tc_linear_kernel<1,0> (FFN1 [T,96]x[96,384] + bias + ReLU -> bf16 image)", "bound": "hbm",
+                               "achieved": ffn_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ffn_gbs / pk["hbm_gbs"],
+                               "ms": ffn_ms, "algorithmic_bytes": ffn_bytes})
+        del x_img, q, k, v, o
     else:
-        roof_name = "TSFormer encoder, fp32 CUDA-core kernels (gemm_tn_kernel / attn_fwd_kernel), %d tokens" % tokens
+        roofline = dict(roofline_other[0])
+        roofline["traffic"] = None
+        roofline["peak_source"] = pk["source"]
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -343,10 +384,7 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": roof_name, "bound": "tensor", "achieved": enc_tflops, "peak": pk["bf16_tflops"],
-                     "unit": "TFLOP/s", "frac": enc_tflops / pk["bf16_tflops"], "traffic": None,
-                     "peak_source": pk["source"] + " (burst cuBLAS bf16, kernels timed alone)", "ms": enc_ms,
-                     "useful_flops": enc_flops},
+        "roofline": roofline, "roofline_other": roofline_other,
         "loss": losses[-1] if losses else None,
     }
     if not args.no_cpu_baseline:
