@@ -208,6 +208,18 @@ int step_gumbel_sample_bwd(const float *dsampled, const float *y0, int B, int N,
 
 
 /* ------------------------------------------------------------------------ *
+ * STEP loss, value + gradients in one call
+ *   step/step_loss/step_loss.py:5-16 + basicts/metrics/mae.py:5-28 + basicts/data/transform.py:48-65
+ *   loss = masked_mae(pred*std+mean, real*std+mean, null_val) + coeff * BCE(theta, adj_knn)
+ * pred/real: n_pred values of the selected target feature (unscaled); theta: [N,N] (batch-invariant);
+ * adj_knn: [B,N,N].  use_nan_mask != 0 <=> null_val is NaN.  Outputs: loss [1], dpred [n_pred] (w.r.t. the unscaled
+ * prediction), dtheta [N,N].  scratch: >= 64 bytes.
+ * ------------------------------------------------------------------------ */
+int step_loss_fwd_bwd(const float *pred, const float *real, long long n_pred, float mean, float stdv, float null_val,
+                      int use_nan_mask, const float *theta, const float *adj_knn, int B, int N, float coeff, float *loss,
+                      float *dpred, float *dtheta, void *scratch, void *stream);
+
+/* ------------------------------------------------------------------------ *
  * Discrete graph learning: convolutional part of the batch-invariant "global feature" trunk
  *   step/step_arch/discrete_graph_learning.py:131-133
  *   x [N, L0] -> Conv1d(1,8,10) -> ReLU -> BN(8) -> Conv1d(8,16,10) -> ReLU -> BN(16) -> y2n [N, 16, L0-18]

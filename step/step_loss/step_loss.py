@@ -18,6 +18,12 @@ def masked_mae(preds: torch.Tensor, labels: torch.Tensor, null_val: float = np.n
 
 
 def step_loss(prediction, real_value, theta, priori_adj, gsl_coefficient, null_val=np.nan):
+    """Reference signature (step/step_loss/step_loss.py:5).  On CUDA with the batch-invariant theta our STEP module
+    returns (a stride-0 expanded [N,N] tensor), value and gradients come from the fused kernels
+    (step_loss_fwd_bwd); any other input takes the elementwise formulation below (same math)."""
+    if prediction.is_cuda and theta.dim() == 3 and theta.stride(0) == 0 and prediction.dtype == torch.float32:
+        from step_b200 import ops
+        return ops.FusedStepLoss.apply(prediction, real_value, theta[0], priori_adj, float(gsl_coefficient), float(null_val), 0.0, 1.0)
     # theta may be an expanded (stride-0) view of the batch-invariant [N,N] probabilities
     log_t = torch.log(theta).clamp_min(-100.0)
     log_1mt = torch.log(1.0 - theta).clamp_min(-100.0)

@@ -270,3 +270,92 @@ extern "C" int step_gumbel_sample_bwd(const float *dsampled, const float *y0, in
                                                                                     accumulate, dlogits);
   return check_launch("gumbel_bwd_kernel");
 }
+
+// ===========================================================================
+// STEP loss, forward + backward in two launches:
+//   loss = masked_mae(pred, real, null_val) + coeff * BCE(theta, adj_knn)
+//   step/step_loss/step_loss.py:5-16, basicts/metrics/mae.py:5-28 (mask = |real - null| > 5e-5, weights mask/mean(mask)),
+//   nn.BCELoss (log clamped at -100).  theta is the batch-invariant [N,N] probability matrix (the reference's
+//   [B,N,N] tensor has B identical slices), adj_knn [B,N,N].
+// ===========================================================================
+namespace stepk {
+
+// sums[0] = sum |p - y| * m, sums[1] = sum m, sums[2] = sum_ij (c1 log(th) + (B - c1) log(1 - th))
+__global__ void __launch_bounds__(256) step_loss_reduce_kernel(const float *__restrict__ pred, const float *__restrict__ real,
+                                                               long long n_pred, float mean, float stdv, float null_val,
+                                                               int use_nan_mask, const float *__restrict__ theta,
+                                                               const float *__restrict__ knn, int B, long long nn,
+                                                               double *__restrict__ sums) {
+  float s_abs = 0.f, s_m = 0.f, s_bce = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pred; i += stride) {
+    const float y = fmaf(real[i], stdv, mean), p = fmaf(pred[i], stdv, mean);
+    const bool m = use_nan_mask ? !isnan(y) : (fabsf(y - null_val) > 5e-5f);
+    if (m) { s_abs += fabsf(p - y); s_m += 1.f; }
+  }
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nn; e += stride) {
+    float c1 = 0.f;
+    for (int b = 0; b < B; ++b) c1 += knn[(size_t)b * nn + e];
+    const float th = theta[e];
+    s_bce += c1 * fmaxf(logf(th), -100.f) + ((float)B - c1) * fmaxf(logf(1.f - th), -100.f);
+  }
+  __shared__ float red[3][8];
+  s_abs = warp_sum(s_abs); s_m = warp_sum(s_m); s_bce = warp_sum(s_bce);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[0][w] = s_abs; red[1][w] = s_m; red[2][w] = s_bce; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+    atomicAdd(sums + threadIdx.x, (double)t);
+  }
+}
+
+// loss value + gradients (d loss / d pred in the *unscaled* prediction space, d loss / d theta)
+__global__ void __launch_bounds__(256) step_loss_finish_kernel(const float *__restrict__ pred, const float *__restrict__ real,
+                                                               long long n_pred, float mean, float stdv, float null_val,
+                                                               int use_nan_mask, const float *__restrict__ theta,
+                                                               const float *__restrict__ knn, int B, long long nn, float coeff,
+                                                               const double *__restrict__ sums, float *__restrict__ loss,
+                                                               float *__restrict__ dpred, float *__restrict__ dtheta) {
+  const double sm = sums[1];
+  const float inv_m = sm > 0.0 ? (float)(1.0 / sm) : 0.f;
+  const float bce_scale = coeff / ((float)B * (float)nn);
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    loss[0] = (sm > 0.0 ? (float)(sums[0] / sm) : 0.f) - bce_scale * (float)sums[2];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pred; i += stride) {
+    const float y = fmaf(real[i], stdv, mean), p = fmaf(pred[i], stdv, mean);
+    const bool m = use_nan_mask ? !isnan(y) : (fabsf(y - null_val) > 5e-5f);
+    const float d = p - y;
+    dpred[i] = m ? (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * inv_m * stdv : 0.f;
+  }
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nn; e += stride) {
+    float c1 = 0.f;
+    for (int b = 0; b < B; ++b) c1 += knn[(size_t)b * nn + e];
+    const float th = theta[e];
+    // d/dth of -(c1 log th + (B-c1) log(1-th)); the -100 clamp has zero slope where it is active
+    const float g1 = (logf(th) > -100.f) ? c1 / th : 0.f;
+    const float g0 = (logf(1.f - th) > -100.f) ? ((float)B - c1) / (1.f - th) : 0.f;
+    dtheta[e] = -bce_scale * (g1 - g0);
+  }
+}
+
+}  // namespace stepk
+
+extern "C" int step_loss_fwd_bwd(const float *pred, const float *real, long long n_pred, float mean, float stdv, float null_val,
+                                 int use_nan_mask, const float *theta, const float *adj_knn, int B, int N, float coeff,
+                                 float *loss, float *dpred, float *dtheta, void *scratch, void *stream) {
+  STEP_REQUIRE(pred && real && theta && adj_knn && loss && dpred && dtheta && scratch && n_pred > 0 && B > 0 && N > 0,
+               "step_loss_fwd_bwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  double *sums = reinterpret_cast<double *>(scratch);
+  cudaError_t e = cudaMemsetAsync(sums, 0, 3 * sizeof(double), st);
+  if (e != cudaSuccess) return fail_msg((int)e, cudaGetErrorString(e));
+  const long long nn = (long long)N * N;
+  step_loss_reduce_kernel<<<296, 256, 0, st>>>(pred, real, n_pred, mean, stdv, null_val, use_nan_mask, theta, adj_knn, B, nn, sums);
+  STEP_LAUNCH_CHECK("step_loss_reduce_kernel");
+  step_loss_finish_kernel<<<296, 256, 0, st>>>(pred, real, n_pred, mean, stdv, null_val, use_nan_mask, theta, adj_knn, B, nn, coeff,
+                                               sums, loss, dpred, dtheta);
+  return check_launch("step_loss_finish_kernel");
+}

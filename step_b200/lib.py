@@ -71,6 +71,8 @@ SIGNATURES = {
     "step_edge_logits_bwd": (C.c_int, [f32p, f32p, f32p, f32p, C.c_int, C.c_int, f32p, f32p, f32p, f32p, vp]),
     "step_gumbel_sample_fwd": (C.c_int, [f32p, f32p, C.c_int, C.c_int, C.c_float, ull, f32p, f32p, vp]),
     "step_gumbel_sample_bwd": (C.c_int, [f32p, f32p, C.c_int, C.c_int, C.c_float, C.c_int, f32p, vp]),
+    "step_loss_fwd_bwd": (C.c_int, [f32p, f32p, ll, C.c_float, C.c_float, C.c_float, C.c_int, f32p, f32p, C.c_int, C.c_int,
+                                    C.c_float, f32p, f32p, f32p, vp, vp]),
     "step_dgl_conv_fwd": (C.c_int, [f32p, C.c_int, C.c_int] + [f32p] * 8 + [C.c_float, C.c_int, f32p, f32p, f32p, f32p, vp, vp]),
     "step_dgl_conv_bwd": (C.c_int, [f32p, f32p, C.c_int, C.c_int] + [f32p] * 5 + [C.c_float] + [f32p] * 12 + [vp, vp]),
     "step_gwnet_stash_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

@@ -467,3 +467,35 @@ class TrunkConv(torch.autograd.Function):
               "step_dgl_conv_bwd")
         launch_counter["kernels"] += 5
         return (None, *grads, None, None, None, None)
+
+
+# --------------------------------------------------------------------------- #
+# fused STEP loss (masked MAE + graph BCE), value and gradients from one pass
+# --------------------------------------------------------------------------- #
+class FusedStepLoss(torch.autograd.Function):
+    """(pred [..], real [..] unscaled target feature, theta [N,N], adj_knn [B,N,N]) -> scalar loss."""
+
+    @staticmethod
+    def forward(ctx, pred, real, theta, adj_knn, coeff, null_val, mean, std):
+        import math
+        pred, real, theta, adj_knn = _f32(pred, "pred"), _f32(real, "real"), _f32(theta, "theta"), _f32(adj_knn, "adj_knn")
+        B, N, _ = adj_knn.shape
+        st = _enter(pred)
+        dev = pred.device
+        loss = torch.empty(1, device=dev, dtype=torch.float32)
+        dpred = torch.empty_like(pred)
+        dtheta = torch.empty_like(theta)
+        scratch = torch.empty(64, device=dev, dtype=torch.uint8)
+        nan_mask = 1 if (isinstance(null_val, float) and math.isnan(null_val)) else 0
+        check(_L().step_loss_fwd_bwd(pred.data_ptr(), real.data_ptr(), pred.numel(), float(mean), float(std),
+                                     0.0 if nan_mask else float(null_val), nan_mask, theta.data_ptr(), adj_knn.data_ptr(), B, N,
+                                     float(coeff), loss.data_ptr(), dpred.data_ptr(), dtheta.data_ptr(), scratch.data_ptr(), st),
+              "step_loss_fwd_bwd")
+        launch_counter["kernels"] += 2
+        ctx.save_for_backward(dpred, dtheta)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        dpred, dtheta = ctx.saved_tensors
+        return dpred * g, None, dtheta * g, None, None, None, None, None

@@ -351,3 +351,28 @@ def test_trunk_conv_fwd_bwd(N, L0):
         out_e, _, _ = ops.TrunkConv.apply(x.to(DEV), *[prm[k].to(DEV) for k in ("w1", "b1", "g1", "be1", "w2", "b2", "g2", "be2")],
                                           1e-5, False, st1.to(DEV), st2.to(DEV))
     assert (out_e.cpu() - y.reshape(N, -1)).abs().max().item() < 2e-4
+
+
+# --------------------------------------------------------------------------- fused loss
+@pytest.mark.parametrize("null_val", [0.0, float("nan")])
+def test_fused_step_loss_matches_oracle(null_val):
+    from step.step_loss import step_loss
+    g = torch.Generator().manual_seed(4)
+    B, N = 3, 37
+    pred = torch.randn(B, 12, N, 1, generator=g).requires_grad_(True)
+    real = torch.randn(B, 12, N, 1, generator=g)
+    real[0, :, 5] = 0.0
+    real[1, 3, :4] = float("nan") if math.isnan(null_val) else 0.0
+    th = torch.rand(N, N, generator=g).clamp(1e-4, 1 - 1e-4).requires_grad_(True)
+    th.data[0, 0] = 1.0            # exercises the -100 clamp of BCELoss
+    prior = (torch.rand(B, N, N, generator=g) > 0.9).float()
+    ref = O.step_loss(pred, real, th.unsqueeze(0).expand(B, N, N), prior, 0.5, null_val=null_val)
+    ref.backward()
+    p2 = pred.detach().to(DEV).requires_grad_(True)
+    t2 = th.detach().to(DEV).requires_grad_(True)
+    out = step_loss(p2, real.to(DEV), t2.unsqueeze(0).expand(B, N, N), prior.to(DEV), 0.5, null_val=null_val)
+    assert abs(out.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    (out * 2.0).backward()
+    assert rel_err(p2.grad.cpu(), 2.0 * pred.grad) < 1e-5
+    mask = torch.ones(N, N, dtype=torch.bool); mask[0, 0] = False
+    assert rel_err(t2.grad.cpu()[mask], 2.0 * th.grad[mask]) < 1e-4

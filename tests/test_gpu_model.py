@@ -162,3 +162,38 @@ def test_large_graph_shapes_run_and_stay_consistent(dataset, B, P, tmp_path):
     assert (outs["tc"][0] - outs["simt"][0]).abs().mean().item() < 1e-5
     for a, b in zip(outs["tc"][1:], outs["simt"][1:]):
         assert (a - b).abs().max().item() <= 2e-3 * max(b.abs().max().item(), 1e-6)
+
+
+def test_runner_contract_train_iters(tmp_path):
+    """The runner glue (reference step_runner.py:43-75 + base_tsf_runner.py:225-255): host tuple in, loss out,
+    gradients for the trainable parameters, curriculum slicing of the loss horizon."""
+    import pickle
+    from step.configs import step_config
+    from step.step_data import ForecastingDataset
+    ds_name, n = "METR-LA", 207
+    d = tmp_path / "datasets" / ds_name
+    d.mkdir(parents=True)
+    with open(d / "data_in12_out12.pkl", "wb") as f:
+        pickle.dump({"processed_data": O.synthetic_node_feats(ds_name, 0).unsqueeze(-1).numpy()}, f)
+    (tmp_path / "tsformer_ckpt").mkdir()
+    torch.save({"model_state_dict": torch.load(os.path.join(GOLDEN, "tsformer_METR-LA_state.pt"))},
+               tmp_path / "tsformer_ckpt" / "TSFormer_METR-LA.pt")
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        cfg = step_config(ds_name)
+        runner = cfg.RUNNER(cfg, device=DEV)
+    finally:
+        os.chdir(cwd)
+    runner.model.train()
+    data = ForecastingDataset(mode="train", seq_len=2016, synthetic=True, num_nodes=n, length=4)
+    batch = tuple(torch.stack(x) for x in zip(*[data[i] for i in range(2)]))          # (future, history, long_history) on the host
+    assert batch[2].shape == (2, 2016, n, 3) and not batch[0].is_cuda
+    pred, real, pred_adj, prior_adj, coeff = runner.forward(batch, epoch=1, iter_num=0, train=True)
+    assert pred.shape == (2, 12, n, 1) and real.shape == (2, 12, n, 1) and pred_adj.shape == (2, n, n) and coeff == 1.0
+    assert runner.curriculum_learning(1) == 1 and runner.curriculum_learning(7) == 2 and runner.curriculum_learning(100) == 12
+    loss = runner.train_iters(1, 0, batch)
+    loss.backward()
+    assert torch.isfinite(loss)
+    assert runner.model.backend.start_conv.weight.grad is not None
+    assert all(p.grad is None for p in runner.model.tsformer.parameters())
