@@ -27,15 +27,17 @@ enum { TCM_F32 = 0, TCM_RELU_IMG = 1, TCM_RESLN = 2, TCM_QKV = 3 };
 // which matters because TSFormer draws 3.0 G attention-probability masks per step; still counter-based,
 // so a mask is a pure function of (seed, site, element index).
 __device__ __forceinline__ uint32_t hash32(uint32_t x) {
-  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  // one odd multiply spreads the counter into the high half, the xor-fold brings it back into the low half, a second
+  // multiply-fold decorrelates neighbouring counters; 16-bit halves are used as two Bernoulli thresholds
+  x *= 0x9E3779B1u; x ^= x >> 16; x *= 0x85EBCA77u; x ^= x >> 15;
   return x;
 }
 __device__ __forceinline__ void drop8(float *v, uint64_t idx8, uint32_t thr16, float scale, uint64_t key) {
   const uint32_t salt = (uint32_t)key ^ ((uint32_t)(key >> 32) * 0x9E3779B9u) ^ ((uint32_t)(idx8 >> 30) * 0x85EBCA6Bu);
-  const uint32_t c = (uint32_t)idx8 << 2;
+  const uint32_t c = ((uint32_t)idx8 << 2) ^ salt;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const uint32_t w = hash32((c + i) ^ salt);
+    const uint32_t w = hash32(c + (uint32_t)i * 0x632BE5ABu);
     v[2 * i] = ((w & 0xFFFFu) >= thr16) ? v[2 * i] * scale : 0.f;
     v[2 * i + 1] = ((w >> 16) >= thr16) ? v[2 * i + 1] * scale : 0.f;
   }
@@ -108,55 +110,59 @@ __global__ void tc_hidden_to_seq_image_kernel(const float *__restrict__ h, int B
 }
 
 // ===========================================================================
-// patch embedding -> X tile image.  block = (32 patches, 16 nodes, b): coalesced node-major reads of the
-// series through smem, coalesced row-major image writes.
+// patch embedding -> X tile image.  block = (32 patches, 16 nodes, b) = 512 tokens; the series tile is staged
+// through smem (coalesced node-major reads); thread = (feature chunk c, token lane): the 8 x 12 weights of its
+// chunk live in registers and the thread walks over the block's tokens, so the inner loop is 12 broadcast-free
+// LDS + 96 FMA + one coalesced 16-byte image store per token.
 // ===========================================================================
 __global__ void __launch_bounds__(256) tc_embed_kernel(const float *__restrict__ series, long long sB, long long sT,
                                                        long long sN, int N, int P, const float *__restrict__ w,
                                                        const float *__restrict__ bias, const float *__restrict__ pos,
                                                        uint4 *__restrict__ img, uint32_t thr16, float dscale, uint64_t key) {
-  __shared__ float sw[96 * 12];
-  __shared__ float sb[96];
-  __shared__ float sv[16][32 * 12 + 1];   // [node][time]
+  __shared__ float sv[16][32 * 13 + 3];   // [node][patch][13]: 12 time steps + 1 pad word (conflict-free strided reads)
   const int b = blockIdx.z, n0 = blockIdx.y * 16, p0 = blockIdx.x * 32, tid = threadIdx.x;
-  for (int i = tid; i < 96 * 12; i += 256) sw[i] = w[i];
-  if (tid < 96) sb[tid] = bias[tid];
   const int np = min(32, P - p0);
   for (int i = tid; i < 16 * np * 12; i += 256) {
     const int nn = i & 15, tt = i >> 4;
     const int n = n0 + nn;
-    sv[nn][tt] = (n < N) ? series[b * sB + (long long)(p0 * 12 + tt) * sT + n * sN] : 0.f;
+    sv[nn][(tt / 12) * 13 + tt % 12] = (n < N) ? series[b * sB + (long long)(p0 * 12 + tt) * sT + n * sN] : 0.f;
+  }
+  const int c = tid / 21, lane = tid % 21;          // 12 chunks x 21 token lanes (252 of 256 threads): a warp stores consecutive image rows
+  float wr[8][12], br[8];
+  if (c < 12) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      br[j] = bias[c * 8 + j];
+#pragma unroll
+      for (int t = 0; t < 12; ++t) wr[j][t] = w[(c * 8 + j) * 12 + t];
+    }
   }
   __syncthreads();
-  const int pp = tid & 31, ng = tid >> 5;
-  if (pp >= np) return;
-  const int p = p0 + pp;
+  if (c >= 12) return;
   const float scale = sqrtf(96.f);
-  for (int k = 0; k < 2; ++k) {
-    const int nn = ng * 2 + k, n = n0 + nn;
+  for (int tk = lane; tk < 16 * np; tk += 21) {
+    const int nn = tk / np, pp = tk - nn * np;      // consecutive lanes -> consecutive patches of one node: consecutive image rows
+    const int n = n0 + nn;
     if (n >= N) break;
+    const int p = p0 + pp;
     float x[12];
 #pragma unroll
-    for (int t = 0; t < 12; ++t) x[t] = sv[nn][pp * 12 + t];
-    const long long token = ((long long)(b * N + n)) * P + p;
-    const long long mt = token >> 7;
-    const int r = (int)(token & 127);
-#pragma unroll 1
-    for (int c = 0; c < 12; ++c) {
-      float v[8];
+    for (int t = 0; t < 12; ++t) x[t] = sv[nn][pp * 13 + t];
+    const float4 pa = *reinterpret_cast<const float4 *>(pos + (size_t)p * 96 + c * 8);
+    const float4 pb = *reinterpret_cast<const float4 *>(pos + (size_t)p * 96 + c * 8 + 4);
+    float v[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int f = c * 8 + j;
-        float acc = sb[f] + pos[(size_t)p * 96 + f];
+    for (int j = 0; j < 8; ++j) {
+      float acc = br[j] + v[j];
 #pragma unroll
-        for (int t = 0; t < 12; ++t) acc = fmaf(sw[f * 12 + t], x[t], acc);
-        v[j] = acc;
-      }
-      if (thr16) drop8(v, (uint64_t)token * 12 + c, thr16, dscale, key);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] *= scale;
-      img[(mt * 12 + c) * 128 + r] = pack8_bf16(v);
+      for (int t = 0; t < 12; ++t) acc = fmaf(wr[j][t], x[t], acc);
+      v[j] = acc;
     }
+    const long long token = ((long long)(b * N + n)) * P + p;
+    if (thr16) drop8(v, (uint64_t)token * 12 + c, thr16, dscale, key);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= scale;
+    img[((token >> 7) * 12 + c) * 128 + (token & 127)] = pack8_bf16(v);
   }
 }
 

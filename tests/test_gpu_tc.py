@@ -128,3 +128,21 @@ def test_tc_cosine_gram_from_encoder_image(B, N, P):
     ref = O.cosine_similarity_gram(x.double()).float()
     assert (sim - ref).abs().max().item() < 2e-4
     assert (sim.diagonal(dim1=1, dim2=2) - 1).abs().max().item() < 1e-5
+
+
+def test_tc_attention_dropout_statistics():
+    """Counter-hash dropout of the tensor-core path: keep probability 1 - p, binomial spread, reproducible per seed."""
+    from step_b200 import ops
+    S, P, p = 16, 168, 0.1
+    T = S * P
+    x_img = ops.tc_rows_to_image(torch.zeros(T, 96, device=DEV))
+    w = ops.tc_pack_weight(torch.zeros(288, 96, device=DEV))
+    b = torch.zeros(288); b[192:] = 1.0                       # q = k = 0 (uniform attention), v = 1
+    outs = []
+    for seed in (5, 5, 6):
+        o_img = ops.tc_qkv_attention(x_img, w, b.to(DEV), S, P, drop_p=p, seed=seed)
+        outs.append(ops.tc_image_to_rows(o_img, T, 96).cpu())
+    kept = outs[0] * (1 - p)                                   # = (#kept keys) / P per (row, head), replicated over 24 dims
+    assert abs(kept.mean().item() - (1 - p)) < 3e-3
+    assert kept[:, ::24].std().item() == pytest.approx(math.sqrt(p * (1 - p) / P), rel=0.2)
+    assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
