@@ -234,10 +234,15 @@ __global__ void trunk_bn_bwd_finalize_kernel(const double *sums, double count, i
 
 // ---------------------------------------------------------------------------
 // B2: backward through BN2 -> ReLU -> conv2: d(y1n) [N,8,L1], dW2, db2, and the BN1 backward sums.
-// grid (ceil(L1/512), N), 256 threads, dynamic smem.
+// grid (6, N): each CTA walks over tiles of 256 y1 positions of one node (one position per thread), keeps its
+// dW2 / db2 / BN-sum partials in registers across tiles and flushes them with one round of atomics.
+// 54 KB of dynamic smem per CTA -> 4 CTAs per SM.
 // ---------------------------------------------------------------------------
-constexpr int DPW = TL + HALO;     // 521 dpre2 positions [t0-9, t0+512)
+constexpr int TLB = 256;
+constexpr int DPW = TLB + HALO;    // dpre2 positions [t0-9, t0+256)
 constexpr int DPS = DPW + 3;
+constexpr int Y1WB = TLB + HALO;   // normalised y1 positions [t0, t0+265)
+constexpr int Y1SB = Y1WB + 3;
 
 __global__ void __launch_bounds__(256) trunk_conv2_bwd_kernel(const float *__restrict__ x, TrunkDims d,
                                                               const float *__restrict__ w1, const float *__restrict__ b1,
@@ -249,14 +254,15 @@ __global__ void __launch_bounds__(256) trunk_conv2_bwd_kernel(const float *__res
   extern __shared__ __align__(16) float sm[];
   float *dp_cl = sm;                         // [16][DPS]      dpre2 by channel (for the transposed conv)
   float *dp_lc = dp_cl + C2 * DPS;           // [DPW][16]      dpre2 by position (broadcast reads for dW2)
-  float *y1s = dp_lc + DPW * C2;             // [8][Y1S]       normalised y1 at [t0, t0+521)
-  float *y1r = y1s + C1 * Y1S;               // [8][TL]        raw y1 at [t0, t0+512) for x-hat
-  float *xs = y1r + C1 * TL;                 // [Y1W + HALO + 2]
-  float *w2t = xs + (Y1W + HALO + 2 + 3) / 4 * 4;   // [co][k][ci]  (8 contiguous ci)
+  float *y1s = dp_lc + DPW * C2;             // [8][Y1SB]      normalised y1 at [t0, t0+265)
+  float *y1r = y1s + C1 * Y1SB;              // [8][TLB]       raw y1 at [t0, t0+256) for x-hat
+  float *xs = y1r + C1 * TLB;                // [Y1WB + HALO + 2]
+  float *w2t = xs + (Y1WB + HALO + 2 + 3) / 4 * 4;   // [co][k][ci]  (8 contiguous ci)
   float *w1s = w2t + C2 * TK * C1;           // 80
   float *b1s = w1s + C1 * TK;                // 8
   float *sc1 = b1s + C1, *sh1 = sc1 + C1;    // 8 + 8
-  float *red = sh1 + C1;                     // 32
+  float *cf2 = sh1 + C1;                     // 5 * 16 BN2 backward coefficients
+  float *red = cf2 + 5 * C2;                 // 32
   const int n = blockIdx.y, tid = threadIdx.x;
   const float *xr = x + (size_t)n * d.L0;
   for (int i = tid; i < C2 * C1 * TK; i += 256) {
@@ -265,105 +271,104 @@ __global__ void __launch_bounds__(256) trunk_conv2_bwd_kernel(const float *__res
   }
   if (tid < C1 * TK) w1s[tid] = w1[tid];
   if (tid < C1) { b1s[tid] = b1[tid]; sc1[tid] = bn1[2 * C1 + tid]; sh1[tid] = bn1[3 * C1 + tid]; }
-  // weight / bias gradient partials stay in registers across the tiles of this CTA (one atomic flush at the end:
-  // per-tile atomics to the 1280 dW2 addresses serialise in L2)
+  if (tid < 5 * C2) cf2[tid] = coef2[tid];
   float accw[C2], accb = 0.f, s1acc[C1], s2acc[C1];
 #pragma unroll
   for (int co = 0; co < C2; ++co) accw[co] = 0.f;
 #pragma unroll
   for (int ci = 0; ci < C1; ++ci) { s1acc[ci] = 0.f; s2acc[ci] = 0.f; }
-  const int ntiles = (d.L1 + TL - 1) / TL;
+  float mean1[C1], rstd1[C1];
+#pragma unroll
+  for (int ci = 0; ci < C1; ++ci) { mean1[ci] = bn1[ci]; rstd1[ci] = 1.0f / sqrtf(bn1[C1 + ci] + eps); }
+  const int ntiles = (d.L1 + TLB - 1) / TLB;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-  const int t0 = tile * TL;
-  __syncthreads();
-  for (int i = tid; i < Y1W + HALO; i += 256) xs[i] = (t0 + i < d.L0) ? xr[t0 + i] : 0.f;
-  // dpre2 tile: position j <-> l = t0 - 9 + j
-  for (int idx = tid; idx < C2 * DPW; idx += 256) {
-    const int co = idx / DPW, j = idx - co * DPW, l = t0 - HALO + j;
-    float v = 0.f;
-    if (l >= 0 && l < d.L2) {
-      const size_t off = ((size_t)n * C2 + co) * d.L2 + l;
-      const float yv = y2[off];
-      if (yv > 0.f) {
-        const float xhat = (yv - coef2[3 * C2 + co]) * coef2[4 * C2 + co];
-        v = coef2[co] * (dy2n[off] - coef2[C2 + co] - xhat * coef2[2 * C2 + co]);
+    const int t0 = tile * TLB;
+    __syncthreads();
+    for (int i = tid; i < Y1WB + HALO; i += 256) xs[i] = (t0 + i < d.L0) ? xr[t0 + i] : 0.f;
+    // dpre2 tile: position j <-> l = t0 - 9 + j
+    for (int idx = tid; idx < C2 * DPW; idx += 256) {
+      const int co = idx / DPW, j = idx - co * DPW, l = t0 - HALO + j;
+      float v = 0.f;
+      if (l >= 0 && l < d.L2) {
+        const size_t off = ((size_t)n * C2 + co) * d.L2 + l;
+        const float yv = y2[off];
+        if (yv > 0.f) {
+          const float xhat = (yv - cf2[3 * C2 + co]) * cf2[4 * C2 + co];
+          v = cf2[co] * (dy2n[off] - cf2[C2 + co] - xhat * cf2[2 * C2 + co]);
+        }
       }
+      dp_cl[co * DPS + j] = v;
+      dp_lc[j * C2 + co] = v;
     }
-    dp_cl[co * DPS + j] = v;
-    dp_lc[j * C2 + co] = v;
-  }
-  __syncthreads();
-  compute_y1_tile(xs, w1s, b1s, t0, Y1W, d.L1, y1s, Y1S, sc1, sh1);
-  compute_y1_tile(xs, w1s, b1s, t0, TL, d.L1, y1r, TL, nullptr, nullptr);
-  __syncthreads();
+    __syncthreads();
+    // y1 (raw for x-hat on the own range, normalised everywhere) with ONE conv1 evaluation per element
+    for (int idx = tid; idx < C1 * Y1WB; idx += 256) {
+      const int c = idx / Y1WB, j = idx - c * Y1WB;
+      float a = 0.f, an = 0.f;
+      if (t0 + j < d.L1) {
+        a = b1s[c];
+#pragma unroll
+        for (int k = 0; k < TK; ++k) a = fmaf(w1s[c * TK + k], xs[j + k], a);
+        a = fmaxf(a, 0.f);
+        an = fmaf(a, sc1[c], sh1[c]);
+      }
+      y1s[c * Y1SB + j] = an;
+      if (j < TLB) y1r[c * TLB + j] = a;
+    }
+    __syncthreads();
 
-  // ---- d(y1n)[ci][l'] = sum_co sum_k w2[co][ci][k] dpre2[co][l'-k];  l' = t0 + p, dpre2 index j = p - k + 9 ----
-  {
-    float acc[2][C1];
+    // ---- d(y1n)[ci][l'] = sum_co sum_k w2[co][ci][k] dpre2[co][l'-k];  l' = t0 + p, dpre2 index j = p - k + 9 ----
+    {
+      float acc[C1];
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int ci = 0; ci < C1; ++ci) acc[j][ci] = 0.f;
-    const int p0 = tid, p1 = tid + 256;
+      for (int ci = 0; ci < C1; ++ci) acc[ci] = 0.f;
+      const int p0 = tid;
 #pragma unroll 1
-    for (int co = 0; co < C2; ++co) {
-      const float *dr = dp_cl + co * DPS + HALO;
+      for (int co = 0; co < C2; ++co) {
+        const float *dr = dp_cl + co * DPS + HALO;
 #pragma unroll
-      for (int k = 0; k < TK; ++k) {
-        const float a0 = dr[p0 - k], a1 = dr[p1 - k];
-        const float4 *w = reinterpret_cast<const float4 *>(w2t + (co * TK + k) * C1);
-        const float4 wa = w[0], wb = w[1];
-        acc[0][0] = fmaf(wa.x, a0, acc[0][0]); acc[0][1] = fmaf(wa.y, a0, acc[0][1]);
-        acc[0][2] = fmaf(wa.z, a0, acc[0][2]); acc[0][3] = fmaf(wa.w, a0, acc[0][3]);
-        acc[0][4] = fmaf(wb.x, a0, acc[0][4]); acc[0][5] = fmaf(wb.y, a0, acc[0][5]);
-        acc[0][6] = fmaf(wb.z, a0, acc[0][6]); acc[0][7] = fmaf(wb.w, a0, acc[0][7]);
-        acc[1][0] = fmaf(wa.x, a1, acc[1][0]); acc[1][1] = fmaf(wa.y, a1, acc[1][1]);
-        acc[1][2] = fmaf(wa.z, a1, acc[1][2]); acc[1][3] = fmaf(wa.w, a1, acc[1][3]);
-        acc[1][4] = fmaf(wb.x, a1, acc[1][4]); acc[1][5] = fmaf(wb.y, a1, acc[1][5]);
-        acc[1][6] = fmaf(wb.z, a1, acc[1][6]); acc[1][7] = fmaf(wb.w, a1, acc[1][7]);
+        for (int k = 0; k < TK; ++k) {
+          const float a0 = dr[p0 - k];
+          const float4 *w = reinterpret_cast<const float4 *>(w2t + (co * TK + k) * C1);
+          const float4 wa = w[0], wb = w[1];
+          acc[0] = fmaf(wa.x, a0, acc[0]); acc[1] = fmaf(wa.y, a0, acc[1]);
+          acc[2] = fmaf(wa.z, a0, acc[2]); acc[3] = fmaf(wa.w, a0, acc[3]);
+          acc[4] = fmaf(wb.x, a0, acc[4]); acc[5] = fmaf(wb.y, a0, acc[5]);
+          acc[6] = fmaf(wb.z, a0, acc[6]); acc[7] = fmaf(wb.w, a0, acc[7]);
+        }
+      }
+      if (t0 + p0 < d.L1) {
+        float *o = dy1n + (size_t)n * C1 * d.L1 + t0;
+#pragma unroll
+        for (int ci = 0; ci < C1; ++ci) {
+          o[(size_t)ci * d.L1 + p0] = acc[ci];
+          s1acc[ci] += acc[ci];
+          s2acc[ci] = fmaf(acc[ci], (y1r[ci * TLB + p0] - mean1[ci]) * rstd1[ci], s2acc[ci]);
+        }
       }
     }
-    const bool ok0 = t0 + p0 < d.L1, ok1 = t0 + p1 < d.L1;
-    float *o = dy1n + (size_t)n * C1 * d.L1 + t0;
-#pragma unroll
-    for (int ci = 0; ci < C1; ++ci) {
-      const float mean = bn1[ci], rstd = 1.0f / sqrtf(bn1[C1 + ci] + eps);
-      float a = 0.f, b = 0.f;
-      if (ok0) {
-        o[(size_t)ci * d.L1 + p0] = acc[0][ci];
-        a += acc[0][ci];
-        b = fmaf(acc[0][ci], (y1r[ci * TL + p0] - mean) * rstd, b);
-      }
-      if (ok1) {
-        o[(size_t)ci * d.L1 + p1] = acc[1][ci];
-        a += acc[1][ci];
-        b = fmaf(acc[1][ci], (y1r[ci * TL + p1] - mean) * rstd, b);
-      }
-      s1acc[ci] += a; s2acc[ci] += b;
-    }
-  }
 
-  // ---- dW2[co][ci][k] += sum_{l in own range} dpre2[co][l] y1n[ci][l+k];  own l = t0 + p, p in [0,512) ----
-  // thread = (ci, k) pair x one of 3 position segments, 16 output channels in registers
-  if (tid < 240) {
-    const int pair = tid % 80, seg = tid / 80, ci = pair / TK, k = pair - ci * TK;
-    const int pbeg = seg * 171, pend = min(TL, pbeg + 171);
-    for (int p = pbeg; p < pend; ++p) {
-      const float yv = y1s[ci * Y1S + p + k];
-      const float4 *dpp = reinterpret_cast<const float4 *>(dp_lc + (p + HALO) * C2);
+    // ---- dW2[co][ci][k] += sum_{l in own range} dpre2[co][l] y1n[ci][l+k];  own l = t0 + p, p in [0,256) ----
+    // thread = (ci, k) pair x one of 3 position segments, 16 output channels in registers
+    if (tid < 240) {
+      const int pair = tid % 80, seg = tid / 80, ci = pair / TK, k = pair - ci * TK;
+      const int pbeg = seg * 86, pend = min(TLB, pbeg + 86);
+      for (int p = pbeg; p < pend; ++p) {
+        const float yv = y1s[ci * Y1SB + p + k];
+        const float4 *dpp = reinterpret_cast<const float4 *>(dp_lc + (p + HALO) * C2);
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const float4 g = dpp[c4];
-        accw[4 * c4] = fmaf(g.x, yv, accw[4 * c4]); accw[4 * c4 + 1] = fmaf(g.y, yv, accw[4 * c4 + 1]);
-        accw[4 * c4 + 2] = fmaf(g.z, yv, accw[4 * c4 + 2]); accw[4 * c4 + 3] = fmaf(g.w, yv, accw[4 * c4 + 3]);
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 g = dpp[c4];
+          accw[4 * c4] = fmaf(g.x, yv, accw[4 * c4]); accw[4 * c4 + 1] = fmaf(g.y, yv, accw[4 * c4 + 1]);
+          accw[4 * c4 + 2] = fmaf(g.z, yv, accw[4 * c4 + 2]); accw[4 * c4 + 3] = fmaf(g.w, yv, accw[4 * c4 + 3]);
+        }
       }
     }
-  }
-  // ---- db2[co] partial over own range: thread = (co, 16-way position split) ----
-  {
-    const int co = tid >> 4, part = tid & 15;
-    for (int p = part; p < TL; p += 16) accb += dp_cl[co * DPS + HALO + p];
-  }
+    // ---- db2[co] partial over own range: thread = (co, 16-way position split) ----
+    {
+      const int co = tid >> 4, part = tid & 15;
+      for (int p = part; p < TLB; p += 16) accb += dp_cl[co * DPS + HALO + p];
+    }
   }  // tile loop
 
   if (tid < 240) {
@@ -441,8 +446,8 @@ __global__ void __launch_bounds__(256) trunk_conv1_bwd_kernel(const float *__res
 }
 
 static size_t conv2_bwd_smem() {
-  size_t f = (size_t)C2 * DPS + (size_t)DPW * C2 + (size_t)C1 * Y1S + (size_t)C1 * TL + (Y1W + HALO + 2 + 3) / 4 * 4 +
-             C2 * TK * C1 + C1 * TK + 3 * C1 + 32;
+  size_t f = (size_t)C2 * DPS + (size_t)DPW * C2 + (size_t)C1 * Y1SB + (size_t)C1 * TLB + (Y1WB + HALO + 2 + 3) / 4 * 4 +
+             C2 * TK * C1 + C1 * TK + 3 * C1 + 5 * C2 + 32;
   return f * sizeof(float);
 }
 
