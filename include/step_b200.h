@@ -142,7 +142,8 @@ size_t step_tc_attn_image_bytes(int S, int P, int which);
  * log2(e)/sqrt(24)). */
 int step_tc_qkv(const void *x_img, const void *w_img, const float *bias, int S, int P, void *q_img, void *k_img, void *v_img,
                 void *stream);
-/* softmax(Q K^T) V per (sequence, head) on tcgen05 -> O tile image [S*P, 96].  P <= 176. */
+/* softmax(Q K^T) V per (sequence, head) on tcgen05 -> O tile image [S*P, 96].  P <= 352
+ * (P > 176 runs the key-split variant: two 176-key blocks per row tile merged in shared memory). */
 int step_tc_attention(const void *q_img, const void *k_img, const void *v_img, void *o_img, int S, int P, float drop_p,
                       unsigned long long seed, void *stream);
 size_t step_ts_encoder_bf16_workspace_bytes(int B, int N, int P);

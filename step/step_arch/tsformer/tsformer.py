@@ -151,7 +151,7 @@ class TSFormer(nn.Module):
         layers = self.encoder.kernel_weights()
         if self.precision not in ("bf16", "fp32"):
             raise ValueError(f"TSFormer.precision must be 'bf16' or 'fp32', got {self.precision!r}")
-        if self.precision == "bf16" and series.shape[1] // self.patch_size <= 176:
+        if self.precision == "bf16" and series.shape[1] // self.patch_size <= 352:
             key = (series.device, tuple(int(w._version) for lw in layers for w in lw.values()),
                    tuple(w.data_ptr() for lw in layers for w in lw.values()))
             if self._tc_key != key:           # frozen weights: packed into UMMA images once
@@ -161,7 +161,7 @@ class TSFormer(nn.Module):
                 series, emb.weight, emb.bias, self.positional_encoding.position_embedding, layers, self._tc_images,
                 self.encoder_norm.weight, self.encoder_norm.bias, drop_p=drop, seed=seed, want_seq_image=True)
         else:
-            # fp32 kernels (also serves P > 176 until the tensor-core attention handles two key blocks)
+            # fp32 kernels (also serve P > 352: the tensor-core attention holds at most two 176-key blocks in TMEM)
             self.seq_image = None
             hidden = ops.ts_encoder_forward(series, emb.weight, emb.bias, self.positional_encoding.position_embedding, layers,
                                             self.encoder_norm.weight, self.encoder_norm.bias, drop_p=drop, seed=seed,

@@ -433,22 +433,31 @@ struct TcAttnArgs {
 
 constexpr int TCA_THREADS = 320;
 constexpr int TCA_QBUF = 4, TCA_KVBUF = 3;
+constexpr int TCA_KSPLIT = 176, TCA_KVBUF_SPLIT = 2, TCA_XROW = 27;   // key-split mode (P > 176)
 
 // PF > 0: sequence length known at compile time (168 for every 2016-step STEP config) -> unrolled column loops
 // without bounds predicates; DROP: attention-probability dropout compiled in or out.
-template <int PF, bool DROP>
+//
+// SPLIT (176 < P <= 352, e.g. the 4032-step PEMS03/04/08 histories with P = 336): one S accumulator no longer fits
+// next to its ping-pong twin in the 512 TMEM columns, so the two softmax groups share every (sequence, head,
+// row tile) iteration instead of alternating: group 0 owns keys [0, 176), group 1 keys [176, P).  Each computes
+// a local max / sum and a partial O = P_g V_g in its private TMEM region; the halves are merged flash-decoding
+// style through a small shared-memory exchange (O = (O0 2^(m0-m) + O1 2^(m1-m)) / (l0 2^(m0-m) + l1 2^(m1-m))).
+template <int PF, bool DROP, bool SPLIT>
 __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int P = PF > 0 ? PF : a.P, Pk = PF > 0 ? (PF + 15) / 16 * 16 : a.Pk, RT = PF > 0 ? (PF + 127) / 128 : a.RT;
+  constexpr int KVBUFS = SPLIT ? TCA_KVBUF_SPLIT : TCA_KVBUF;
   const uint32_t KVB = 3u * Pk * 16;          // bytes of one K (or V) image
-  const uint32_t PB = (uint32_t)(Pk / 8) * 2048;
+  const uint32_t PB = SPLIT ? (uint32_t)(TCA_KSPLIT / 8) * 2048 : (uint32_t)(Pk / 8) * 2048;
   uint8_t *sQ = smem;                          // TCA_QBUF x 6144
-  uint8_t *sK = sQ + TCA_QBUF * 6144;          // TCA_KVBUF x KVB
-  uint8_t *sV = sK + TCA_KVBUF * KVB;          // TCA_KVBUF x KVB
-  uint8_t *sZ = sV + TCA_KVBUF * KVB;          // zero chunk: max(128, Pk) rows x 16 B
+  uint8_t *sK = sQ + TCA_QBUF * 6144;          // KVBUFS x KVB
+  uint8_t *sV = sK + KVBUFS * KVB;             // KVBUFS x KVB
+  uint8_t *sZ = sV + KVBUFS * KVB;             // zero chunk: max(128, Pk) rows x 16 B
   const uint32_t zrows = Pk > 128 ? Pk : 128;
-  uint8_t *sP = sZ + zrows * 16;               // 2 x [Pk/8][128][16 B]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * PB);
+  uint8_t *sP = sZ + zrows * 16;               // 2 x [cols/8][128][16 B]
+  float *xch = reinterpret_cast<float *>(sP + 2 * PB);   // SPLIT: 2 x [128 rows][TCA_XROW] merge exchange
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * PB + (SPLIT ? 2 * 128 * TCA_XROW * 4 : 0));
   uint64_t *q_full = bars, *q_empty = bars + 4, *kv_full = bars + 8, *kv_empty = bars + 11;
   uint64_t *s_full = bars + 14, *s_empty = bars + 16, *p_ready = bars + 18, *o_full = bars + 20, *o_empty = bars + 22;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
@@ -456,7 +465,7 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TCA_QBUF; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-    for (int i = 0; i < TCA_KVBUF; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < KVBUFS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1); mbar_init(&s_empty[g], 4); mbar_init(&p_ready[g], 4);
       mbar_init(&o_full[g], 1); mbar_init(&o_empty[g], 4);
@@ -479,8 +488,8 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       for (int i = 0; i < NIT; ++i) {
         const int seq = blockIdx.x + (i / per_seq) * gridDim.x, w = i % per_seq, h = w / RT, rt = w % RT;
         if (rt == 0) {
-          const int hi = i / RT, kvb = hi % TCA_KVBUF;
-          mbar_wait(&kv_empty[kvb], ((hi / TCA_KVBUF) & 1) ^ 1);
+          const int hi = i / RT, kvb = hi % KVBUFS;
+          mbar_wait(&kv_empty[kvb], ((hi / KVBUFS) & 1) ^ 1);
           mbar_expect_tx(&kv_full[kvb], 2 * KVB);
           tma_bulk_g2s(sK + kvb * KVB, a.k_img + ((size_t)seq * 4 + h) * KVB, KVB, &kv_full[kvb]);
           tma_bulk_g2s(sV + kvb * KVB, a.v_img + ((size_t)seq * 4 + h) * KVB, KVB, &kv_full[kvb]);
@@ -493,9 +502,49 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, Pk, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, 32, 0, 1);
       const uint32_t zaddr = smem_u32(sZ);
+      if (SPLIT) {
+        const int pkg[2] = {TCA_KSPLIT, Pk - TCA_KSPLIT};
+        const uint32_t idesc_sg[2] = {umma_idesc_bf16(128, TCA_KSPLIT, 0, 0), umma_idesc_bf16(128, Pk - TCA_KSPLIT, 0, 0)};
+        for (int j = 0; j <= NIT; ++j) {
+          if (j < NIT) {
+            const int i = j, rt = (i % per_seq) % RT, hi = i / RT, kvb = hi % KVBUFS, qb = i & 3;
+            if (rt == 0) mbar_wait(&kv_full[kvb], (hi / KVBUFS) & 1);
+            mbar_wait(&q_full[qb], (i >> 2) & 1);
+            mbar_wait(&s_empty[0], (i & 1) ^ 1);
+            mbar_wait(&s_empty[1], (i & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t qa = smem_u32(sQ + qb * 6144);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const uint32_t ka = smem_u32(sK + kvb * KVB) + g * TCA_KSPLIT * 16, ts = tmem + g * 256;
+              umma_bf16(ts, umma_desc(qa, 2048, 128), umma_desc(ka, Pk * 16, 128), idesc_sg[g], 0u);
+              umma_bf16(ts, umma_desc(qa + 2 * 2048, zaddr - (qa + 2 * 2048), 128),
+                        umma_desc(ka + 2 * Pk * 16, zaddr - (ka + 2 * Pk * 16), 128), idesc_sg[g], 1u);
+              umma_commit(&s_full[g]);
+            }
+            umma_commit(&q_empty[qb]);
+          }
+          if (j >= 1) {
+            const int i = j - 1, rt = (i % per_seq) % RT, hi = i / RT, kvb = hi % KVBUFS;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              mbar_wait(&p_ready[g], i & 1);
+              mbar_wait(&o_empty[g], (i & 1) ^ 1);
+              tc_fence_after();
+              const uint32_t pa = smem_u32(sP + g * PB), va = smem_u32(sV + kvb * KVB) + g * TCA_KSPLIT * 16;
+              const uint32_t to = tmem + g * 256 + 192;
+              for (int kk = 0; kk < pkg[g] / 16; ++kk)
+                umma_bf16(to, umma_desc(pa + kk * 2 * 2048, 2048, 128), umma_desc(va + kk * 256, 128, Pk * 16), idesc_o,
+                          kk != 0 ? 1u : 0u);
+              umma_commit(&o_full[g]);
+            }
+            if (rt == RT - 1) umma_commit(&kv_empty[kvb]);
+          }
+        }
+      } else {
+      const uint32_t idesc_s = umma_idesc_bf16(128, Pk, 0, 0);
       for (int j = 0; j <= NIT; ++j) {
         if (j < NIT) {
           const int i = j, g = i & 1, u = i >> 1, rt = (i % per_seq) % RT, hi = i / RT, kvb = hi % TCA_KVBUF, qb = i & 3;
@@ -524,6 +573,7 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
           if (rt == RT - 1) umma_commit(&kv_empty[kvb]);
         }
       }
+      }
     }
   } else {
     const int q = warp & 3, g = (warp - 2) >> 2;
@@ -531,8 +581,11 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t TM_S = tmem + g * 256, TM_O = tmem + g * 256 + 192;
     uint8_t *myP = sP + g * PB;
-    for (int i = g; i < NIT; i += 2) {
-      const int u = i >> 1;
+    // columns this group exponentiates: all Pk (alternating iterations) or its key block (SPLIT, every iteration)
+    const int Pl = SPLIT ? (g == 0 ? TCA_KSPLIT : P - TCA_KSPLIT) : P;
+    const int Pkl = SPLIT ? (g == 0 ? TCA_KSPLIT : Pk - TCA_KSPLIT) : Pk;
+    for (int i = SPLIT ? 0 : g; i < NIT; i += SPLIT ? 1 : 2) {
+      const int u = SPLIT ? i : i >> 1;
       const int seq = blockIdx.x + (i / per_seq) * gridDim.x, w = i % per_seq, h = w / RT, rt = w % RT;
       const int rows_valid = min(128, P - rt * 128);
       const bool warp_active = q * 32 < rows_valid;
@@ -540,8 +593,8 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       mbar_wait(&s_full[g], u & 1);
       tc_fence_after();
       // V rows of the padded keys must be finite zeros (P is 0 there, but 0 * NaN = NaN)
-      if (rt == 0 && q == 2) {
-        const int npad = Pk - P, kvb = (i / RT) % TCA_KVBUF;
+      if (rt == 0 && q == 2 && (!SPLIT || g == 1)) {
+        const int npad = Pk - P, kvb = (i / RT) % KVBUFS;
         for (int jz = lane; jz < npad * 3; jz += 32) {
           const int gg = jz / npad, rr = P + jz % npad;
           *reinterpret_cast<uint4 *>(sV + kvb * KVB + ((size_t)gg * Pk + rr) * 16) = make_uint4(0, 0, 0, 0);
@@ -551,8 +604,8 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       if (warp_active) {
         // Full 32-column blocks run unpredicated with four independent max / sum chains; only the tail block
         // (columns [c_tail, P), then zero fill up to Pk) carries per-element predicates.
-        const int c_tail = (P / 32) * 32;
-        const bool tail32 = c_tail + 32 <= Pk;          // else the tail is one 16-column load (Pk is a multiple of 16)
+        const int c_tail = (Pl / 32) * 32;
+        const bool tail32 = c_tail + 32 <= Pkl;          // else the tail is one 16-column load (Pk is a multiple of 16)
         // ---- pass 1: row maximum ----
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
         for (int c0 = 0; c0 < c_tail; c0 += 32) {
@@ -563,7 +616,7 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
             m0 = fmaxf(m0, t[c]); m1 = fmaxf(m1, t[c + 1]); m2 = fmaxf(m2, t[c + 2]); m3 = fmaxf(m3, t[c + 3]);
           }
         }
-        if (c_tail < P) {
+        if (c_tail < Pl) {
           float t[32];
           if (tail32) {
             tmem_ld32(TM_S + lane_base + c_tail, t);
@@ -576,11 +629,12 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
             for (int c = 16; c < 32; ++c) t[c] = -INFINITY;
           }
 #pragma unroll
-          for (int c = 0; c < 32; ++c) if (c_tail + c < P) m0 = fmaxf(m0, t[c]);
+          for (int c = 0; c < 32; ++c) if (c_tail + c < Pl) m0 = fmaxf(m0, t[c]);
         }
         m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         // ---- pass 2: p = 2^(s - m), row sum, (dropout), bf16 image ----
-        const uint64_t drop_base = (((uint64_t)seq * 4 + h) * P + (rt * 128 + row)) * (uint64_t)(Pk / 8);
+        const uint64_t drop_base = (((uint64_t)seq * 4 + h) * P + (rt * 128 + row)) * (uint64_t)(Pk / 8) +
+                                   (SPLIT ? g * (TCA_KSPLIT / 8) : 0);
         uint4 *prow = reinterpret_cast<uint4 *>(myP) + row;
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
         for (int c0 = 0; c0 < c_tail; c0 += 32) {
@@ -598,7 +652,7 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
             prow[(size_t)((c0 >> 3) + cc) * 128] = pack8_bf16(&t[cc * 8]);
           }
         }
-        if (c_tail < Pk) {
+        if (c_tail < Pkl) {
           float t[32];
           if (tail32) {
             tmem_ld32(TM_S + lane_base + c_tail, t);
@@ -612,13 +666,13 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
           }
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
-            const float pv = (c_tail + c < P) ? fast_exp2(t[c] - m) : 0.f;
+            const float pv = (c_tail + c < Pl) ? fast_exp2(t[c] - m) : 0.f;
             l0 += pv;
             t[c] = pv;
           }
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
-            if (c_tail + cc * 8 < Pk) {
+            if (c_tail + cc * 8 < Pkl) {
               if (DROP) drop8(&t[cc * 8], drop_base + (c_tail >> 3) + cc, a.thr16, 1.0f, a.key);
               prow[(size_t)((c_tail >> 3) + cc) * 128] = pack8_bf16(&t[cc * 8]);
             }
@@ -638,7 +692,26 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[g]);
-      if (row_valid) {
+      float f0 = 1.f;
+      if (SPLIT) {
+        // merge the two key blocks: group 1 publishes (m, l, O[24]); group 0 combines and writes the tile
+        float *x = xch + ((size_t)(i & 1) * 128 + row) * TCA_XROW;
+        if (g == 1 && warp_active) {
+          x[0] = m; x[1] = l;
+#pragma unroll
+          for (int c = 0; c < HD; ++c) x[2 + c] = o[c];
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (g == 0 && row_valid) {
+          const float m1 = x[0], l1 = x[1], mm = fmaxf(m, m1);
+          f0 = fast_exp2(m - mm);
+          const float f1 = fast_exp2(m1 - mm);
+          l = l * f0 + l1 * f1;
+#pragma unroll
+          for (int c = 0; c < HD; ++c) o[c] = o[c] * f0 + x[2 + c] * f1;
+        }
+      }
+      if (row_valid && (!SPLIT || g == 0)) {
         const float inv = a.dscale / l;
         const long long token = (long long)seq * P + rt * 128 + row;
         const long long mt = token >> 7;
@@ -646,10 +719,10 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
         uint4 *dst = reinterpret_cast<uint4 *>(a.o_img) + ((size_t)mt * 12 + 3 * h) * 128 + r;
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
-          float x[8];
+          float x8[8];
 #pragma unroll
-          for (int jx = 0; jx < 8; ++jx) x[jx] = o[cc * 8 + jx] * inv;
-          dst[cc * 128] = pack8_bf16(x);
+          for (int jx = 0; jx < 8; ++jx) x8[jx] = o[cc * 8 + jx] * inv;
+          dst[cc * 128] = pack8_bf16(x8);
         }
       }
     }
@@ -773,6 +846,9 @@ static size_t tcl_smem_bytes(int K, int Nout) {
 }
 static size_t tca_smem_bytes(int Pk) {
   const size_t zrows = Pk > 128 ? Pk : 128;
+  if (Pk > TCA_KSPLIT)
+    return TCA_QBUF * 6144 + 2 * TCA_KVBUF_SPLIT * (size_t)(3 * Pk * 16) + zrows * 16 + 2 * (size_t)(TCA_KSPLIT / 8) * 2048 +
+           2 * 128 * TCA_XROW * 4 + 32 * 8 + 16;
   return TCA_QBUF * 6144 + 2 * TCA_KVBUF * (size_t)(3 * Pk * 16) + zrows * 16 + 2 * (size_t)(Pk / 8) * 2048 + 32 * 8 + 16;
 }
 
@@ -868,7 +944,7 @@ static int tc_attn_launch(const void *q_img, const void *k_img, const void *v_im
   TcAttnArgs a{};
   a.q_img = (const uint8_t *)q_img; a.k_img = (const uint8_t *)k_img; a.v_img = (const uint8_t *)v_img; a.o_img = (uint8_t *)o_img;
   a.S = S; a.P = P; a.Pk = (P + 15) / 16 * 16; a.RT = (P + 127) / 128;
-  if (a.Pk > 176) return fail(STEP_EUNSUPPORTED, "tc_attention: P=%lld > 176 is served by the fp32 path for now", P);
+  if (a.Pk > 2 * TCA_KSPLIT) return fail(STEP_EUNSUPPORTED, "tc_attention: P=%lld > 352 is served by the fp32 path", P);
   if (drop_p > 0.f) { a.thr16 = (uint32_t)(drop_p * 65536.0f); a.dscale = 1.f / (1.f - drop_p); }
   else { a.thr16 = 0; a.dscale = 1.f; }
   a.key = rng_key(seed, site);
@@ -877,13 +953,15 @@ static int tc_attn_launch(const void *q_img, const void *k_img, const void *v_im
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = S < sms ? S : sms;
   const size_t smem = tca_smem_bytes(a.Pk);
-#define TCA_LAUNCH(PF, DR)                                                   \
-  do {                                                                       \
-    if ((rc = allow_smem(tc_attn_kernel<PF, DR>, 227 * 1024))) return rc;    \
-    tc_attn_kernel<PF, DR><<<grid, TCA_THREADS, smem, st>>>(a);              \
+#define TCA_LAUNCH(PF, DR, SP)                                                   \
+  do {                                                                           \
+    if ((rc = allow_smem(tc_attn_kernel<PF, DR, SP>, 227 * 1024))) return rc;    \
+    tc_attn_kernel<PF, DR, SP><<<grid, TCA_THREADS, smem, st>>>(a);              \
   } while (0)
-  if (P == 168) { if (a.thr16) TCA_LAUNCH(168, true); else TCA_LAUNCH(168, false); }
-  else { if (a.thr16) TCA_LAUNCH(0, true); else TCA_LAUNCH(0, false); }
+  if (P == 168) { if (a.thr16) TCA_LAUNCH(168, true, false); else TCA_LAUNCH(168, false, false); }
+  else if (P == 336) { if (a.thr16) TCA_LAUNCH(336, true, true); else TCA_LAUNCH(336, false, true); }
+  else if (a.Pk > TCA_KSPLIT) { if (a.thr16) TCA_LAUNCH(0, true, true); else TCA_LAUNCH(0, false, true); }
+  else { if (a.thr16) TCA_LAUNCH(0, true, false); else TCA_LAUNCH(0, false, false); }
 #undef TCA_LAUNCH
   return check_launch("tc_attn_kernel");
 }

@@ -35,8 +35,8 @@ def test_step_forward_backward_matches_reference_golden(name, tmp_path):
     # --- forward parity (BASELINE.json: fp32 MAE <= 1e-4 vs the reference)
     assert (y_hat.detach().cpu() - fx["y_hat"]).abs().mean().item() <= 1e-4
     th_err = (theta[0].detach().cpu() - fx["theta0"]).abs().max().item()
-    print(f"bf16 mode: theta max err {th_err:.2e}")
-    assert th_err < 2e-4       # the trunk's Linear runs in TF32 in this mode
+    print(f"fp32 mode: theta max err {th_err:.2e}")
+    assert th_err < 2e-4
     ref_knn = unpack(fx["adj_knn_bits"], n)
     assert int((adj_knn.cpu() != ref_knn).sum()) <= 8          # threshold ties are implementation-defined
     with torch.no_grad():
@@ -105,7 +105,7 @@ def test_full_size_properties_metr_la(tmp_path):
             assert p.grad is not None and torch.isfinite(p.grad).all(), k
 
 
-@pytest.mark.parametrize("name", ["step_METR-LA_b2.pt"])
+@pytest.mark.parametrize("name", ["step_METR-LA_b2.pt", "step_PEMS08_b1.pt"])      # P = 168 and P = 336 (key-split attention)
 def test_step_bf16_encoder_against_reference_golden(name, tmp_path):
     """Performance precision: TSFormer on the tensor cores in bf16 (everything downstream fp32).  Stated tolerance
     for this mode: y_hat MAE <= 5e-3, adj_knn differs in <= 2% of the selected edges (the top-k threshold cuts through
@@ -135,7 +135,7 @@ def test_step_bf16_encoder_against_reference_golden(name, tmp_path):
 @pytest.mark.parametrize("dataset,B,P", [("PEMS07", 2, 168), ("PEMS04", 2, 336)])
 def test_large_graph_shapes_run_and_stay_consistent(dataset, B, P, tmp_path):
     """BASELINE configs[2]/[4] shapes (N=307 with 336 patches; N=883): the same kernels, other tiling branches
-    (several row tiles / key blocks, P > 176 -> fp32 encoder, N > 256 -> CUDA-core dP).  Checks: finite fwd+bwd,
+    (several row tiles, P > 176 -> key-split attention, N > 256 -> CUDA-core dP).  Checks: finite fwd+bwd,
     adjacency invariants, and tensor-core vs CUDA-core node mixing agree (split-bf16 mix is fp32-accurate)."""
     import subprocess, sys, json
     from step.step_loss import step_loss

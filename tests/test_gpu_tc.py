@@ -56,7 +56,8 @@ def test_tc_linear_relu_and_resln():
     assert (ops.tc_image_to_rows(y_img, T, 96).cpu() - bf(y.cpu())).abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("S,P", [(3, 168), (16, 168), (5, 100), (2, 24)])
+# P > 176: key-split kernel (two 176-key blocks merged through shared memory); 336 = PEMS03/04/08 histories
+@pytest.mark.parametrize("S,P", [(3, 168), (16, 168), (5, 100), (2, 24), (3, 336), (301, 336), (4, 200), (2, 177), (3, 352)])
 def test_tc_qkv_attention(S, P):
     from step_b200 import ops
     g = torch.Generator().manual_seed(S * 7 + P)
@@ -71,8 +72,18 @@ def test_tc_qkv_attention(S, P):
     o_img = ops.tc_qkv_attention(ops.tc_rows_to_image(x.to(DEV)), ops.tc_pack_weight(w.to(DEV)), b.to(DEV), S, P)
     out = ops.tc_image_to_rows(o_img, T, 96).cpu()
     err = (out - ref).abs()
-    # bf16 q/k/v/p: ~2^-8 relative per operand; values are O(1)
-    assert err.max().item() < 4e-2 and err.mean().item() < 4e-3, (err.max().item(), err.mean().item())
+    # vs exact fp32 softmax: bf16 q/k/v/p carry ~2^-8 relative error per operand; values are O(1).  The max grows with
+    # the number of outputs (a CPU emulation of the same roundings reproduces it), the mean does not.
+    assert err.max().item() < 1e-1 and err.mean().item() < 4e-3, (err.max().item(), err.mean().item())
+    # vs a CPU emulation of the kernel's own roundings (scaled q, k, v and p rounded to bf16, fp32 statistics,
+    # normalisation by the unrounded row sum, bf16 output): only ex2.approx / summation order / rounding flips remain
+    qs = bf(sh(q) * (1.0 / math.sqrt(24)) * 1.4426950408889634)
+    sc = qs @ bf(sh(k)).transpose(-1, -2)
+    p = torch.exp2(sc - sc.max(-1, keepdim=True).values)
+    emu = bf((bf(p) @ bf(sh(v))) / p.sum(-1, keepdim=True)).transpose(1, 2).reshape(T, 96)
+    e2 = (out - emu).abs()
+    rel = (e2 / (emu.abs() + 1.0)).max().item()          # one bf16 ulp of the output is 2^-8 relative
+    assert rel < 1e-2 and e2.mean().item() < 3e-4, (rel, e2.max().item(), e2.mean().item())
 
 
 def _layers(sd):
@@ -88,7 +99,7 @@ def _layers(sd):
     return [{k: v.to(DEV) for k, v in l.items()} for l in out]
 
 
-@pytest.mark.parametrize("B,N,P,real", [(2, 9, 168, False), (1, 40, 168, True), (3, 5, 24, False)])
+@pytest.mark.parametrize("B,N,P,real", [(2, 9, 168, False), (1, 40, 168, True), (3, 5, 24, False), (1, 11, 336, False)])
 def test_ts_encoder_bf16_close_to_oracle(B, N, P, real):
     import os
     from conftest import GOLDEN
