@@ -30,6 +30,19 @@ sys.path.insert(0, ROOT)
 DATASET = "METR-LA"
 NODES, BATCH, PATCHES = 207, 32, 168
 METRIC = "STEP fwd+bwd samples/sec (STEP_METR-LA, N=207, per-GPU batch 32, 12->12)"
+# (nodes, per-GPU batch, patches) of the reference's STEP_<NAME>.py configs
+WORKLOADS = {"METR-LA": (207, 32, 168), "PEMS04": (307, 8, 336), "PEMS-BAY": (325, 32, 168), "PEMS07": (883, 4, 168)}
+
+
+def set_workload(name):
+    global DATASET, NODES, BATCH, PATCHES, METRIC
+    DATASET = name
+    NODES, BATCH, PATCHES = WORKLOADS[name]
+    METRIC = "STEP fwd+bwd samples/sec (STEP_%s, N=%d, per-GPU batch %d, 12->12)" % (name, NODES, BATCH)
+    GW_ARGS["num_nodes"] = NODES
+    TS_ARGS["num_token"] = float(PATCHES)
+
+
 TS_ARGS = dict(patch_size=12, in_channel=1, embed_dim=96, num_heads=4, mlp_ratio=4, dropout=0.1, num_token=168.0,
                mask_ratio=0.75, encoder_depth=4, decoder_depth=1, mode="forecasting")
 GW_ARGS = dict(num_nodes=NODES, support_len=2, dropout=0.3, gcn_bool=True, addaptadj=True, aptinit=None, in_dim=2,
@@ -43,7 +56,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help="per-GPU batch (default: the config's 32)")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's, 32 for METR-LA)")
+    ap.add_argument("--workload", default="METR-LA", choices=sorted(WORKLOADS),
+                    help="STEP config to run; METR-LA is the headline (BASELINE.json configs[1]), the others are "
+                         "the remaining configs' shapes with synthetic TSFormer weights (not bench lines)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only-resident", action="store_true", help="profiling aid: run only the device-resident loop")
     ap.add_argument("--no-dropout", action="store_true", help="parity-style run (all dropout off); not the headline")
@@ -109,6 +125,9 @@ def write_dataset(tmp, node_feats):
 
 
 def ts_state():
+    if DATASET != "METR-LA":        # only the METR-LA checkpoint is small enough to ship as a fixture
+        from oracle import step_oracle as O
+        return O.synthetic_tsformer_params(1)
     return torch.load(os.path.join(ROOT, "tests", "golden", "tsformer_METR-LA_state.pt"))
 
 
@@ -140,7 +159,7 @@ def cpu_reference_run(steps, warmup, batch, dropout=True):
             times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
     return batch / dt, {"cores": torch.get_num_threads(), "kind": "port",
-                        "sample": f"{steps} timed fwd+bwd steps (after {warmup} warm-up) of STEP_METR-LA at batch {batch} "
+                        "sample": f"{steps} timed fwd+bwd steps (after {warmup} warm-up) of STEP_{DATASET} at batch {batch} "
                                   f"(CPU samples/s is ~flat in batch), fp32, dropout {'live as in the reference train()' if dropout else 'off'}, "
                                   f"{dt:.2f} s/step"}
 
@@ -148,6 +167,9 @@ def cpu_reference_run(steps, warmup, batch, dropout=True):
 # --------------------------------------------------------------------------------------------- our arm
 def main():
     args = parse()
+    set_workload(args.workload)
+    if args.batch is None:
+        args.batch = BATCH
     if not os.environ.get("STEP_B200_KEEP_NCCL_DEBUG"):
         os.environ["NCCL_DEBUG"] = "WARN"       # NCCL's version banner goes to stdout and would precede the JSON line
     rank = int(os.environ.get("RANK", "0"))
@@ -163,7 +185,7 @@ def main():
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * b / v,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
-                          "data": "synthetic", "config": {"workload": "STEP_METR-LA N=207 P=168 12->12, CPU sample batch %d" % b},
+                          "data": "synthetic", "config": {"workload": "STEP_%s N=%d P=%d 12->12, CPU sample batch %d" % (DATASET, NODES, PATCHES, b)},
                           "cpu_baseline": info,
                           "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -344,8 +366,8 @@ def main():
         ffn_ms = time_ms(lambda: ops.tc_linear(x_img, w1, b1, tokens, 96, 384, 1))
         ffn_bytes = tokens * (96 + 384) * 2.0                            # bf16 activations in + out (weights stay in smem)
         ffn_gbs = ffn_bytes / (ffn_ms * 1e-3) / 1e9
-        roofline = {"kernel": "tc_attn_kernel<168,%d> (one TSFormer layer: S=QK^T, softmax, PV on tcgen05; %d sequences x 4 heads, "
-                              "P=168, head dim 24)" % (1 if drop > 0 else 0, S_seq),
+        roofline = {"kernel": "tc_attn_kernel<%d,%d> (one TSFormer layer: S=QK^T, softmax, PV on tcgen05; %d sequences x 4 heads, "
+                              "P=%d, head dim 24)" % (PATCHES, 1 if drop > 0 else 0, S_seq, PATCHES),
                     "bound": "tensor", "achieved": att_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": att_tflops / pk["bf16_tflops"], "ms": att_ms, "useful_flops": att_flops,
                     "traffic": 970.5e6, "traffic_source": "profiles/r01_ncu_full_attn.txt (dram read+write per launch)",
@@ -373,13 +395,15 @@ def main():
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "fp32", "data": "synthetic",
-        "config": {"workload": "STEP_METR-LA fwd+loss+bwd, N=207, per-GPU batch %d, P=168 (2016-step history), 12->12" % B,
+        "config": {"workload": "STEP_%s fwd+loss+bwd, N=%d, per-GPU batch %d, P=%d (%d-step history), 12->12"
+                               % (DATASET, NODES, B, PATCHES, PATCHES * 12),
                    "parallelism": "dp%d (batch-parallel, NCCL grad all-reduce)" % world if world > 1 else "single GPU",
                    "dropout": "off" if args.no_dropout else "live (TSFormer 0.1 in train(), gcn 0.3) as the reference trains",
                    "l2": "inputs > L2: each step streams a fresh 160 MB long-history batch and ~1 GB of activations",
                    "precision": ("TSFormer encoder bf16 operands / fp32 accumulate on tcgen05; graph learning + GWNet fp32"
                                  if args.precision == "bf16" else "fp32 everywhere"),
-                   "ts_chunk_seqs": args.chunk_seqs, "weights": "real TSFormer_METR-LA encoder, seeded random GWNet/DGL"},
+                   "ts_chunk_seqs": args.chunk_seqs, "weights": ("real TSFormer_METR-LA encoder" if DATASET == "METR-LA" else "seeded random TSFormer encoder")
+                              + ", seeded random GWNet/DGL"},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
