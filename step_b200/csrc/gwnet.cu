@@ -33,10 +33,12 @@ struct GwPlan {
   size_t off_sums_fwd, off_sums_bwd;  // doubles, [L][2][32] each (offsets in floats)
   size_t off_coef;                  // [L][4][32] floats: BN-backward coefficients
   size_t off_z[GW_MAX_LAYERS], off_f[GW_MAX_LAYERS], off_g[GW_MAX_LAYERS], off_q[GW_MAX_LAYERS][3];
+  size_t off_a[GW_MAX_LAYERS][3];   // a_s = W_s2 u, kept for dP and the weight gradients (tensor-core mix path)
   size_t off_U, off_M, off_H;       // forward scratch, [B,12,N,32]
   size_t off_DH, off_DZC, off_DQ[3], off_A[3], off_DA, off_DU, off_DPF, off_DPG, off_DR[2];
   size_t off_M3[3], off_O3[3], off_DA3[3];   // tensor-core mix path: per-support mix outputs
   size_t off_img[3];                          // bf16 split images of P1, P2 (per sample) and P3
+  size_t off_dus;                             // [L][B,N,32] skip-path gradient wrt u at each layer's last time step
   size_t total;
 };
 
@@ -60,6 +62,7 @@ static GwPlan make_plan(int B, int N, int L) {
     const size_t n = (size_t)B * p.Tout[i] * p.col;
     p.off_z[i] = take(n); p.off_f[i] = take(n); p.off_g[i] = take(n);
     for (int s = 0; s < 3; ++s) p.off_q[i][s] = take(n);
+    for (int s = 0; s < 3; ++s) p.off_a[i][s] = take(n);
   }
   const size_t big = (size_t)B * 12 * p.col;
   p.off_U = take(big); p.off_M = take(big); p.off_H = take(big);
@@ -73,6 +76,7 @@ static GwPlan make_plan(int B, int N, int L) {
   p.off_img[0] = take(img_floats * B);
   p.off_img[1] = take(img_floats * B);
   p.off_img[2] = take(img_floats);
+  p.off_dus = take((size_t)L * B * p.col);
   p.total = o;
   return p;
 }
@@ -299,7 +303,7 @@ struct GwFwdArgs {
   const float *in_scale, *in_shift;      // [32] BN-on-load of the previous layer
   const float *P[3]; long long pstride[3];  // supports, per-sample stride (0 for the shared adaptive one)
   step_gw_layer_params w;
-  float *f, *g, *q[3], *U, *M, *H, *skip;
+  float *f, *g, *q[3], *U, *M, *H;
   int stage;                              // 0: fused CUDA-core layer; 1: conv + skip + a_s; 2: q_s; 3: output (tensor-core mixes in between)
   float *Aout[3];                         // stage 1: a_s = W_s2 u
   const float *Min[3], *Oin[3];           // stage 2 / 3: tensor-core mix results
@@ -373,30 +377,6 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
   }
   __syncthreads();
 
-  // ---- phase S: skip conv at the last time step only ----
-  if (t == a.Tout - 1) {
-    copy_to_smem(Y, U, N);
-    __syncthreads();
-    {
-      const int k = tid;  // 256 skip channels
-      float wk[GC];
-      load_row(a.w.skip_w + (size_t)k * GC, wk);
-      const float bk = a.w.skip_b[k];
-      float *sk = a.skip + (size_t)b * N * GSKIP + k;
-      for (int n = 0; n < N; ++n) {
-        const float4 *y = reinterpret_cast<const float4 *>(Y + (size_t)n * GC);
-        float acc = bk;
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 yy = y[c4];
-          acc = fmaf(wk[4 * c4], yy.x, acc); acc = fmaf(wk[4 * c4 + 1], yy.y, acc);
-          acc = fmaf(wk[4 * c4 + 2], yy.z, acc); acc = fmaf(wk[4 * c4 + 3], yy.w, acc);
-        }
-        sk[(size_t)n * GSKIP] += acc;
-      }
-    }
-    __syncthreads();
-  }
   }  // stage <= 1
   if (!a.has_gcn) return;
 
@@ -507,6 +487,131 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
   if (a.collect_stats) column_sums_to(Y, N, Wb, a.sums, a.sums + 32);
 }
 
+// ---------------------------------------------------------------------------
+// skip convolutions of ALL layers, hoisted out of the layer kernels (only the last time step of each layer's
+// u = f*g reaches the output because skip[..., -T:] truncation ends at T = 1; model.py:189-197):
+//   skip[b,n,:] = sum_l ( Wk_l u_l[b, Tout_l - 1, n, :] + bk_l )
+// grid (ceil(N/64), B), 256 threads = skip channels; a 64-node tile of u_l is staged in shared memory per layer.
+// ---------------------------------------------------------------------------
+struct GwSkipArgs {
+  int L, N, B;
+  int Tout[GW_MAX_LAYERS];
+  const float *f[GW_MAX_LAYERS], *g[GW_MAX_LAYERS];      // [B,Tout_l,N,32]
+  const float *skip_w[GW_MAX_LAYERS], *skip_b[GW_MAX_LAYERS];
+  float *dskip_w[GW_MAX_LAYERS], *dskip_b[GW_MAX_LAYERS];
+  float *skip;              // forward out [B,N,256]
+  const float *dskip;       // backward in [B,N,256]
+  float *dus;               // backward out [L][B,N,32]
+};
+
+constexpr int SKIP_NT = 64;
+
+__global__ void __launch_bounds__(GSKIP) gw_skip_fwd_kernel(GwSkipArgs a) {
+  __shared__ __align__(16) float Us[SKIP_NT][GC];
+  const int k = threadIdx.x, b = blockIdx.y, n0 = blockIdx.x * SKIP_NT;
+  const int nn = min(SKIP_NT, a.N - n0);
+  float acc[SKIP_NT];
+  float bsum = 0.f;
+#pragma unroll
+  for (int n = 0; n < SKIP_NT; ++n) acc[n] = 0.f;
+  for (int l = 0; l < a.L; ++l) {
+    const size_t base = (((size_t)b * a.Tout[l] + a.Tout[l] - 1) * a.N + n0) * GC;
+    __syncthreads();
+    for (int i = k; i < SKIP_NT * GC / 4; i += GSKIP) {
+      float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i * 4 < nn * GC) {
+        const float4 fv = *reinterpret_cast<const float4 *>(a.f[l] + base + (size_t)i * 4);
+        const float4 gv = *reinterpret_cast<const float4 *>(a.g[l] + base + (size_t)i * 4);
+        u = make_float4(fv.x * gv.x, fv.y * gv.y, fv.z * gv.z, fv.w * gv.w);
+      }
+      reinterpret_cast<float4 *>(&Us[0][0])[i] = u;
+    }
+    __syncthreads();
+    float wk[GC];
+    load_row(a.skip_w[l] + (size_t)k * GC, wk);
+    bsum += a.skip_b[l][k];
+#pragma unroll
+    for (int n = 0; n < SKIP_NT; ++n) {
+      const float4 *y = reinterpret_cast<const float4 *>(&Us[n][0]);
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; c4 += 2) {
+        const float4 y0 = y[c4], y1 = y[c4 + 1];
+        s0 = fmaf(wk[4 * c4], y0.x, s0); s0 = fmaf(wk[4 * c4 + 1], y0.y, s0);
+        s0 = fmaf(wk[4 * c4 + 2], y0.z, s0); s0 = fmaf(wk[4 * c4 + 3], y0.w, s0);
+        s1 = fmaf(wk[4 * c4 + 4], y1.x, s1); s1 = fmaf(wk[4 * c4 + 5], y1.y, s1);
+        s1 = fmaf(wk[4 * c4 + 6], y1.z, s1); s1 = fmaf(wk[4 * c4 + 7], y1.w, s1);
+      }
+      acc[n] += s0 + s1;
+    }
+  }
+  float *sk = a.skip + ((size_t)b * a.N + n0) * GSKIP + k;
+#pragma unroll
+  for (int n = 0; n < SKIP_NT; ++n)
+    if (n < nn) sk[(size_t)n * GSKIP] = acc[n] + bsum;
+}
+
+// backward of the same: grid (L, B), 256 threads.
+//   dus_l[b,n,:] = Wk_l^T dskip[b,n,:]  (thread = node),  dWk_l += dskip[b]^T u_l,  dbk_l += column sums (thread = channel)
+__global__ void __launch_bounds__(GSKIP) gw_skip_bwd_kernel(GwSkipArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, l = blockIdx.x, b = blockIdx.y, N = a.N;
+  float *Wk = smem;                    // [256][32]
+  float *Us = smem + GSKIP * GC;       // [N][32]
+  const float *ds = a.dskip + (size_t)b * N * GSKIP;
+  const size_t base = (((size_t)b * a.Tout[l] + a.Tout[l] - 1) * N) * GC;
+  for (int i = tid; i < GSKIP * GC / 4; i += GSKIP)
+    reinterpret_cast<float4 *>(Wk)[i] = reinterpret_cast<const float4 *>(a.skip_w[l])[i];
+  for (int i = tid; i < N * GC / 4; i += GSKIP) {
+    const float4 fv = *reinterpret_cast<const float4 *>(a.f[l] + base + (size_t)i * 4);
+    const float4 gv = *reinterpret_cast<const float4 *>(a.g[l] + base + (size_t)i * 4);
+    reinterpret_cast<float4 *>(Us)[i] = make_float4(fv.x * gv.x, fv.y * gv.y, fv.z * gv.z, fv.w * gv.w);
+  }
+  __syncthreads();
+  for (int n = tid; n < N; n += GSKIP) {
+    float du[GC];
+#pragma unroll
+    for (int c = 0; c < GC; ++c) du[c] = 0.f;
+    const float4 *dsn = reinterpret_cast<const float4 *>(ds + (size_t)n * GSKIP);
+    for (int k4 = 0; k4 < GSKIP / 4; ++k4) {
+      const float4 d4 = dsn[k4];
+      const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 *wk = reinterpret_cast<const float4 *>(Wk + (size_t)(4 * k4 + j) * GC);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 ww = wk[c4];
+          du[4 * c4] = fmaf(ww.x, dd[j], du[4 * c4]); du[4 * c4 + 1] = fmaf(ww.y, dd[j], du[4 * c4 + 1]);
+          du[4 * c4 + 2] = fmaf(ww.z, dd[j], du[4 * c4 + 2]); du[4 * c4 + 3] = fmaf(ww.w, dd[j], du[4 * c4 + 3]);
+        }
+      }
+    }
+    store_row(a.dus + (((size_t)l * a.B + b) * N + n) * GC, du);
+  }
+  {
+    const int k = tid;
+    float acc[GC];
+#pragma unroll
+    for (int c = 0; c < GC; ++c) acc[c] = 0.f;
+    float bsum = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const float d = ds[(size_t)n * GSKIP + k];
+      bsum += d;
+      const float4 *y = reinterpret_cast<const float4 *>(Us + (size_t)n * GC);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 yy = y[c4];
+        acc[4 * c4] = fmaf(d, yy.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(d, yy.y, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(d, yy.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(d, yy.w, acc[4 * c4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < GC; ++c) atomicAdd(a.dskip_w[l] + (size_t)k * GC + c, acc[c]);
+    atomicAdd(a.dskip_b[l] + k, bsum);
+  }
+}
+
 // sums (double [2][32]) -> stats [4][32] floats: mean, biased var, scale, shift
 __global__ void bn_finalize_kernel(const double *sums, double count, const float *gamma, const float *beta, float *stats) {
   const int c = threadIdx.x;
@@ -534,7 +639,7 @@ struct GwBwdArgs {
   step_gw_layer_params w;
   step_gw_layer_grads gr;
   const float *f, *g;
-  const float *dskip;       // [B,N,256]
+  const float *dus;         // [B,N,32] = Wk^T dskip of this layer (gw_skip_bwd_kernel), added at the last time step
   float *U, *DH, *DZC, *DQ[3], *A[3], *DA, *DU, *DPF, *DPG;
   int stage;                // 0: fused CUDA-core layer; 1: up to dh/du0 (before the tensor-core mixes); 2: after them
   const float *DA3[3];      // stage 2: da_s = P_s dq_s from the tensor-core mix
@@ -573,8 +678,12 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
       store_row(U + (size_t)n * GC, fv);
     }
     float du[GC];
+    if (t == a.Tout - 1) {          // skip path: Wk^T dskip of this layer, from gw_skip_bwd_kernel
+      load_row(a.dus + ((size_t)b * N + n) * GC, du);
+    } else {
 #pragma unroll
-    for (int c = 0; c < GC; ++c) du[c] = 0.f;
+      for (int c = 0; c < GC; ++c) du[c] = 0.f;
+    }
     if (a.has_gcn) {
       float dh[GC];
       {
@@ -618,24 +727,17 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
   }
   if (STAGE == 1) return;
   if (a.has_gcn && STAGE == 2) {
-    // dq_s = P_s dh and da_s = P_s dq_s were produced by tc_mix_kernel
-    for (int s = 0; s < 3; ++s) {
-      const float *W1 = Wb + (1 + 2 * s) * 1024, *W2 = Wb + (2 + 2 * s) * 1024;
-      const float *DQ = a.DQ[s] + ocol, *DAs = a.DA3[s] + ocol;
-      float *As = a.A[s] + ocol;
-      for (int n = tid; n < N; n += GW_THREADS) {
-        {
-          float u[GC];
-          load_row(U + (size_t)n * GC, u);
-          float *ar = As + (size_t)n * GC;
-          matvec_chunks(W2, u, [&](int cg, float4 v) { st4(ar + 4 * cg, v); });
-        }
-        float du[GC];
-        load_row(DU + (size_t)n * GC, du);
-        matvec_t_acc(W1, DQ + (size_t)n * GC, du);
-        matvec_t_acc(W2, DAs + (size_t)n * GC, du);
-        store_row(DU + (size_t)n * GC, du);
+    // dq_s = P_s dh and da_s = P_s dq_s were produced by tc_mix_kernel: du += sum_s W_s1^T dq_s + W_s2^T da_s
+    // (a_s = W_s2 u, needed by dP, comes from the forward stash)
+    for (int n = tid; n < N; n += GW_THREADS) {
+      float du[GC];
+      load_row(DU + (size_t)n * GC, du);
+#pragma unroll 1
+      for (int s = 0; s < 3; ++s) {
+        matvec_t_acc(Wb + (1 + 2 * s) * 1024, a.DQ[s] + ocol + (size_t)n * GC, du);
+        matvec_t_acc(Wb + (2 + 2 * s) * 1024, a.DA3[s] + ocol + (size_t)n * GC, du);
       }
+      store_row(DU + (size_t)n * GC, du);
     }
     {
       const float *const Xs[6] = {a.DQ[0] + ocol, a.DA3[0] + ocol, a.DQ[1] + ocol, a.DA3[1] + ocol, a.DQ[2] + ocol, a.DA3[2] + ocol};
@@ -676,52 +778,6 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
       copy_to_smem(Y, DH, N);
       __syncthreads();
     }
-  }
-
-  // ---- skip path (last time step only): du += Wk^T dskip, dWk, dbk ----
-  if (t == a.Tout - 1) {
-    const float *ds = a.dskip + (size_t)b * N * GSKIP;
-    for (int n = tid; n < N; n += GW_THREADS) {
-      float du[GC];
-      load_row(DU + (size_t)n * GC, du);
-      const float *dsn = ds + (size_t)n * GSKIP;
-      for (int k = 0; k < GSKIP; ++k) {
-        const float d = dsn[k];
-        const float4 *wk = reinterpret_cast<const float4 *>(a.w.skip_w + (size_t)k * GC);
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 ww = wk[c4];
-          du[4 * c4] = fmaf(ww.x, d, du[4 * c4]); du[4 * c4 + 1] = fmaf(ww.y, d, du[4 * c4 + 1]);
-          du[4 * c4 + 2] = fmaf(ww.z, d, du[4 * c4 + 2]); du[4 * c4 + 3] = fmaf(ww.w, d, du[4 * c4 + 3]);
-        }
-      }
-      store_row(DU + (size_t)n * GC, du);
-    }
-    __syncthreads();
-    copy_to_smem(Y, U, N);
-    __syncthreads();
-    {
-      const int k = tid;
-      float acc[GC];
-#pragma unroll
-      for (int c = 0; c < GC; ++c) acc[c] = 0.f;
-      float bsum = 0.f;
-      for (int n = 0; n < N; ++n) {
-        const float d = ds[(size_t)n * GSKIP + k];
-        bsum += d;
-        const float4 *y = reinterpret_cast<const float4 *>(Y + (size_t)n * GC);
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 yy = y[c4];
-          acc[4 * c4] = fmaf(d, yy.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(d, yy.y, acc[4 * c4 + 1]);
-          acc[4 * c4 + 2] = fmaf(d, yy.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(d, yy.w, acc[4 * c4 + 3]);
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < GC; ++c) atomicAdd(a.gr.skip_w + (size_t)k * GC + c, acc[c]);
-      atomicAdd(a.gr.skip_b + k, bsum);
-    }
-    __syncthreads();
   }
 
   // ---- through the gate: d(pre-tanh), d(pre-sigmoid) ----
@@ -993,8 +1049,7 @@ extern "C" int step_gwnet_stack_fwd(const float *x0, const float *P1, const floa
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const GwPlan p = make_plan(B, N, n_layers);
-  cudaError_t e = cudaMemsetAsync(skip_out, 0, (size_t)B * N * GSKIP * sizeof(float), st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(stash + p.off_sums_fwd, 0, (size_t)n_layers * 2 * 32 * sizeof(double), st);
+  cudaError_t e = cudaMemsetAsync(stash + p.off_sums_fwd, 0, (size_t)n_layers * 2 * 32 * sizeof(double), st);
   if (e != cudaSuccess) return fail_msg((int)e, cudaGetErrorString(e));
   const bool use_tc = gw_use_tc(N);
   const MixGeom geom = mix_geom(N);
@@ -1020,7 +1075,6 @@ extern "C" int step_gwnet_stack_fwd(const float *x0, const float *P1, const floa
     a.f = stash + p.off_f[i]; a.g = stash + p.off_g[i];
     for (int s = 0; s < 3; ++s) a.q[s] = stash + p.off_q[i][s];
     a.U = stash + p.off_U; a.M = stash + p.off_M; a.H = stash + p.off_H;
-    a.skip = skip_out;
     a.sums = reinterpret_cast<double *>(stash + p.off_sums_fwd) + (size_t)i * 64;
     if (training && drop_p > 0.f) { a.drop_thr = drop_threshold(drop_p); a.drop_scale = 1.f / (1.f - drop_p); }
     else { a.drop_thr = 0; a.drop_scale = 1.f; }
@@ -1035,13 +1089,13 @@ extern "C" int step_gwnet_stack_fwd(const float *x0, const float *P1, const floa
       for (int s = 0; s < 3; ++s) {
         m.img[s] = reinterpret_cast<const uint8_t *>(stash + p.off_img[s]);
         m.img_bstride[s] = (s < 2) ? (long long)img_floats * 4 : 0;
-        a.Aout[s] = stash + p.off_A[s];
+        a.Aout[s] = stash + p.off_a[i][s];
         a.Min[s] = stash + p.off_M3[s];
         a.Oin[s] = stash + p.off_O3[s];
       }
       gw_layer_fwd_kernel<1><<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
       STEP_LAUNCH_CHECK("gw_layer_fwd_kernel[conv]");
-      for (int s = 0; s < 3; ++s) { m.Y[s] = stash + p.off_A[s]; m.out[s] = stash + p.off_M3[s]; }
+      for (int s = 0; s < 3; ++s) { m.Y[s] = stash + p.off_a[i][s]; m.out[s] = stash + p.off_M3[s]; }
       if ((rc = tc_mix_launch(m, st))) return rc;
       gw_layer_fwd_kernel<2><<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
       STEP_LAUNCH_CHECK("gw_layer_fwd_kernel[q]");
@@ -1054,6 +1108,16 @@ extern "C" int step_gwnet_stack_fwd(const float *x0, const float *P1, const floa
       bn_finalize_kernel<<<1, 32, 0, st>>>(a.sums, (double)B * a.Tout * N, Lp[i].bn_w, Lp[i].bn_b, bn_stats + (size_t)i * 128);
       STEP_LAUNCH_CHECK("bn_finalize_kernel");
     }
+  }
+  {
+    GwSkipArgs k{};
+    k.L = n_layers; k.N = N; k.B = B; k.skip = skip_out;
+    for (int i = 0; i < n_layers; ++i) {
+      k.Tout[i] = p.Tout[i]; k.f[i] = stash + p.off_f[i]; k.g[i] = stash + p.off_g[i];
+      k.skip_w[i] = Lp[i].skip_w; k.skip_b[i] = Lp[i].skip_b;
+    }
+    gw_skip_fwd_kernel<<<dim3((N + SKIP_NT - 1) / SKIP_NT, B), GSKIP, 0, st>>>(k);
+    STEP_LAUNCH_CHECK("gw_skip_fwd_kernel");
   }
   return STEP_OK;
 }
@@ -1100,6 +1164,20 @@ extern "C" int step_gwnet_stack_bwd(const float *dskip, const float *x0, const f
   const MixGeom geom = mix_geom(N);
   const size_t img_floats = (mix_images_bytes(N) + 3) / 4;
 
+  {
+    // skip path of every layer in one launch: dus_l = Wk_l^T dskip, dWk_l, dbk_l
+    GwSkipArgs k{};
+    k.L = n_layers; k.N = N; k.B = B; k.dskip = dskip; k.dus = stash + p.off_dus;
+    for (int i = 0; i < n_layers; ++i) {
+      k.Tout[i] = p.Tout[i]; k.f[i] = stash + p.off_f[i]; k.g[i] = stash + p.off_g[i];
+      k.skip_w[i] = Lp[i].skip_w; k.dskip_w[i] = Lg[i].skip_w; k.dskip_b[i] = Lg[i].skip_b;
+    }
+    const size_t smem_skip = ((size_t)GSKIP * GC + (size_t)N * GC) * sizeof(float);
+    if ((rc = allow_smem(gw_skip_bwd_kernel, 227 * 1024))) return rc;
+    gw_skip_bwd_kernel<<<dim3(n_layers, B), GSKIP, smem_skip, st>>>(k);
+    STEP_LAUNCH_CHECK("gw_skip_bwd_kernel");
+  }
+
   for (int i = n_layers - 1; i >= 0; --i) {
     const bool has_gcn = (Lp[i].mlp_w != nullptr);
     GwBwdArgs a{};
@@ -1112,7 +1190,7 @@ extern "C" int step_gwnet_stack_bwd(const float *dskip, const float *x0, const f
     a.pstride[0] = (long long)nn; a.pstride[1] = (long long)nn; a.pstride[2] = 0;
     a.w = Lp[i]; a.gr = Lg[i];
     a.f = stash + p.off_f[i]; a.g = stash + p.off_g[i];
-    a.dskip = dskip;
+    a.dus = stash + p.off_dus + (size_t)i * B * p.col;
     a.U = stash + p.off_U; a.DH = stash + p.off_DH; a.DZC = stash + p.off_DZC;
     for (int s = 0; s < 3; ++s) { a.DQ[s] = stash + p.off_DQ[s]; a.A[s] = stash + p.off_A[s]; }
     a.DA = stash + p.off_DA; a.DU = stash + p.off_DU; a.DPF = stash + p.off_DPF; a.DPG = stash + p.off_DPG;
@@ -1141,7 +1219,10 @@ extern "C" int step_gwnet_stack_bwd(const float *dskip, const float *x0, const f
     if (has_gcn) {
       GwDpArgs d{};
       d.N = N; d.T = p.Tout[i]; d.B = B;
-      for (int s = 0; s < 3; ++s) { d.Q[s] = stash + p.off_q[i][s]; d.A[s] = stash + p.off_A[s]; d.DQ[s] = stash + p.off_DQ[s]; }
+      // a_s: stashed by the forward on the tensor-core path, recomputed into scratch by the fused CUDA-core backward
+      for (int s = 0; s < 3; ++s) {
+        d.Q[s] = stash + p.off_q[i][s]; d.A[s] = stash + (use_tc ? p.off_a[i][s] : p.off_A[s]); d.DQ[s] = stash + p.off_DQ[s];
+      }
       d.DH = stash + p.off_DH;
       d.dP[0] = dP1; d.dP[1] = dP2; d.dP[2] = dP3;
       d.pstride[0] = (long long)nn; d.pstride[1] = (long long)nn; d.pstride[2] = 0;
