@@ -112,6 +112,14 @@ int step_ts_encoder_fwd(const float *series, long long sB, long long sT, long lo
                         void *workspace, size_t workspace_bytes, int chunk_seqs,
                         float drop_p, unsigned long long seed, void *stream);
 
+/* The transformer layer stack alone, on caller-provided tokens x [S*P, 96] (already multiplied by sqrt(96));
+ * x is replaced by the output, fnw/fnb (both or neither) = a final LayerNorm fused into the last epilogue.
+ * Used by TSFormer(mode="pre-train") for the encoder over the unmasked tokens and for the decoder
+ * (reference tsformer.py:86-136, transformer_layers.py:13-20).  workspace: step_ts_encoder_workspace_bytes(S, P). */
+int step_ts_layers_fwd(float *x, int S, int P, const step_ts_layer_weights *L, int n_layers, const float *fnw,
+                       const float *fnb, void *workspace, size_t workspace_bytes, float drop_p,
+                       unsigned long long seed, void *stream);
+
 
 /* ------------------------------------------------------------------------ *
  * TSFormer encoder, bf16 tensor-core path (tcgen05.mma + TMEM + TMA bulk copies)

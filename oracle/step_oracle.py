@@ -107,6 +107,36 @@ def tsformer_encode(sd: SD, long_history: Tensor, pre: str = "", heads: int = 4,
     return z.view(B, N, -1, d)
 
 
+def tsformer_pretrain(sd: SD, history: Tensor, unmasked: list, masked: list, pre: str = "", heads: int = 4,
+                      depth: int = 4, dec_depth: int = 1, p_drop: float = 0.0):
+    """TSFormer.forward(mode="pre-train") with the mask draw given (the reference draws it with Python's
+    ``random``, tsformer/mask.py:15-24): step/step_arch/tsformer/tsformer.py:179-188 ->
+    encoding :86-105 (patchify, positional embedding, keep the unmasked tokens, encoder, encoder_norm),
+    decoding :107-136 (enc_2_dec_emb, mask tokens + positional embedding of the masked positions, decoder,
+    decoder_norm, output_layer), get_reconstructed_masked_tokens :138-160.
+    ``history``: [B, P*L, N, C] -> (reconstruction [B, r*P*L, N], label [B, r*P*L, N])."""
+    B, T, N, _ = history.shape
+    series = history[..., 0].permute(0, 2, 1).reshape(B * N, T)
+    z = _drop(tsformer_tokens(sd, series, pre), p_drop)                       # [S, P, d]
+    S, P, d = z.shape
+    L = T // P
+    z = z[:, unmasked, :] * math.sqrt(d)
+    for i in range(depth):
+        z = encoder_layer(sd, f"{pre}encoder.transformer_encoder.layers.{i}.", z, heads, p_drop)
+    z = _layer_norm(z, sd[pre + "encoder_norm.weight"], sd[pre + "encoder_norm.bias"])
+    z = z @ sd[pre + "enc_2_dec_emb.weight"].t() + sd[pre + "enc_2_dec_emb.bias"]
+    m = sd[pre + "mask_token"].view(1, 1, d) + sd[pre + "positional_encoding.position_embedding"][masked].unsqueeze(0)
+    m = _drop(m.expand(S, len(masked), d), p_drop)
+    z = torch.cat([z, m], dim=1) * math.sqrt(d)
+    for i in range(dec_depth):
+        z = encoder_layer(sd, f"{pre}decoder.transformer_encoder.layers.{i}.", z, heads, p_drop)
+    z = _layer_norm(z, sd[pre + "decoder_norm.weight"], sd[pre + "decoder_norm.bias"])
+    rec = (z @ sd[pre + "output_layer.weight"].t() + sd[pre + "output_layer.bias"]).view(B, N, P, L)
+    rec = rec[:, :, len(unmasked):, :].reshape(B, N, -1).transpose(1, 2)
+    label = series.view(B, N, P, L)[:, :, masked, :].reshape(B, N, -1).transpose(1, 2)
+    return rec, label
+
+
 # --------------------------------------------------------------------------- #
 # Discrete graph learning
 # --------------------------------------------------------------------------- #

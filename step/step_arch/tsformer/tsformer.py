@@ -87,6 +87,35 @@ class PositionalEncoding(nn.Module):
         self.position_embedding = nn.Parameter(torch.empty(max_len, hidden_dim), requires_grad=True)
 
 
+class MaskGenerator(nn.Module):
+    """Uniform random patch masking (reference: tsformer/mask.py:6-29): a shuffled ``range(num_tokens)`` from
+    Python's ``random`` module, the first ``int(num_tokens * mask_ratio)`` entries are masked; both index lists are
+    returned sorted.  ``fixed`` (a pair of index lists) pins the draw for parity tests."""
+
+    def __init__(self, num_tokens, mask_ratio):
+        super().__init__()
+        self.num_tokens, self.mask_ratio, self.sort = num_tokens, mask_ratio, True
+        self.fixed = None
+        self.masked_tokens, self.unmasked_tokens = None, None
+
+    def uniform_rand(self):
+        import random
+        order = list(range(int(self.num_tokens)))
+        random.shuffle(order)
+        n_masked = int(self.num_tokens * self.mask_ratio)
+        masked, unmasked = order[:n_masked], order[n_masked:]
+        if self.sort:
+            masked, unmasked = sorted(masked), sorted(unmasked)
+        self.masked_tokens, self.unmasked_tokens = masked, unmasked
+        return unmasked, masked
+
+    def forward(self):
+        if self.fixed is not None:
+            self.unmasked_tokens, self.masked_tokens = list(self.fixed[0]), list(self.fixed[1])
+            return self.unmasked_tokens, self.masked_tokens
+        return self.uniform_rand()
+
+
 class TSFormer(nn.Module):
     """Masked-patch transformer for long time series; ``mode="forecasting"`` is the STEP hot path."""
 
@@ -107,6 +136,7 @@ class TSFormer(nn.Module):
         self.decoder_norm = nn.LayerNorm(embed_dim)
         self.patch_embedding = PatchEmbedding(patch_size, in_channel, embed_dim, norm_layer=None)
         self.positional_encoding = PositionalEncoding(embed_dim, dropout=dropout)
+        self.mask = MaskGenerator(num_token, mask_ratio)
         self.encoder = TransformerLayers(embed_dim, encoder_depth, mlp_ratio, num_heads, dropout)
         self.enc_2_dec_emb = nn.Linear(embed_dim, embed_dim, bias=True)
         self.mask_token = nn.Parameter(torch.zeros(1, 1, 1, embed_dim))
@@ -137,7 +167,7 @@ class TSFormer(nn.Module):
     def encoding(self, long_term_history, mask=False):
         """long_term_history: [B, N, 1, P*L] view -> hidden states [B, N, P, d] (no masking on this path)."""
         if mask:
-            raise NotImplementedError("masked pre-training encoder is listed as 'next' in DESIGN.md (SURVEY section 8(f).3)")
+            raise NotImplementedError("the masked encoding is fused into pretrain_forward(); call forward() in mode='pre-train'")
         series = long_term_history[:, :, 0, :].permute(0, 2, 1)      # [B, P*L, N] view, no copy
         num_nodes = series.shape[2]
         if self.node_shard is not None:
@@ -173,13 +203,52 @@ class TSFormer(nn.Module):
             self.seq_image = ops.tc_hidden_to_seq_image(hidden) if self.precision == "bf16" and hidden.shape[2] * 12 % 8 == 0 else None
         return hidden, None, None
 
+    @torch.no_grad()
+    def pretrain_forward(self, history_data):
+        """``mode="pre-train"`` forward (reference tsformer.py:71-160): embed all patches, encode the unmasked 25 %,
+        ``enc_2_dec_emb``, append mask tokens (+ positional embedding of the masked positions), one decoder layer,
+        ``decoder_norm``, ``output_layer``; returns (reconstruction of the masked patches, their ground truth), both
+        ``[B, r*P*L, N]``.  Forward only on the fp32 kernels: the masked encoder's *backward* (stage-1 training) is
+        listed as next work in DESIGN.md, so the outputs carry no autograd graph.
+        history_data: [B, N, 1, P*L] view."""
+        B, N, _, T = history_data.shape
+        L, d = self.patch_size, self.embed_dim
+        P = T // L
+        S = B * N
+        series = history_data[:, :, 0, :].permute(0, 2, 1)          # [B, P*L, N] view
+        drop = self.dropout_p if self.training else 0.0
+        seed = self._next_seed() if drop > 0 else 0
+        emb, pos = self.patch_embedding.input_embedding, self.positional_encoding.position_embedding
+        unmasked, masked = self.mask()
+        dev = history_data.device
+        ui = torch.as_tensor(unmasked, device=dev, dtype=torch.long)
+        mi = torch.as_tensor(masked, device=dev, dtype=torch.long)
+        # --- encoder over the unmasked tokens (tokens already carry the sqrt(d) scale of transformer_layers.py:15)
+        tokens = ops.ts_embed(series, emb.weight, emb.bias, pos, drop_p=drop, seed=seed).view(S, P, d)
+        enc_in = tokens.index_select(1, ui).reshape(S * len(unmasked), d)
+        hidden_u = ops.ts_layers(enc_in, S, len(unmasked), self.encoder.kernel_weights(), self.encoder_norm.weight,
+                                 self.encoder_norm.bias, drop_p=drop, seed=seed + 1)
+        # --- decoder over [unmasked | mask tokens]
+        dec_u = ops.linear(hidden_u, self.enc_2_dec_emb.weight, self.enc_2_dec_emb.bias).view(S, len(unmasked), d)
+        dec_m = (self.mask_token.view(1, 1, d) + pos[mi].unsqueeze(0)).expand(S, len(masked), d)
+        if drop > 0:
+            dec_m = torch.nn.functional.dropout(dec_m, drop, training=True)      # positional_encoding.py:32
+        full = (torch.cat([dec_u, dec_m], dim=1) * math.sqrt(d)).reshape(S * P, d)
+        hidden_f = ops.ts_layers(full, S, P, self.decoder.kernel_weights(), self.decoder_norm.weight,
+                                 self.decoder_norm.bias, drop_p=drop, seed=seed + 2)
+        recon = ops.linear(hidden_f, self.output_layer.weight, self.output_layer.bias).view(B, N, P, L)
+        # --- masked tokens vs ground truth (tsformer.py:138-160)
+        recon_masked = recon[:, :, len(unmasked):, :].reshape(B, N, -1).transpose(1, 2)
+        label = history_data[:, :, self.selected_feature, :].reshape(B, N, P, L).index_select(2, mi)
+        label_masked = label.reshape(B, N, -1).transpose(1, 2)
+        return recon_masked, label_masked
+
     def forward(self, history_data: torch.Tensor, future_data: torch.Tensor = None, batch_seen: int = None,
                 epoch: int = None, **kwargs) -> torch.Tensor:
         """history_data: [B, L*P, N, 1].  forecasting mode -> [B, N, P, d]."""
         history_data = history_data.permute(0, 2, 3, 1)     # B, N, 1, L*P (view)
         if self.mode == "pre-train":
-            raise NotImplementedError("TSFormer pre-training (mask + decoder + encoder backward) is not part of the "
-                                      "round-1 hot path; see DESIGN.md 'what comes next'")
+            return self.pretrain_forward(history_data)
         with torch.no_grad():
             hidden_states_full, _, _ = self.encoding(history_data, mask=False)
         return hidden_states_full

@@ -449,6 +449,51 @@ extern "C" size_t step_ts_encoder_workspace_bytes(int chunk_seqs, int P) {
   return enc_ws_floats((size_t)chunk_seqs * P) * sizeof(float) + 256;
 }
 
+// the encoder layer stack on T = Sc*P tokens held in X [T,96] (already scaled by sqrt(d)); the result replaces X.
+// fnw/fnb: optional final LayerNorm (encoder_norm / decoder_norm) fused into the last layer's epilogue.
+static int run_layer_stack(float *X, int Sc, int P, const step_ts_layer_weights *L, int n_layers, const float *fnw,
+                           const float *fnb, float *ws, size_t Tc_max, float drop_p, uint64_t cseed, cudaStream_t st) {
+  float *X1 = ws, *O = X1 + Tc_max * 96, *X2 = O + Tc_max * 96, *QKV = X2 + Tc_max * 96;  // QKV/H share
+  uint32_t thr; float dscale;
+  drop_consts(drop_p, thr, dscale);
+  const long long T = (long long)Sc * P;
+  const float *cur = X;
+  int rc;
+  for (int l = 0; l < n_layers; ++l) {
+    const step_ts_layer_weights &w = L[l];
+    const uint32_t site = 16u * (l + 1);
+    GemmArgs g{};
+    // QKV = cur W_in^T + b_in
+    g.A = cur; g.W = w.in_proj_w; g.bias = w.in_proj_b; g.C = QKV; g.M = T; g.K = 96; g.Nout = 288;
+    g.drop_thr = 0; g.drop_scale = 1.f;
+    if ((rc = launch_gemm(g, EPI_NONE, 1, st))) return rc;
+    if ((rc = attn_launch(QKV, O, Sc, P, drop_p, cseed, site + 1, st))) return rc;
+    // X1 = LN1(cur + drop(O W_o^T + b_o))
+    g = GemmArgs{};
+    g.A = O; g.W = w.out_proj_w; g.bias = w.out_proj_b; g.C = X1; g.M = T; g.K = 96; g.Nout = 96;
+    g.residual = cur; g.ln_w = w.norm1_w; g.ln_b = w.norm1_b;
+    g.drop_thr = thr; g.drop_scale = dscale; g.key = rng_key(cseed, site + 2);
+    if ((rc = launch_gemm(g, EPI_RES_LN, 1, st))) return rc;
+    // H = drop(relu(X1 W_1^T + b_1))
+    float *H = QKV;
+    g = GemmArgs{};
+    g.A = X1; g.W = w.lin1_w; g.bias = w.lin1_b; g.C = H; g.M = T; g.K = 96; g.Nout = 384;
+    g.drop_thr = thr; g.drop_scale = dscale; g.key = rng_key(cseed, site + 3);
+    if ((rc = launch_gemm(g, EPI_RELU, 1, st))) return rc;
+    // X2 = LN2(X1 + drop(H W_2^T + b_2)); the last layer also applies the final norm and lands in X
+    const bool last = (l == n_layers - 1);
+    float *dst = last ? X : X2;
+    g = GemmArgs{};
+    g.A = H; g.W = w.lin2_w; g.bias = w.lin2_b; g.C = dst; g.M = T; g.K = 384; g.Nout = 96;
+    g.residual = X1; g.ln_w = w.norm2_w; g.ln_b = w.norm2_b;
+    if (last && fnw != nullptr) { g.ln2_w = fnw; g.ln2_b = fnb; }
+    g.drop_thr = thr; g.drop_scale = dscale; g.key = rng_key(cseed, site + 4);
+    if ((rc = launch_gemm(g, EPI_RES_LN, 1, st))) return rc;
+    cur = dst;
+  }
+  return STEP_OK;
+}
+
 extern "C" int step_ts_encoder_fwd(const float *series, long long sB, long long sT, long long sN, int B, int N, int P,
                                    const float *patch_w, const float *patch_b, const float *pos,
                                    const step_ts_layer_weights *L, int n_layers, const float *fnw, const float *fnb,
@@ -468,49 +513,28 @@ extern "C" int step_ts_encoder_fwd(const float *series, long long sB, long long 
   if (rc) return rc;
   const size_t Tc_max = (size_t)chunk_seqs * P;
   float *ws = reinterpret_cast<float *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  float *X1 = ws, *O = X1 + Tc_max * 96, *X2 = O + Tc_max * 96, *QKV = X2 + Tc_max * 96;  // QKV/H share
-  uint32_t thr; float dscale;
-  drop_consts(drop_p, thr, dscale);
   for (int s0 = 0; s0 < S; s0 += chunk_seqs) {
     const int Sc = (S - s0 < chunk_seqs) ? (S - s0) : chunk_seqs;
-    const long long T = (long long)Sc * P;
-    float *X = hidden + (size_t)s0 * P * 96;
-    const float *cur = X;
-    for (int l = 0; l < n_layers; ++l) {
-      const step_ts_layer_weights &w = L[l];
-      const uint32_t site = 16u * (l + 1);
-      const uint64_t cseed = seed + 0x51ED27ull * (uint64_t)s0;  // decorrelate chunks
-      GemmArgs g{};
-      // QKV = cur W_in^T + b_in
-      g.A = cur; g.W = w.in_proj_w; g.bias = w.in_proj_b; g.C = QKV; g.M = T; g.K = 96; g.Nout = 288;
-      g.drop_thr = 0; g.drop_scale = 1.f;
-      if ((rc = launch_gemm(g, EPI_NONE, 1, st))) return rc;
-      if ((rc = attn_launch(QKV, O, Sc, P, drop_p, cseed, site + 1, st))) return rc;
-      // X1 = LN1(cur + drop(O W_o^T + b_o))
-      g = GemmArgs{};
-      g.A = O; g.W = w.out_proj_w; g.bias = w.out_proj_b; g.C = X1; g.M = T; g.K = 96; g.Nout = 96;
-      g.residual = cur; g.ln_w = w.norm1_w; g.ln_b = w.norm1_b;
-      g.drop_thr = thr; g.drop_scale = dscale; g.key = rng_key(cseed, site + 2);
-      if ((rc = launch_gemm(g, EPI_RES_LN, 1, st))) return rc;
-      // H = drop(relu(X1 W_1^T + b_1))
-      float *H = QKV;
-      g = GemmArgs{};
-      g.A = X1; g.W = w.lin1_w; g.bias = w.lin1_b; g.C = H; g.M = T; g.K = 96; g.Nout = 384;
-      g.drop_thr = thr; g.drop_scale = dscale; g.key = rng_key(cseed, site + 3);
-      if ((rc = launch_gemm(g, EPI_RELU, 1, st))) return rc;
-      // X2 = LN2(X1 + drop(H W_2^T + b_2)); the last layer also applies encoder_norm and lands in `hidden`
-      const bool last = (l == n_layers - 1);
-      float *dst = last ? X : X2;
-      g = GemmArgs{};
-      g.A = H; g.W = w.lin2_w; g.bias = w.lin2_b; g.C = dst; g.M = T; g.K = 384; g.Nout = 96;
-      g.residual = X1; g.ln_w = w.norm2_w; g.ln_b = w.norm2_b;
-      if (last) { g.ln2_w = fnw; g.ln2_b = fnb; }
-      g.drop_thr = thr; g.drop_scale = dscale; g.key = rng_key(cseed, site + 4);
-      if ((rc = launch_gemm(g, EPI_RES_LN, 1, st))) return rc;
-      cur = dst;
-    }
+    const uint64_t cseed = seed + 0x51ED27ull * (uint64_t)s0;  // decorrelate chunks
+    if ((rc = run_layer_stack(hidden + (size_t)s0 * P * 96, Sc, P, L, n_layers, fnw, fnb, ws, Tc_max, drop_p, cseed, st)))
+      return rc;
   }
   return STEP_OK;
+}
+
+// Transformer layer stack on caller-provided tokens (TSFormer pre-training: the encoder over the unmasked tokens
+// and the decoder over [unmasked | mask tokens]; reference tsformer.py:86-136, transformer_layers.py:13-20).
+// x: [S*P, 96] tokens already multiplied by sqrt(96), replaced by the (optionally final-normed) output.
+extern "C" int step_ts_layers_fwd(float *x, int S, int P, const step_ts_layer_weights *L, int n_layers, const float *fnw,
+                                  const float *fnb, void *workspace, size_t workspace_bytes, float drop_p,
+                                  unsigned long long seed, void *stream) {
+  STEP_REQUIRE(x && L && workspace && S > 0 && P > 0 && n_layers >= 1, "ts_layers: bad argument");
+  STEP_REQUIRE((fnw == nullptr) == (fnb == nullptr), "ts_layers: final norm needs both weight and bias");
+  if (workspace_bytes < step_ts_encoder_workspace_bytes(S, P))
+    return fail(STEP_EWORKSPACE, "ts_layers: workspace too small (%lld bytes needed)",
+                (long long)step_ts_encoder_workspace_bytes(S, P));
+  float *ws = reinterpret_cast<float *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  return run_layer_stack(x, S, P, L, n_layers, fnw, fnb, ws, (size_t)S * P, drop_p, seed, (cudaStream_t)stream);
 }
 
 // ===========================================================================

@@ -51,6 +51,8 @@ SIGNATURES = {
     "step_ts_encoder_fwd": (C.c_int, [f32p, ll, ll, ll, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p,
                                       C.POINTER(TsLayerWeights), C.c_int, f32p, f32p, f32p, vp, C.c_size_t, C.c_int,
                                       C.c_float, ull, vp]),
+    "step_ts_layers_fwd": (C.c_int, [f32p, C.c_int, C.c_int, C.POINTER(TsLayerWeights), C.c_int, f32p, f32p, vp, C.c_size_t,
+                                     C.c_float, ull, vp]),
     "step_tc_pack_weight": (C.c_int, [f32p, C.c_int, C.c_int, vp, vp]),
     "step_tc_rows_to_image": (C.c_int, [f32p, ll, C.c_int, vp, vp]),
     "step_tc_image_to_rows": (C.c_int, [vp, ll, C.c_int, f32p, vp]),

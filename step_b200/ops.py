@@ -84,15 +84,51 @@ def ts_encoder_forward(series: Tensor, patch_w: Tensor, patch_b: Tensor, pos: Te
     return hidden
 
 
+def ts_embed(series: Tensor, patch_w: Tensor, patch_b: Tensor, pos: Tensor, drop_p: float = 0.0, seed: int = 0) -> Tensor:
+    """Patch + positional embedding (x sqrt(96), positional dropout): series [B, P*12, N] view -> tokens [B*N*P, 96]."""
+    if not series.is_cuda or series.dtype != torch.float32:
+        raise _lib.StepB200Error("ts_embed: series must be a float32 CUDA tensor")
+    B, T, N = series.shape
+    if T % 12 != 0:
+        raise _lib.StepB200Error(f"ts_embed: history length {T} is not a multiple of the patch size 12")
+    P = T // 12
+    st = _enter(series)
+    x = torch.empty(B * N * P, 96, device=series.device, dtype=torch.float32)
+    pw, pb, ps = _f32(patch_w.reshape(96, 12), "patch_w"), _f32(patch_b, "patch_b"), _f32(pos, "pos")
+    sB, sT, sN = series.stride()
+    check(_L().step_ts_embed_fwd(series.data_ptr(), sB, sT, sN, B, N, P, pw.data_ptr(), pb.data_ptr(), ps.data_ptr(),
+                                 x.data_ptr(), float(drop_p), int(seed) & (2**64 - 1), st), "step_ts_embed_fwd")
+    launch_counter["kernels"] += 1
+    return x
+
+
+def ts_layers(x: Tensor, S: int, P: int, layers: Sequence[Dict[str, Tensor]], norm_w: Optional[Tensor] = None,
+              norm_b: Optional[Tensor] = None, drop_p: float = 0.0, seed: int = 0) -> Tensor:
+    """Transformer layer stack (+ optional final LayerNorm) on tokens x [S*P, 96] (already x sqrt(96)); returns a new tensor."""
+    x = _f32(x, "x").clone()
+    if x.shape != (S * P, 96):
+        raise _lib.StepB200Error(f"ts_layers: x must be [{S * P}, 96], got {tuple(x.shape)}")
+    st = _enter(x)
+    ws_bytes = _L().step_ts_encoder_workspace_bytes(S, P)
+    ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+    arr, keep = ts_layer_struct(layers)
+    nw = _f32(norm_w, "norm_w") if norm_w is not None else None
+    nb = _f32(norm_b, "norm_b") if norm_b is not None else None
+    check(_L().step_ts_layers_fwd(x.data_ptr(), S, P, arr, len(layers), _p(nw), _p(nb), ws.data_ptr(), ws_bytes,
+                                  float(drop_p), int(seed) & (2**64 - 1), st), "step_ts_layers_fwd")
+    launch_counter["kernels"] += len(layers) * 5
+    return x
+
+
 def linear(a: Tensor, w: Tensor, bias: Optional[Tensor], epilogue: int = 0, residual: Optional[Tensor] = None,
-           ln_w: Optional[Tensor] = None, ln_b: Optional[Tensor] = None) -> Tensor:
+           ln_w: Optional[Tensor] = None, ln_b: Optional[Tensor] = None, drop_p: float = 0.0, seed: int = 0) -> Tensor:
     a = _f32(a, "a"); w = _f32(w, "w")
     M, K = a.shape
     Nout = w.shape[0]
     st = _enter(a)
     c = torch.empty(M, Nout, device=a.device, dtype=torch.float32)
     check(_L().step_linear_f32(a.data_ptr(), w.data_ptr(), _p(bias), c.data_ptr(), M, K, Nout, epilogue, _p(residual),
-                               _p(ln_w), _p(ln_b), 0.0, 0, 0, st), "step_linear_f32")
+                               _p(ln_w), _p(ln_b), float(drop_p), int(seed) & (2**64 - 1), 7, st), "step_linear_f32")
     launch_counter["kernels"] += 1
     return c
 

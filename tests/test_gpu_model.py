@@ -197,3 +197,31 @@ def test_runner_contract_train_iters(tmp_path):
     assert torch.isfinite(loss)
     assert runner.model.backend.start_conv.weight.grad is not None
     assert all(p.grad is None for p in runner.model.tsformer.parameters())
+
+
+@pytest.mark.gpu
+def test_tsformer_pretrain_forward_matches_reference_golden():
+    """TSFormer(mode="pre-train") forward (BASELINE configs[0] / SURVEY section 8 row P1) on the fp32 kernels vs the
+    reference's own output: same mask draw (random.seed), MAE <= 1e-4 on the reconstruction, labels bit-exact."""
+    import random
+    from step.step_arch import TSFormer
+    fx = torch.load(os.path.join(GOLDEN, "tsformer_pretrain_METR-LA.pt"), weights_only=False)
+    model = TSFormer(patch_size=12, in_channel=1, embed_dim=96, num_heads=4, mlp_ratio=4, dropout=0.1,
+                     num_token=float(fx["P"]), mask_ratio=0.75, encoder_depth=4, decoder_depth=1, mode="pre-train")
+    model.load_state_dict(torch.load(os.path.join(GOLDEN, "tsformer_METR-LA_state.pt")), strict=True)
+    model = model.to(DEV).eval()
+    g = torch.Generator().manual_seed(fx["input_seed"])
+    history = torch.randn(fx["B"], fx["P"] * 12, fx["N"], 1, generator=g)
+    random.seed(fx["random_seed"])
+    rec, label = model(history_data=history.to(DEV), future_data=None, batch_seen=0, epoch=1)
+    assert model.mask.masked_tokens == fx["masked"]
+    assert tuple(rec.shape) == tuple(fx["recon"].shape)
+    err = (rec.cpu() - fx["recon"]).abs()
+    print(f"pre-train forward: recon MAE {err.mean().item():.2e} max {err.max().item():.2e}")
+    assert err.mean().item() <= 1e-4 and err.max().item() < 1e-3
+    assert torch.equal(label.cpu(), fx["label"])
+    # train(): dropout live (0.1) - finite, same shape, differs from the deterministic pass
+    model.train()
+    model.mask.fixed = (fx["unmasked"], fx["masked"])
+    rec2, _ = model(history_data=history.to(DEV))
+    assert torch.isfinite(rec2).all() and (rec2 - rec).abs().max().item() > 1e-3

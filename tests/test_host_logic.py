@@ -47,3 +47,17 @@ def test_step_loss_matches_oracle():
     a = step_loss(pred, real, theta, prior, 0.5, null_val=0.0)
     b = O.step_loss(pred, real, theta, prior, 0.5, null_val=0.0)
     assert abs(a.item() - b.item()) < 1e-6
+
+
+def test_mask_generator_reproduces_the_reference_draw():
+    """MaskGenerator (reference tsformer/mask.py:15-24) consumes Python's ``random`` exactly like the reference: with
+    the seed the golden fixture was generated under, it returns the mask the reference drew."""
+    import random
+    from step.step_arch.tsformer.tsformer import MaskGenerator
+    fx = torch.load(os.path.join(GOLDEN, "tsformer_pretrain_METR-LA.pt"), weights_only=False)
+    mg = MaskGenerator(float(fx["P"]), 0.75)          # num_token arrives as a float in the shipped configs
+    random.seed(fx["random_seed"])
+    unmasked, masked = mg()
+    assert unmasked == fx["unmasked"] and masked == fx["masked"]
+    mg.fixed = ([1, 2], [0, 3])
+    assert mg() == ([1, 2], [0, 3])
