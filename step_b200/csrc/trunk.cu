@@ -8,6 +8,7 @@
 // it is recomputed inside every consumer (statistics pass, conv2 forward, conv2 backward, conv1 backward) from the
 // 20 MB input series, and BatchNorm1 is an affine applied on the fly.  Stored tensors: y2 (pre-BN2, needed for the
 // ReLU mask and x-hat in backward) and y2n (the Linear's input).
+#include <math.h>
 #include "common.cuh"
 
 namespace stepk {
@@ -263,44 +264,70 @@ __global__ void __launch_bounds__(256) trunk_conv2_bwd_kernel(const float *__res
   float *sc1 = b1s + C1, *sh1 = sc1 + C1;    // 8 + 8
   float *cf2 = sh1 + C1;                     // 5 * 16 BN2 backward coefficients
   float *red = cf2 + 5 * C2;                 // 32
+  float *mean1 = red + 32, *rstd1 = mean1 + C1;   // BN1 mean / rstd for x-hat
+  float *rawy = rstd1 + C1;                  // [16][DPS] y2 of the NEXT tile, landed by cp.async during this tile's math
+  float *rawd = rawy + C2 * DPS;             // [16][DPS] dy2n, same
   const int n = blockIdx.y, tid = threadIdx.x;
   const float *xr = x + (size_t)n * d.L0;
   for (int i = tid; i < C2 * C1 * TK; i += 256) {
     const int co = i / (C1 * TK), r = i - co * (C1 * TK), ci = r / TK, k = r - ci * TK;
     w2t[(co * TK + k) * C1 + ci] = w2[i];
   }
+  if (tid < C1) { mean1[tid] = bn1[tid]; rstd1[tid] = 1.0f / sqrtf(bn1[C1 + tid] + eps); }
   if (tid < C1 * TK) w1s[tid] = w1[tid];
   if (tid < C1) { b1s[tid] = b1[tid]; sc1[tid] = bn1[2 * C1 + tid]; sh1[tid] = bn1[3 * C1 + tid]; }
   if (tid < 5 * C2) cf2[tid] = coef2[tid];
-  float accw[C2], accb = 0.f, s1acc[C1], s2acc[C1];
+  // warps 0-3 own d(y1n) (two adjacent positions per thread), warps 4-7 own dW2/db2 (lane = (ci, 4 output channels),
+  // all 10 taps, one 64-position segment per warp): both halves do 2560 FMAs per thread and tile, and the register
+  // tiling keeps shared-memory traffic at ~0.1 wavefronts per FFMA (it was the bound at 0.7).
+  const bool is_dx = tid < 128;
+  const int wl = tid & 31, wci = wl >> 2, wcog = wl & 3, wseg = (tid >> 5) - 4;
+  float accw[TK][4], accb[4], s1acc[C1], s2acc[C1];
 #pragma unroll
-  for (int co = 0; co < C2; ++co) accw[co] = 0.f;
+  for (int k = 0; k < TK; ++k)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) accw[k][c] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) accb[c] = 0.f;
 #pragma unroll
   for (int ci = 0; ci < C1; ++ci) { s1acc[ci] = 0.f; s2acc[ci] = 0.f; }
-  float mean1[C1], rstd1[C1];
-#pragma unroll
-  for (int ci = 0; ci < C1; ++ci) { mean1[ci] = bn1[ci]; rstd1[ci] = 1.0f / sqrtf(bn1[C1 + ci] + eps); }
   const int ntiles = (d.L1 + TLB - 1) / TLB;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  // raw y2 / dy2n of one tile -> shared memory with 4-byte cp.async (rows start at t0 - 9: no 16-byte alignment for
+  // bulk copies); positions outside [0, L2) are zero-filled, which makes dpre2 zero there.
+  auto prefetch_tile = [&](int tile) {
     const int t0 = tile * TLB;
-    __syncthreads();
-    for (int i = tid; i < Y1WB + HALO; i += 256) xs[i] = (t0 + i < d.L0) ? xr[t0 + i] : 0.f;
-    // dpre2 tile: position j <-> l = t0 - 9 + j
     for (int idx = tid; idx < C2 * DPW; idx += 256) {
       const int co = idx / DPW, j = idx - co * DPW, l = t0 - HALO + j;
+      const bool ok = l >= 0 && l < d.L2;
+      const size_t off = ((size_t)n * C2 + co) * d.L2 + (ok ? l : 0);
+      const uint32_t nbytes = ok ? 4u : 0u;
+      const uint32_t sy = (uint32_t)__cvta_generic_to_shared(rawy + co * DPS + j);
+      const uint32_t sd = (uint32_t)__cvta_generic_to_shared(rawd + co * DPS + j);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sy), "l"(y2 + off), "r"(nbytes) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sd), "l"(dy2n + off), "r"(nbytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if ((int)blockIdx.x < ntiles) prefetch_tile(blockIdx.x);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int t0 = tile * TLB;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    for (int i = tid; i < Y1WB + HALO; i += 256) xs[i] = (t0 + i < d.L0) ? xr[t0 + i] : 0.f;
+    // dpre2 tile: position j <-> l = t0 - 9 + j (zero-filled raw values give v = 0 outside [0, L2))
+    for (int idx = tid; idx < C2 * DPW; idx += 256) {
+      const int co = idx / DPW, j = idx - co * DPW;
+      const float yv = rawy[co * DPS + j];
       float v = 0.f;
-      if (l >= 0 && l < d.L2) {
-        const size_t off = ((size_t)n * C2 + co) * d.L2 + l;
-        const float yv = y2[off];
-        if (yv > 0.f) {
-          const float xhat = (yv - cf2[3 * C2 + co]) * cf2[4 * C2 + co];
-          v = cf2[co] * (dy2n[off] - cf2[C2 + co] - xhat * cf2[2 * C2 + co]);
-        }
+      if (yv > 0.f) {
+        const float xhat = (yv - cf2[3 * C2 + co]) * cf2[4 * C2 + co];
+        v = cf2[co] * (rawd[co * DPS + j] - cf2[C2 + co] - xhat * cf2[2 * C2 + co]);
       }
       dp_cl[co * DPS + j] = v;
       dp_lc[j * C2 + co] = v;
     }
     __syncthreads();
+    if (tile + (int)gridDim.x < ntiles) prefetch_tile(tile + gridDim.x);     // overlaps with everything below
     // y1 (raw for x-hat on the own range, normalised everywhere) with ONE conv1 evaluation per element
     for (int idx = tid; idx < C1 * Y1WB; idx += 256) {
       const int c = idx / Y1WB, j = idx - c * Y1WB;
@@ -317,71 +344,108 @@ __global__ void __launch_bounds__(256) trunk_conv2_bwd_kernel(const float *__res
     }
     __syncthreads();
 
-    // ---- d(y1n)[ci][l'] = sum_co sum_k w2[co][ci][k] dpre2[co][l'-k];  l' = t0 + p, dpre2 index j = p - k + 9 ----
-    {
-      float acc[C1];
+    if (is_dx) {
+      // ---- d(y1n)[ci][l'] = sum_co sum_k w2[co][ci][k] dpre2[co][l'-k];  l' = t0 + p, p in {p0, p0 + 1} ----
+      float acc0[C1], acc1[C1];
 #pragma unroll
-      for (int ci = 0; ci < C1; ++ci) acc[ci] = 0.f;
-      const int p0 = tid;
+      for (int ci = 0; ci < C1; ++ci) { acc0[ci] = 0.f; acc1[ci] = 0.f; }
+      const int p0 = 2 * tid;
 #pragma unroll 1
       for (int co = 0; co < C2; ++co) {
-        const float *dr = dp_cl + co * DPS + HALO;
+        // v[i] = dpre2[co] at own-range position p0 - 9 + i (smem index p0 + i: HALO == 9 keeps it 8-byte aligned)
+        const float *dr = dp_cl + co * DPS + p0;
+        float v[TK + 2];
+#pragma unroll
+        for (int i = 0; i < TK; i += 2) {
+          const float2 t = *reinterpret_cast<const float2 *>(dr + i);
+          v[i] = t.x; v[i + 1] = t.y;
+        }
+        v[TK] = dr[TK];
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
-          const float a0 = dr[p0 - k];
+          const float a0 = v[HALO - k], a1 = v[HALO + 1 - k];
           const float4 *w = reinterpret_cast<const float4 *>(w2t + (co * TK + k) * C1);
           const float4 wa = w[0], wb = w[1];
-          acc[0] = fmaf(wa.x, a0, acc[0]); acc[1] = fmaf(wa.y, a0, acc[1]);
-          acc[2] = fmaf(wa.z, a0, acc[2]); acc[3] = fmaf(wa.w, a0, acc[3]);
-          acc[4] = fmaf(wb.x, a0, acc[4]); acc[5] = fmaf(wb.y, a0, acc[5]);
-          acc[6] = fmaf(wb.z, a0, acc[6]); acc[7] = fmaf(wb.w, a0, acc[7]);
+          acc0[0] = fmaf(wa.x, a0, acc0[0]); acc0[1] = fmaf(wa.y, a0, acc0[1]);
+          acc0[2] = fmaf(wa.z, a0, acc0[2]); acc0[3] = fmaf(wa.w, a0, acc0[3]);
+          acc0[4] = fmaf(wb.x, a0, acc0[4]); acc0[5] = fmaf(wb.y, a0, acc0[5]);
+          acc0[6] = fmaf(wb.z, a0, acc0[6]); acc0[7] = fmaf(wb.w, a0, acc0[7]);
+          acc1[0] = fmaf(wa.x, a1, acc1[0]); acc1[1] = fmaf(wa.y, a1, acc1[1]);
+          acc1[2] = fmaf(wa.z, a1, acc1[2]); acc1[3] = fmaf(wa.w, a1, acc1[3]);
+          acc1[4] = fmaf(wb.x, a1, acc1[4]); acc1[5] = fmaf(wb.y, a1, acc1[5]);
+          acc1[6] = fmaf(wb.z, a1, acc1[6]); acc1[7] = fmaf(wb.w, a1, acc1[7]);
         }
       }
+      float *o = dy1n + (size_t)n * C1 * d.L1 + t0;
       if (t0 + p0 < d.L1) {
-        float *o = dy1n + (size_t)n * C1 * d.L1 + t0;
 #pragma unroll
         for (int ci = 0; ci < C1; ++ci) {
-          o[(size_t)ci * d.L1 + p0] = acc[ci];
-          s1acc[ci] += acc[ci];
-          s2acc[ci] = fmaf(acc[ci], (y1r[ci * TLB + p0] - mean1[ci]) * rstd1[ci], s2acc[ci]);
+          o[(size_t)ci * d.L1 + p0] = acc0[ci];
+          s1acc[ci] += acc0[ci];
+          s2acc[ci] = fmaf(acc0[ci], (y1r[ci * TLB + p0] - mean1[ci]) * rstd1[ci], s2acc[ci]);
         }
       }
-    }
-
-    // ---- dW2[co][ci][k] += sum_{l in own range} dpre2[co][l] y1n[ci][l+k];  own l = t0 + p, p in [0,256) ----
-    // thread = (ci, k) pair x one of 3 position segments, 16 output channels in registers
-    if (tid < 240) {
-      const int pair = tid % 80, seg = tid / 80, ci = pair / TK, k = pair - ci * TK;
-      const int pbeg = seg * 86, pend = min(TLB, pbeg + 86);
-      for (int p = pbeg; p < pend; ++p) {
-        const float yv = y1s[ci * Y1SB + p + k];
-        const float4 *dpp = reinterpret_cast<const float4 *>(dp_lc + (p + HALO) * C2);
+      if (t0 + p0 + 1 < d.L1) {
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const float4 g = dpp[c4];
-          accw[4 * c4] = fmaf(g.x, yv, accw[4 * c4]); accw[4 * c4 + 1] = fmaf(g.y, yv, accw[4 * c4 + 1]);
-          accw[4 * c4 + 2] = fmaf(g.z, yv, accw[4 * c4 + 2]); accw[4 * c4 + 3] = fmaf(g.w, yv, accw[4 * c4 + 3]);
+        for (int ci = 0; ci < C1; ++ci) {
+          o[(size_t)ci * d.L1 + p0 + 1] = acc1[ci];
+          s1acc[ci] += acc1[ci];
+          s2acc[ci] = fmaf(acc1[ci], (y1r[ci * TLB + p0 + 1] - mean1[ci]) * rstd1[ci], s2acc[ci]);
         }
       }
-    }
-    // ---- db2[co] partial over own range: thread = (co, 16-way position split) ----
-    {
-      const int co = tid >> 4, part = tid & 15;
-      for (int p = part; p < TLB; p += 16) accb += dp_cl[co * DPS + HALO + p];
+    } else {
+      // ---- dW2[co][ci][k] += sum_p dpre2[co][p] y1n[ci][p + k] over this warp's 64 positions; db2 on the ci == 0 lanes.
+      // The 10-tap window of y1n slides through registers (rotating static indices, one new load per position).
+      const int pbeg = wseg * 64;
+      const float *yrow = y1s + wci * Y1SB + pbeg;
+      const float *dprow = dp_lc + (size_t)(pbeg + HALO) * C2 + 4 * wcog;
+      float y[TK];
+#pragma unroll
+      for (int k = 0; k < TK; ++k) y[k] = yrow[k];
+      auto step10 = [&](int base, int count) {
+#pragma unroll
+        for (int i = 0; i < TK; ++i) {
+          if (i < count) {
+            const float4 g = *reinterpret_cast<const float4 *>(dprow + (size_t)(base + i) * C2);
+#pragma unroll
+            for (int k = 0; k < TK; ++k) {
+              const float yv = y[(i + k) % TK];
+              accw[k][0] = fmaf(g.x, yv, accw[k][0]); accw[k][1] = fmaf(g.y, yv, accw[k][1]);
+              accw[k][2] = fmaf(g.z, yv, accw[k][2]); accw[k][3] = fmaf(g.w, yv, accw[k][3]);
+            }
+            if (wci == 0) { accb[0] += g.x; accb[1] += g.y; accb[2] += g.z; accb[3] += g.w; }
+            y[i] = yrow[base + i + TK];
+          }
+        }
+      };
+#pragma unroll 1
+      for (int base = 0; base < 60; base += TK) step10(base, TK);
+      step10(60, 4);
     }
   }  // tile loop
 
-  if (tid < 240) {
-    const int pair = tid % 80, ci = pair / TK, k = pair - ci * TK;
+  // flush: the four dW2 warps combine through shared memory (the tile buffers are free now), one atomic per entry and CTA
+  __syncthreads();
+  float *wred = sm;                          // [4 warps][C2*C1*TK] + [4][C2]
+  if (!is_dx) {
+    float *wr = wred + wseg * (C2 * C1 * TK);
 #pragma unroll
-    for (int co = 0; co < C2; ++co) atomicAdd(dw2 + (co * C1 + ci) * TK + k, accw[co]);
-  }
-  {
-    const int co = tid >> 4, part = tid & 15;
+    for (int k = 0; k < TK; ++k)
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) accb += __shfl_xor_sync(0xffffffffu, accb, o);
-    if (part == 0) atomicAdd(db2 + co, accb);
+      for (int c = 0; c < 4; ++c) wr[((4 * wcog + c) * C1 + wci) * TK + k] = accw[k][c];
+    if (wci == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) wred[4 * C2 * C1 * TK + wseg * C2 + 4 * wcog + c] = accb[c];
+    }
   }
+  __syncthreads();
+  for (int i = tid; i < C2 * C1 * TK; i += 256)
+    atomicAdd(dw2 + i, (wred[i] + wred[C2 * C1 * TK + i]) + (wred[2 * C2 * C1 * TK + i] + wred[3 * C2 * C1 * TK + i]));
+  if (tid < C2) {
+    const float *bb = wred + 4 * C2 * C1 * TK;
+    atomicAdd(db2 + tid, (bb[tid] + bb[C2 + tid]) + (bb[2 * C2 + tid] + bb[3 * C2 + tid]));
+  }
+  __syncthreads();
 #pragma unroll
   for (int ci = 0; ci < C1; ++ci) {
     block_reduce_add_double(s1acc[ci], sums1 + ci, red);
@@ -447,7 +511,7 @@ __global__ void __launch_bounds__(256) trunk_conv1_bwd_kernel(const float *__res
 
 static size_t conv2_bwd_smem() {
   size_t f = (size_t)C2 * DPS + (size_t)DPW * C2 + (size_t)C1 * Y1SB + (size_t)C1 * TLB + (Y1WB + HALO + 2 + 3) / 4 * 4 +
-             C2 * TK * C1 + C1 * TK + 3 * C1 + 5 * C2 + 32;
+             C2 * TK * C1 + C1 * TK + 3 * C1 + 5 * C2 + 32 + 2 * C1 + 2 * (size_t)C2 * DPS;
   return f * sizeof(float);
 }
 
@@ -511,8 +575,27 @@ extern "C" int step_dgl_conv_bwd(const float *dy2n, const float *x, int N, int L
   STEP_LAUNCH_CHECK("trunk_bn_bwd_finalize_kernel");
   int rc = allow_smem(trunk_conv2_bwd_kernel, conv2_bwd_smem());
   if (rc) return rc;
-  trunk_conv2_bwd_kernel<<<dim3(6, N), 256, conv2_bwd_smem(), st>>>(x, d, w1, b1, bn1_stats, eps, w2, dy2n, y2,
-                                                                                       coef2, dy1n_scratch, dw2, db2, sums);
+  // CTAs per node: fill whole waves of the resident slots (tiles per CTA stay >= ~8 so the final flush is amortised)
+  int dev = 0, sms = 148, per_sm = 2;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trunk_conv2_bwd_kernel, 256, conv2_bwd_smem());
+  if (per_sm < 1) per_sm = 1;
+  const int ntiles = (d.L1 + TLB - 1) / TLB;
+  int gx = 6;
+  {
+    const double slots = (double)sms * per_sm;
+    double best = -1.0;
+    const int gmax = ntiles / 8 > 4 ? (ntiles / 8 < 12 ? ntiles / 8 : 12) : 4;
+    for (int c = 4; c <= gmax; ++c) {
+      const double waves = (double)N * c / slots;
+      const double per_cta = (double)((ntiles + c - 1) / c) * c / ntiles;       // tile imbalance between CTAs
+      const double eff = waves / ceil(waves) / per_cta;
+      if (eff > best + 1e-9) { best = eff; gx = c; }
+    }
+  }
+  trunk_conv2_bwd_kernel<<<dim3(gx, N), 256, conv2_bwd_smem(), st>>>(x, d, w1, b1, bn1_stats, eps, w2, dy2n, y2,
+                                                                    coef2, dy1n_scratch, dw2, db2, sums);
   STEP_LAUNCH_CHECK("trunk_conv2_bwd_kernel");
   trunk_bn_bwd_finalize_kernel<<<1, 32, 0, st>>>(sums, (double)N * d.L1, C1, g1, bn1_stats, eps, coef1, dg1, dbe1);
   STEP_LAUNCH_CHECK("trunk_bn_bwd_finalize_kernel");
