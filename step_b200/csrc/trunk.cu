@@ -119,19 +119,30 @@ __device__ __forceinline__ void compute_y1_tile(const float *xs /* x at [p0, p0+
 constexpr int Y1W = TL + HALO;          // 521 y1 positions per tile
 constexpr int Y1S = Y1W + 3;            // smem row stride
 
-__global__ void __launch_bounds__(256) trunk_conv2_fwd_kernel(const float *__restrict__ x, TrunkDims d,
+__global__ void __launch_bounds__(256, 3) trunk_conv2_fwd_kernel(const float *__restrict__ x, TrunkDims d,
                                                               const float *__restrict__ w1, const float *__restrict__ b1,
                                                               const float *__restrict__ bn1 /*[4][8]*/,
                                                               const float *__restrict__ w2, const float *__restrict__ b2,
                                                               float *__restrict__ y2, double *__restrict__ sums2 /*[2][16] or null*/) {
-  __shared__ float xs[Y1W + HALO + 2];
+  __shared__ float xs2[2][Y1W + HALO + 3];   // double-buffered series tile (cp.async prefetch of the next tile)
   __shared__ float y1s[C1 * Y1S];
   __shared__ __align__(16) float w2s[C1 * TK * C2];   // [ci][k][co]
   __shared__ float w1s[C1 * TK], b1s[C1], sc1[C1], sh1[C1], b2s[C2];
   __shared__ float red[32];
-  const int n = blockIdx.y, t0 = blockIdx.x * TL, tid = threadIdx.x;
+  const int n = blockIdx.y, tid = threadIdx.x;
   const float *xr = x + (size_t)n * d.L0;
-  for (int i = tid; i < Y1W + HALO; i += 256) xs[i] = (t0 + i < d.L0) ? xr[t0 + i] : 0.f;
+  const int ntiles = (d.L2 + TL - 1) / TL;
+  auto prefetch_x = [&](int tile, int buf) {
+    const int t0 = tile * TL;
+    for (int i = tid; i < Y1W + HALO; i += 256) {
+      const bool ok = t0 + i < d.L0;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&xs2[buf][i]);
+      const uint32_t nbytes = ok ? 4u : 0u;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(xr + (ok ? t0 + i : 0)), "r"(nbytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if ((int)blockIdx.x < ntiles) prefetch_x(blockIdx.x, 0);
   for (int i = tid; i < C2 * C1 * TK; i += 256) {
     const int co = i / (C1 * TK), r = i - co * (C1 * TK), ci = r / TK, k = r - ci * TK;
     w2s[(ci * TK + k) * C2 + co] = w2[i];
@@ -139,43 +150,49 @@ __global__ void __launch_bounds__(256) trunk_conv2_fwd_kernel(const float *__res
   if (tid < C1 * TK) w1s[tid] = w1[tid];
   if (tid < C1) { b1s[tid] = b1[tid]; sc1[tid] = bn1[2 * C1 + tid]; sh1[tid] = bn1[3 * C1 + tid]; }
   if (tid < C2) b2s[tid] = b2[tid];
-  __syncthreads();
-  compute_y1_tile(xs, w1s, b1s, t0, Y1W, d.L1, y1s, Y1S, sc1, sh1);
-  __syncthreads();
+  float s[C2], q[C2];          // BN2 batch-sum partials, kept across this CTA's tiles
+#pragma unroll
+  for (int co = 0; co < C2; ++co) { s[co] = 0.f; q[co] = 0.f; }
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    const int t0 = tile * TL;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                       // series tile landed; previous tile's y1s reads are done
+    if (tile + (int)gridDim.x < ntiles) prefetch_x(tile + gridDim.x, buf ^ 1);
+    compute_y1_tile(xs2[buf], w1s, b1s, t0, Y1W, d.L1, y1s, Y1S, sc1, sh1);
+    __syncthreads();
 
-  float acc[2][C2];
+    float acc[2][C2];
 #pragma unroll
-  for (int j = 0; j < 2; ++j)
+    for (int j = 0; j < 2; ++j)
 #pragma unroll
-    for (int co = 0; co < C2; ++co) acc[j][co] = b2s[co];
-  const int p0 = tid, p1 = tid + 256;
+      for (int co = 0; co < C2; ++co) acc[j][co] = b2s[co];
+    const int p0 = tid, p1 = tid + 256;
 #pragma unroll 1
-  for (int ci = 0; ci < C1; ++ci) {
-    const float *yr = y1s + ci * Y1S;
+    for (int ci = 0; ci < C1; ++ci) {
+      const float *yr = y1s + ci * Y1S;
 #pragma unroll
-    for (int k = 0; k < TK; ++k) {
-      const float a0 = yr[p0 + k], a1 = yr[p1 + k];
-      const float4 *w = reinterpret_cast<const float4 *>(w2s + (ci * TK + k) * C2);
+      for (int k = 0; k < TK; ++k) {
+        const float a0 = yr[p0 + k], a1 = yr[p1 + k];
+        const float4 *w = reinterpret_cast<const float4 *>(w2s + (ci * TK + k) * C2);
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const float4 ww = w[c4];
-        acc[0][4 * c4] = fmaf(ww.x, a0, acc[0][4 * c4]); acc[0][4 * c4 + 1] = fmaf(ww.y, a0, acc[0][4 * c4 + 1]);
-        acc[0][4 * c4 + 2] = fmaf(ww.z, a0, acc[0][4 * c4 + 2]); acc[0][4 * c4 + 3] = fmaf(ww.w, a0, acc[0][4 * c4 + 3]);
-        acc[1][4 * c4] = fmaf(ww.x, a1, acc[1][4 * c4]); acc[1][4 * c4 + 1] = fmaf(ww.y, a1, acc[1][4 * c4 + 1]);
-        acc[1][4 * c4 + 2] = fmaf(ww.z, a1, acc[1][4 * c4 + 2]); acc[1][4 * c4 + 3] = fmaf(ww.w, a1, acc[1][4 * c4 + 3]);
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 ww = w[c4];
+          acc[0][4 * c4] = fmaf(ww.x, a0, acc[0][4 * c4]); acc[0][4 * c4 + 1] = fmaf(ww.y, a0, acc[0][4 * c4 + 1]);
+          acc[0][4 * c4 + 2] = fmaf(ww.z, a0, acc[0][4 * c4 + 2]); acc[0][4 * c4 + 3] = fmaf(ww.w, a0, acc[0][4 * c4 + 3]);
+          acc[1][4 * c4] = fmaf(ww.x, a1, acc[1][4 * c4]); acc[1][4 * c4 + 1] = fmaf(ww.y, a1, acc[1][4 * c4 + 1]);
+          acc[1][4 * c4 + 2] = fmaf(ww.z, a1, acc[1][4 * c4 + 2]); acc[1][4 * c4 + 3] = fmaf(ww.w, a1, acc[1][4 * c4 + 3]);
+        }
       }
     }
-  }
-  float s[C2], q[C2];
-  const bool ok0 = t0 + p0 < d.L2, ok1 = t0 + p1 < d.L2;
-  float *yo = y2 + (size_t)n * C2 * d.L2 + t0;
+    const bool ok0 = t0 + p0 < d.L2, ok1 = t0 + p1 < d.L2;
+    float *yo = y2 + (size_t)n * C2 * d.L2 + t0;
 #pragma unroll
-  for (int co = 0; co < C2; ++co) {
-    const float v0 = fmaxf(acc[0][co], 0.f), v1 = fmaxf(acc[1][co], 0.f);
-    if (ok0) yo[(size_t)co * d.L2 + p0] = v0;
-    if (ok1) yo[(size_t)co * d.L2 + p1] = v1;
-    s[co] = (ok0 ? v0 : 0.f) + (ok1 ? v1 : 0.f);
-    q[co] = (ok0 ? v0 * v0 : 0.f) + (ok1 ? v1 * v1 : 0.f);
+    for (int co = 0; co < C2; ++co) {
+      const float v0 = fmaxf(acc[0][co], 0.f), v1 = fmaxf(acc[1][co], 0.f);
+      if (ok0) { yo[(size_t)co * d.L2 + p0] = v0; s[co] += v0; q[co] = fmaf(v0, v0, q[co]); }
+      if (ok1) { yo[(size_t)co * d.L2 + p1] = v1; s[co] += v1; q[co] = fmaf(v1, v1, q[co]); }
+    }
   }
   if (sums2 != nullptr) {
 #pragma unroll
@@ -186,13 +203,23 @@ __global__ void __launch_bounds__(256) trunk_conv2_fwd_kernel(const float *__res
   }
 }
 
-// F3: y2n = y2 * scale[c] + shift[c]   ([N][C][L] layout)
-__global__ void trunk_bn_apply_kernel(const float *__restrict__ y, long long total, int C, int L, const float *__restrict__ stats,
-                                      float *__restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = (int)((i / L) % C);
-  out[i] = fmaf(y[i], stats[2 * C + c], stats[3 * C + c]);
+// F3: y2n = y2 * scale[c] + shift[c]   ([N][C][L] layout).  grid (ceil(L/1024), N*C): one (node, channel) row per
+// blockIdx.y, float4 per thread when the rows are 16-byte aligned (L % 4 == 0), scalar otherwise.
+__global__ void __launch_bounds__(256) trunk_bn_apply_kernel(const float *__restrict__ y, int C, int L,
+                                                             const float *__restrict__ stats, float *__restrict__ out) {
+  const int row = blockIdx.y, c = row % C;
+  const float sc = stats[2 * C + c], sh = stats[3 * C + c];
+  const float *yr = y + (size_t)row * L;
+  float *orow = out + (size_t)row * L;
+  if ((L & 3) == 0) {
+    const int i = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i < L) {
+      const float4 v = *reinterpret_cast<const float4 *>(yr + i);
+      *reinterpret_cast<float4 *>(orow + i) = make_float4(fmaf(v.x, sc, sh), fmaf(v.y, sc, sh), fmaf(v.z, sc, sh), fmaf(v.w, sc, sh));
+    }
+  } else {
+    for (int i = blockIdx.x * 1024 + threadIdx.x; i < min(L, (int)(blockIdx.x + 1) * 1024); i += 256) orow[i] = fmaf(yr[i], sc, sh);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -509,6 +536,30 @@ __global__ void __launch_bounds__(256) trunk_conv1_bwd_kernel(const float *__res
   else if (tid < C1 * TK + C1) atomicAdd(db1 + (tid - C1 * TK), accs[tid]);
 }
 
+// CTAs per node for the tile-loop kernels: fill whole waves of the resident CTA slots while keeping at least
+// `min_tiles` tiles per CTA (so per-CTA prologue / final reductions are amortised) and the tile split even.
+template <typename K>
+static int wave_aware_ctas(K kernel, size_t smem, int ntiles, int N, int min_tiles) {
+  int dev = 0, sms = 148, per_sm = 2;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem);
+  if (per_sm < 1) per_sm = 1;
+  const double slots = (double)sms * per_sm;
+  int gmax = ntiles / min_tiles;
+  if (gmax > 12) gmax = 12;
+  if (gmax < 1) gmax = 1;
+  int gx = gmax < 4 ? gmax : 4;
+  double best = -1.0;
+  for (int c = gx; c <= gmax; ++c) {
+    const double waves = (double)N * c / slots;
+    const double per_cta = (double)((ntiles + c - 1) / c) * c / ntiles;       // tile imbalance between CTAs
+    const double eff = waves / ceil(waves) / per_cta;
+    if (eff > best + 1e-9) { best = eff; gx = c; }
+  }
+  return gx;
+}
+
 static size_t conv2_bwd_smem() {
   size_t f = (size_t)C2 * DPS + (size_t)DPW * C2 + (size_t)C1 * Y1SB + (size_t)C1 * TLB + (Y1WB + HALO + 2 + 3) / 4 * 4 +
              C2 * TK * C1 + C1 * TK + 3 * C1 + 5 * C2 + 32 + 2 * C1 + 2 * (size_t)C2 * DPS;
@@ -538,15 +589,15 @@ extern "C" int step_dgl_conv_fwd(const float *x, int N, int L0, const float *w1,
     trunk_bn_finalize_kernel<<<1, 32, 0, st>>>(sums, (double)N * d.L1, C1, g1, be1, eps, bn1_stats);
     STEP_LAUNCH_CHECK("trunk_bn_finalize_kernel");
   }
-  trunk_conv2_fwd_kernel<<<dim3((d.L2 + TL - 1) / TL, N), 256, 0, st>>>(x, d, w1, b1, bn1_stats, w2, b2, y2,
-                                                                        training ? sums + 16 : nullptr);
+  trunk_conv2_fwd_kernel<<<dim3(wave_aware_ctas(trunk_conv2_fwd_kernel, 0, (d.L2 + TL - 1) / TL, N, 4), N), 256, 0, st>>>(
+      x, d, w1, b1, bn1_stats, w2, b2, y2, training ? sums + 16 : nullptr);
   STEP_LAUNCH_CHECK("trunk_conv2_fwd_kernel");
   if (training) {
     trunk_bn_finalize_kernel<<<1, 32, 0, st>>>(sums + 16, (double)N * d.L2, C2, g2, be2, eps, bn2_stats);
     STEP_LAUNCH_CHECK("trunk_bn_finalize_kernel");
   }
   const long long total = (long long)N * C2 * d.L2;
-  trunk_bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(y2, total, C2, d.L2, bn2_stats, y2n);
+  trunk_bn_apply_kernel<<<dim3((d.L2 + 1023) / 1024, N * C2), 256, 0, st>>>(y2, C2, d.L2, bn2_stats, y2n);
   return check_launch("trunk_bn_apply_kernel");
 }
 
@@ -575,25 +626,7 @@ extern "C" int step_dgl_conv_bwd(const float *dy2n, const float *x, int N, int L
   STEP_LAUNCH_CHECK("trunk_bn_bwd_finalize_kernel");
   int rc = allow_smem(trunk_conv2_bwd_kernel, conv2_bwd_smem());
   if (rc) return rc;
-  // CTAs per node: fill whole waves of the resident slots (tiles per CTA stay >= ~8 so the final flush is amortised)
-  int dev = 0, sms = 148, per_sm = 2;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trunk_conv2_bwd_kernel, 256, conv2_bwd_smem());
-  if (per_sm < 1) per_sm = 1;
-  const int ntiles = (d.L1 + TLB - 1) / TLB;
-  int gx = 6;
-  {
-    const double slots = (double)sms * per_sm;
-    double best = -1.0;
-    const int gmax = ntiles / 8 > 4 ? (ntiles / 8 < 12 ? ntiles / 8 : 12) : 4;
-    for (int c = 4; c <= gmax; ++c) {
-      const double waves = (double)N * c / slots;
-      const double per_cta = (double)((ntiles + c - 1) / c) * c / ntiles;       // tile imbalance between CTAs
-      const double eff = waves / ceil(waves) / per_cta;
-      if (eff > best + 1e-9) { best = eff; gx = c; }
-    }
-  }
+  const int gx = wave_aware_ctas(trunk_conv2_bwd_kernel, conv2_bwd_smem(), (d.L1 + TLB - 1) / TLB, N, 8);
   trunk_conv2_bwd_kernel<<<dim3(gx, N), 256, conv2_bwd_smem(), st>>>(x, d, w1, b1, bn1_stats, eps, w2, dy2n, y2,
                                                                     coef2, dy1n_scratch, dw2, db2, sums);
   STEP_LAUNCH_CHECK("trunk_conv2_bwd_kernel");
