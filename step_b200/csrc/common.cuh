@@ -100,4 +100,13 @@ __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
   return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
 }
 
+
+// Packed fp32 FMA (Blackwell FFMA2, PTX fma.rn.f32x2): (c0, c1) += (a0, a1) * (b0, b1) in one issue slot.
+__device__ __forceinline__ void ffma2(float &c0, float &c1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(c0), "+f"(c1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 }  // namespace stepk

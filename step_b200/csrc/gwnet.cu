@@ -106,14 +106,14 @@ __device__ __forceinline__ void matvec_chunks(const float *W, const float (&x)[G
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float4 *w = reinterpret_cast<const float4 *>(W + (4 * cg + j) * GC);
-      float a = 0.f;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // packed FFMA2: even / odd input channels, two chains
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) {
         const float4 ww = w[c4];
-        a = fmaf(ww.x, x[4 * c4], a); a = fmaf(ww.y, x[4 * c4 + 1], a);
-        a = fmaf(ww.z, x[4 * c4 + 2], a); a = fmaf(ww.w, x[4 * c4 + 3], a);
+        ffma2(a0, a1, ww.x, ww.y, x[4 * c4], x[4 * c4 + 1]);
+        ffma2(a2, a3, ww.z, ww.w, x[4 * c4 + 2], x[4 * c4 + 3]);
       }
-      o[j] = a;
+      o[j] = (a0 + a1) + (a2 + a3);
     }
     f(cg, make_float4(o[0], o[1], o[2], o[3]));
   }
@@ -127,10 +127,41 @@ __device__ __forceinline__ void matvec_t_acc(const float *W, const float *xp, fl
 #pragma unroll
     for (int c4 = 0; c4 < 8; ++c4) {
       const float4 ww = w[c4];
-      out[4 * c4] = fmaf(ww.x, xv, out[4 * c4]); out[4 * c4 + 1] = fmaf(ww.y, xv, out[4 * c4 + 1]);
-      out[4 * c4 + 2] = fmaf(ww.z, xv, out[4 * c4 + 2]); out[4 * c4 + 3] = fmaf(ww.w, xv, out[4 * c4 + 3]);
+      ffma2(out[4 * c4], out[4 * c4 + 1], ww.x, ww.y, xv, xv);
+      ffma2(out[4 * c4 + 2], out[4 * c4 + 3], ww.z, ww.w, xv, xv);
     }
   }
+}
+// same with the input row already in registers (loaded with 8 independent 16-byte loads, so that one memory
+// round trip is exposed per row instead of one per 4 elements); fully unrolled: every register index is static.
+__device__ __forceinline__ void matvec_t_reg(const float *W, const float (&x)[GC], float (&out)[GC]) {
+#pragma unroll
+  for (int co = 0; co < GC; ++co) {
+    const float4 *w = reinterpret_cast<const float4 *>(W + co * GC);
+    const float xv = x[co];
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 ww = w[c4];
+      ffma2(out[4 * c4], out[4 * c4 + 1], ww.x, ww.y, xv, xv);
+      ffma2(out[4 * c4 + 2], out[4 * c4 + 3], ww.z, ww.w, xv, xv);
+    }
+  }
+}
+// Column sums of a [32 lanes][32] register tile: lane L returns sum over the warp's lanes of v[L] (recursive halving:
+// 31 shuffles instead of 32 full butterflies).  v is destroyed.  All 32 lanes must call.
+__device__ __forceinline__ float warp_colsum32(float (&v)[GC]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = up ? v[i] : v[i + h];
+      const float keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return v[0];
 }
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
@@ -228,7 +259,7 @@ __device__ __forceinline__ void outer_acc(const float *X, const float *U, int N,
     for (int n = 0; n < 64; ++n) {
       const float x = T1[n * GC + co];                 // 4 distinct words per warp: broadcast
       const float4 u = ld4(T2 + n * GC + ci4);         // 8 distinct 16-byte words per warp: conflict-free
-      a0 = fmaf(x, u.x, a0); a1 = fmaf(x, u.y, a1); a2 = fmaf(x, u.z, a2); a3 = fmaf(x, u.w, a3);
+      ffma2(a0, a1, u.x, u.y, x, x); ffma2(a2, a3, u.z, u.w, x, x);
     }
   }
   float *d = dst + (size_t)co * ldd + ci4;
@@ -263,8 +294,7 @@ __device__ __forceinline__ void outer_acc_multi(const float *const (&X)[NB], con
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
         const float x = tiles[(k + 1) * 64 * GC + n * GC + co];
-        acc[k][0] = fmaf(x, u.x, acc[k][0]); acc[k][1] = fmaf(x, u.y, acc[k][1]);
-        acc[k][2] = fmaf(x, u.z, acc[k][2]); acc[k][3] = fmaf(x, u.w, acc[k][3]);
+        ffma2(acc[k][0], acc[k][1], u.x, u.y, x, x); ffma2(acc[k][2], acc[k][3], u.z, u.w, x, x);
       }
     }
   }
@@ -354,19 +384,16 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
         const float4 *wf1 = reinterpret_cast<const float4 *>(Wb + 1024 + co * GC);
         const float4 *wg0 = reinterpret_cast<const float4 *>(Wb + 2048 + co * GC);
         const float4 *wg1 = reinterpret_cast<const float4 *>(Wb + 3072 + co * GC);
-        float af = a.w.filter_b[co], ag = a.w.gate_b[co];
+        float f0 = a.w.filter_b[co], f1 = 0.f, f2 = 0.f, f3 = 0.f, g0 = a.w.gate_b[co], g1 = 0.f, g2 = 0.f, g3 = 0.f;
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
           const float4 A0 = wf0[c4], A1 = wf1[c4], G0 = wg0[c4], G1 = wg1[c4];
-          af = fmaf(A0.x, r0[4 * c4], af); af = fmaf(A0.y, r0[4 * c4 + 1], af);
-          af = fmaf(A0.z, r0[4 * c4 + 2], af); af = fmaf(A0.w, r0[4 * c4 + 3], af);
-          af = fmaf(A1.x, r1[4 * c4], af); af = fmaf(A1.y, r1[4 * c4 + 1], af);
-          af = fmaf(A1.z, r1[4 * c4 + 2], af); af = fmaf(A1.w, r1[4 * c4 + 3], af);
-          ag = fmaf(G0.x, r0[4 * c4], ag); ag = fmaf(G0.y, r0[4 * c4 + 1], ag);
-          ag = fmaf(G0.z, r0[4 * c4 + 2], ag); ag = fmaf(G0.w, r0[4 * c4 + 3], ag);
-          ag = fmaf(G1.x, r1[4 * c4], ag); ag = fmaf(G1.y, r1[4 * c4 + 1], ag);
-          ag = fmaf(G1.z, r1[4 * c4 + 2], ag); ag = fmaf(G1.w, r1[4 * c4 + 3], ag);
+          ffma2(f0, f1, A0.x, A0.y, r0[4 * c4], r0[4 * c4 + 1]); ffma2(f2, f3, A0.z, A0.w, r0[4 * c4 + 2], r0[4 * c4 + 3]);
+          ffma2(f0, f1, A1.x, A1.y, r1[4 * c4], r1[4 * c4 + 1]); ffma2(f2, f3, A1.z, A1.w, r1[4 * c4 + 2], r1[4 * c4 + 3]);
+          ffma2(g0, g1, G0.x, G0.y, r0[4 * c4], r0[4 * c4 + 1]); ffma2(g2, g3, G0.z, G0.w, r0[4 * c4 + 2], r0[4 * c4 + 3]);
+          ffma2(g0, g1, G1.x, G1.y, r1[4 * c4], r1[4 * c4 + 1]); ffma2(g2, g3, G1.z, G1.w, r1[4 * c4 + 2], r1[4 * c4 + 3]);
         }
+        const float af = (f0 + f1) + (f2 + f3), ag = (g0 + g1) + (g2 + g3);
         fv[j] = tanhf(af);
         gv[j] = 1.0f / (1.0f + expf(-ag));
       }
@@ -700,7 +727,7 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
       if (a.drop_thr) dropout_row(dh, (uint64_t)(ocol + (size_t)n * GC), a.drop_thr, a.drop_scale, a.key);
       store_row(DH + (size_t)n * GC, dh);
       store_row(Y + (size_t)n * GC, dh);
-      matvec_t_acc(Wb, Y + (size_t)n * GC, du);
+      matvec_t_reg(Wb, dh, du);
     }
     store_row(DU + (size_t)n * GC, du);
   }
@@ -730,12 +757,16 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
     // dq_s = P_s dh and da_s = P_s dq_s were produced by tc_mix_kernel: du += sum_s W_s1^T dq_s + W_s2^T da_s
     // (a_s = W_s2 u, needed by dP, comes from the forward stash)
     for (int n = tid; n < N; n += GW_THREADS) {
-      float du[GC];
+      const size_t ro = ocol + (size_t)n * GC;
+      float du[GC], xa[GC], xb[GC];
+      load_row(a.DQ[0] + ro, xa);
       load_row(DU + (size_t)n * GC, du);
 #pragma unroll 1
       for (int s = 0; s < 3; ++s) {
-        matvec_t_acc(Wb + (1 + 2 * s) * 1024, a.DQ[s] + ocol + (size_t)n * GC, du);
-        matvec_t_acc(Wb + (2 + 2 * s) * 1024, a.DA3[s] + ocol + (size_t)n * GC, du);
+        load_row(a.DA3[s] + ro, xb);                        // in flight under the first product
+        matvec_t_reg(Wb + (1 + 2 * s) * 1024, xa, du);
+        if (s < 2) load_row(a.DQ[s + 1] + ro, xa);          // in flight under the second product
+        matvec_t_reg(Wb + (2 + 2 * s) * 1024, xb, du);
       }
       store_row(DU + (size_t)n * GC, du);
     }
@@ -874,7 +905,7 @@ struct GwBwdInArgs {
   double *sums;              // previous layer's backward sums [2][32] (S1, S2) or null
 };
 
-__global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_in_kernel(GwBwdInArgs a) {
+__global__ void __launch_bounds__(GW_THREADS, 2) gw_layer_bwd_in_kernel(GwBwdInArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int N = a.N, tid = threadIdx.x, tau = blockIdx.x, b = blockIdx.y;
   float *Y = smem;                       // r (normalised input) [N][32]
@@ -893,58 +924,64 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_in_kernel(GwBwdInArgs
   if (tid < 128) red[tid] = 0.f;
   __syncthreads();
 
-  float p1[GC], p2[GC], pbf[GC], pbg[GC];   // per-thread partials: S1, S2, d filter_b, d gate_b
-#pragma unroll
-  for (int c = 0; c < GC; ++c) { p1[c] = 0.f; p2[c] = 0.f; pbf[c] = 0.f; pbg[c] = 0.f; }
-
-  for (int n = tid; n < N; n += GW_THREADS) {
-    float acc[GC], x[GC];
+  // every warp walks its node slots with all 32 lanes (inactive lanes carry zero rows) so that the per-channel sums
+  // S1 = sum d, S2 = sum d * xhat, d filter_b, d gate_b can be reduced with register-tile column sums
+  for (int n0 = 0; n0 < N; n0 += GW_THREADS) {
+    if (n0 + (int)(tid & ~31u) >= N) continue;          // whole warp past the end
+    const int n = n0 + tid;
+    const bool active = n < N;
+    const size_t ro = (size_t)(active ? n : 0) * GC;
+    float acc[GC], x[GC], xb[GC];
+    float k1 = 0.f, k2 = 0.f, kf = 0.f, kg = 0.f;
 #pragma unroll
     for (int c = 0; c < GC; ++c) acc[c] = 0.f;
+    auto load_or_zero = [&](const float *p, float (&r)[GC]) {
+      if (active) load_row(p, r);
+      else {
+#pragma unroll
+        for (int c = 0; c < GC; ++c) r[c] = 0.f;
+      }
+    };
     if (has0) {
-      load_row(a.DPF + c0 + (size_t)n * GC, x);
-      matvec_t_acc(Wb, a.DPF + c0 + (size_t)n * GC, acc);
-#pragma unroll
-      for (int c = 0; c < GC; ++c) pbf[c] += x[c];
-      load_row(a.DPG + c0 + (size_t)n * GC, x);
-      matvec_t_acc(Wb + 2048, a.DPG + c0 + (size_t)n * GC, acc);
-#pragma unroll
-      for (int c = 0; c < GC; ++c) pbg[c] += x[c];
+      load_or_zero(a.DPF + c0 + ro, x);
+      load_or_zero(a.DPG + c0 + ro, xb);                  // in flight under the first product
+      matvec_t_reg(Wb, x, acc);
+      kf = warp_colsum32(x);
+      if (has1) load_or_zero(a.DPF + c1 + ro, x);
+      matvec_t_reg(Wb + 2048, xb, acc);
+      kg = warp_colsum32(xb);
+    } else if (has1) {
+      load_or_zero(a.DPF + c1 + ro, x);
     }
     if (has1) {
-      matvec_t_acc(Wb + 1024, a.DPF + c1 + (size_t)n * GC, acc);
-      matvec_t_acc(Wb + 3072, a.DPG + c1 + (size_t)n * GC, acc);
+      load_or_zero(a.DPG + c1 + ro, xb);
+      matvec_t_reg(Wb + 1024, x, acc);
+      if (a.has_gcn) load_or_zero(a.DZC + c1 + ro, x);
+      matvec_t_reg(Wb + 3072, xb, acc);
       if (a.has_gcn) {
-        load_row(a.DZC + c1 + (size_t)n * GC, x);
 #pragma unroll
         for (int c = 0; c < GC; ++c) acc[c] += x[c];
       }
     }
-    store_row(a.drin + icol + (size_t)n * GC, acc);
-    load_row(a.zin + icol + (size_t)n * GC, x);
+    if (active) store_row(a.drin + icol + ro, acc);
+    load_or_zero(a.zin + icol + ro, x);
     if (a.has_in_bn) {
 #pragma unroll
       for (int c = 0; c < GC; ++c) {
         const float mean = a.in_stats[c], var = a.in_stats[32 + c];
         const float xhat = (x[c] - mean) * (1.0f / sqrtf(var + 1e-5f));
-        p1[c] += acc[c];
-        p2[c] = fmaf(acc[c], xhat, p2[c]);
+        xb[c] = acc[c] * xhat;
         x[c] = fmaf(x[c], a.in_stats[64 + c], a.in_stats[96 + c]);
       }
     }
-    store_row(Y + (size_t)n * GC, x);
-  }
-  // reduce the per-thread partials: warp shuffle per channel, lane c keeps channel c
-  {
-    const int lane = tid & 31;
-    float k1 = 0.f, k2 = 0.f, kf = 0.f, kg = 0.f;
-#pragma unroll
-    for (int c = 0; c < GC; ++c) {
-      const float s1 = warp_sum(p1[c]), s2 = warp_sum(p2[c]), sf = warp_sum(pbf[c]), sg = warp_sum(pbg[c]);
-      if (lane == c) { k1 = s1; k2 = s2; kf = sf; kg = sg; }
+    if (active) store_row(Y + ro, x);
+    if (a.has_in_bn) {
+      k1 = warp_colsum32(acc);
+      k2 = warp_colsum32(xb);
     }
-    atomicAdd(&red[lane], k1); atomicAdd(&red[32 + lane], k2);
-    atomicAdd(&red[64 + lane], kf); atomicAdd(&red[96 + lane], kg);
+    const int lane = tid & 31;
+    if (a.has_in_bn) { atomicAdd(&red[lane], k1); atomicAdd(&red[32 + lane], k2); }
+    if (has0) { atomicAdd(&red[64 + lane], kf); atomicAdd(&red[96 + lane], kg); }
   }
   __syncthreads();
   if (tid < 32) {

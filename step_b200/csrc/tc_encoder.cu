@@ -607,6 +607,28 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
         const bool tail32 = c_tail + 32 <= Pkl;          // else the tail is one 16-column load (Pk is a multiple of 16)
         // ---- pass 1: row maximum ----
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        if (PF == 168 && !SPLIT) {
+          // reduction-only pass: 64-column loads and a combined 32 + 16 tail -> 3 TMEM round trips instead of 6
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 64) {
+            float t[64];
+            tmem_ld64(TM_S + lane_base + c0, t);
+#pragma unroll
+            for (int c = 0; c < 64; c += 4) {
+              m0 = fmaxf(m0, t[c]); m1 = fmaxf(m1, t[c + 1]); m2 = fmaxf(m2, t[c + 2]); m3 = fmaxf(m3, t[c + 3]);
+            }
+          }
+          float t[32], tq[16];
+          tmem_ld32_16(TM_S + lane_base + 128, TM_S + lane_base + 160, t, tq);
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            m0 = fmaxf(m0, t[c]); m1 = fmaxf(m1, t[c + 1]); m2 = fmaxf(m2, t[c + 2]); m3 = fmaxf(m3, t[c + 3]);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; c += 4) {
+            m0 = fmaxf(m0, tq[c]); m1 = fmaxf(m1, tq[c + 1]); m2 = fmaxf(m2, tq[c + 2]); m3 = fmaxf(m3, tq[c + 3]);
+          }
+        } else {
         for (int c0 = 0; c0 < c_tail; c0 += 32) {
           float t[32];
           tmem_ld32(TM_S + lane_base + c0, t);
@@ -629,6 +651,7 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
           }
 #pragma unroll
           for (int c = 0; c < 32; ++c) if (c_tail + c < Pl) m0 = fmaxf(m0, t[c]);
+        }
         }
         m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         // ---- pass 2: p = 2^(s - m), row sum, (dropout), bf16 image ----

@@ -178,10 +178,10 @@ __global__ void __launch_bounds__(256, 3) trunk_conv2_fwd_kernel(const float *__
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           const float4 ww = w[c4];
-          acc[0][4 * c4] = fmaf(ww.x, a0, acc[0][4 * c4]); acc[0][4 * c4 + 1] = fmaf(ww.y, a0, acc[0][4 * c4 + 1]);
-          acc[0][4 * c4 + 2] = fmaf(ww.z, a0, acc[0][4 * c4 + 2]); acc[0][4 * c4 + 3] = fmaf(ww.w, a0, acc[0][4 * c4 + 3]);
-          acc[1][4 * c4] = fmaf(ww.x, a1, acc[1][4 * c4]); acc[1][4 * c4 + 1] = fmaf(ww.y, a1, acc[1][4 * c4 + 1]);
-          acc[1][4 * c4 + 2] = fmaf(ww.z, a1, acc[1][4 * c4 + 2]); acc[1][4 * c4 + 3] = fmaf(ww.w, a1, acc[1][4 * c4 + 3]);
+          ffma2(acc[0][4 * c4], acc[0][4 * c4 + 1], ww.x, ww.y, a0, a0);
+          ffma2(acc[0][4 * c4 + 2], acc[0][4 * c4 + 3], ww.z, ww.w, a0, a0);
+          ffma2(acc[1][4 * c4], acc[1][4 * c4 + 1], ww.x, ww.y, a1, a1);
+          ffma2(acc[1][4 * c4 + 2], acc[1][4 * c4 + 3], ww.z, ww.w, a1, a1);
         }
       }
     }
@@ -393,14 +393,10 @@ __global__ void __launch_bounds__(256) trunk_conv2_bwd_kernel(const float *__res
           const float a0 = v[HALO - k], a1 = v[HALO + 1 - k];
           const float4 *w = reinterpret_cast<const float4 *>(w2t + (co * TK + k) * C1);
           const float4 wa = w[0], wb = w[1];
-          acc0[0] = fmaf(wa.x, a0, acc0[0]); acc0[1] = fmaf(wa.y, a0, acc0[1]);
-          acc0[2] = fmaf(wa.z, a0, acc0[2]); acc0[3] = fmaf(wa.w, a0, acc0[3]);
-          acc0[4] = fmaf(wb.x, a0, acc0[4]); acc0[5] = fmaf(wb.y, a0, acc0[5]);
-          acc0[6] = fmaf(wb.z, a0, acc0[6]); acc0[7] = fmaf(wb.w, a0, acc0[7]);
-          acc1[0] = fmaf(wa.x, a1, acc1[0]); acc1[1] = fmaf(wa.y, a1, acc1[1]);
-          acc1[2] = fmaf(wa.z, a1, acc1[2]); acc1[3] = fmaf(wa.w, a1, acc1[3]);
-          acc1[4] = fmaf(wb.x, a1, acc1[4]); acc1[5] = fmaf(wb.y, a1, acc1[5]);
-          acc1[6] = fmaf(wb.z, a1, acc1[6]); acc1[7] = fmaf(wb.w, a1, acc1[7]);
+          ffma2(acc0[0], acc0[1], wa.x, wa.y, a0, a0); ffma2(acc0[2], acc0[3], wa.z, wa.w, a0, a0);
+          ffma2(acc0[4], acc0[5], wb.x, wb.y, a0, a0); ffma2(acc0[6], acc0[7], wb.z, wb.w, a0, a0);
+          ffma2(acc1[0], acc1[1], wa.x, wa.y, a1, a1); ffma2(acc1[2], acc1[3], wa.z, wa.w, a1, a1);
+          ffma2(acc1[4], acc1[5], wb.x, wb.y, a1, a1); ffma2(acc1[6], acc1[7], wb.z, wb.w, a1, a1);
         }
       }
       float *o = dy1n + (size_t)n * C1 * d.L1 + t0;
@@ -437,8 +433,8 @@ __global__ void __launch_bounds__(256) trunk_conv2_bwd_kernel(const float *__res
 #pragma unroll
             for (int k = 0; k < TK; ++k) {
               const float yv = y[(i + k) % TK];
-              accw[k][0] = fmaf(g.x, yv, accw[k][0]); accw[k][1] = fmaf(g.y, yv, accw[k][1]);
-              accw[k][2] = fmaf(g.z, yv, accw[k][2]); accw[k][3] = fmaf(g.w, yv, accw[k][3]);
+              ffma2(accw[k][0], accw[k][1], g.x, g.y, yv, yv);
+              ffma2(accw[k][2], accw[k][3], g.z, g.w, yv, yv);
             }
             if (wci == 0) { accb[0] += g.x; accb[1] += g.y; accb[2] += g.z; accb[3] += g.w; }
             y[i] = yrow[base + i + TK];
