@@ -342,7 +342,7 @@ struct GwFwdArgs {
 };
 
 template <int STAGE>
-__global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
+__global__ void __launch_bounds__(GW_THREADS, 2) gw_layer_fwd_kernel(GwFwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int N = a.N, tid = threadIdx.x, t = blockIdx.x, b = blockIdx.y;
   float *Y = smem;                          // [N][32]
@@ -408,38 +408,55 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
   if (!a.has_gcn) return;
 
   // ---- stage the 7 [32x32] blocks of the gcn 1x1 conv: Wb[k][co][ci] = mlp_w[co][k*32+ci] ----
-  for (int i = tid; i < 7 * 1024; i += GW_THREADS) {
-    const int k = i >> 10, co = (i >> 5) & 31, ci = i & 31;
-    Wb[i] = a.w.mlp_w[(size_t)co * 224 + k * 32 + ci];
+  // STAGE 0 keeps Wb[k][co][ci]; the split stages stage the TRANSPOSED blocks Wb[k][ci][co] so that every channel mix
+  // is the register-row form out[co] += W^T[ci][co] * u[ci] (matvec_t_reg: accumulators and addend rows in registers)
+  // Only the blocks a stage uses are staged (stage 1: W_s2, stage 2: W_s1, stage 3: W_0); global reads stay coalesced
+  // (ci fastest), the transposition happens on the shared-memory store.
+  if (STAGE == 0) {
+    for (int i = tid; i < 7 * 1024; i += GW_THREADS) {
+      const int k = i >> 10, co = (i >> 5) & 31, ci = i & 31;
+      Wb[i] = a.w.mlp_w[(size_t)co * 224 + k * 32 + ci];
+    }
+  } else {
+    constexpr int NK = (STAGE == 3) ? 1 : 3;
+    for (int i = tid; i < NK * 1024; i += GW_THREADS) {
+      const int j = i >> 10, co = (i >> 5) & 31, ci = i & 31;
+      const int k = (STAGE == 3) ? 0 : (STAGE == 1 ? 2 + 2 * j : 1 + 2 * j);
+      Wb[k * 1024 + ci * 32 + co] = a.w.mlp_w[(size_t)co * 224 + k * 32 + ci];
+    }
   }
   __syncthreads();
 
   if (STAGE == 1) {
     // a_s = W_s2 u for the three supports -> global; the node mixes run on the tensor cores (tc_mix_kernel)
-    for (int s = 0; s < 3; ++s) {
-      const float *W2 = Wb + (2 + 2 * s) * 1024;
-      float *ao = a.Aout[s] + ocol;
-      for (int n = tid; n < N; n += GW_THREADS) {
-        float u[GC];
-        load_row(U + (size_t)n * GC, u);
-        float *ar = ao + (size_t)n * GC;
-        matvec_chunks(W2, u, [&](int cg, float4 v) { st4(ar + 4 * cg, v); });
+    for (int n = tid; n < N; n += GW_THREADS) {
+      float u[GC];
+      load_row(U + (size_t)n * GC, u);
+#pragma unroll 1
+      for (int s = 0; s < 3; ++s) {
+        float o[GC];
+#pragma unroll
+        for (int c = 0; c < GC; ++c) o[c] = 0.f;
+        matvec_t_reg(Wb + (2 + 2 * s) * 1024, u, o);
+        store_row(a.Aout[s] + ocol + (size_t)n * GC, o);
       }
     }
     return;
   }
   if (STAGE == 2) {
     // q_s = W_s1 u + (P_s^T a_s)
-    for (int s = 0; s < 3; ++s) {
-      const float *W1 = Wb + (1 + 2 * s) * 1024;
-      float *qs = a.q[s] + ocol;
-      const float *ms = a.Min[s] + ocol;
-      for (int n = tid; n < N; n += GW_THREADS) {
-        float u[GC];
-        load_row(U + (size_t)n * GC, u);
-        float *qr = qs + (size_t)n * GC;
-        const float *mr = ms + (size_t)n * GC;
-        matvec_chunks(W1, u, [&](int cg, float4 v) { st4(qr + 4 * cg, add4(v, ld4(mr + 4 * cg))); });
+    for (int n = tid; n < N; n += GW_THREADS) {
+      const size_t ro = ocol + (size_t)n * GC;
+      float u[GC], q[GC], nx[GC];
+      load_row(a.Min[0] + ro, q);
+      load_row(U + (size_t)n * GC, u);
+#pragma unroll 1
+      for (int s = 0; s < 3; ++s) {
+        if (s < 2) load_row(a.Min[s + 1] + ro, nx);     // next support's addend row, in flight under the product
+        matvec_t_reg(Wb + (1 + 2 * s) * 1024, u, q);
+        store_row(a.q[s] + ro, q);
+#pragma unroll
+        for (int c = 0; c < GC; ++c) q[c] = nx[c];
       }
     }
     return;
@@ -489,6 +506,28 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_fwd_kernel(GwFwdArgs a) {
   }
 
   // ---- phase F: h = bm + W0 u + H; dropout; residual; pre-BN output + BN partial sums ----
+  if (STAGE == 3) {
+    for (int n = tid; n < N; n += GW_THREADS) {
+      const size_t ro = ocol + (size_t)n * GC;
+      float h[GC], u[GC], r[GC];
+      load_row(a.Oin[0] + ro, h);
+      load_row(a.Oin[1] + ro, u);
+      load_row(a.Oin[2] + ro, r);
+#pragma unroll
+      for (int c = 0; c < GC; ++c) h[c] = (h[c] + u[c]) + (r[c] + a.w.mlp_b[c]);
+      load_row(U + (size_t)n * GC, u);
+      load_row(z1 + (size_t)n * GC, r);                 // residual row, in flight under the product
+      matvec_t_reg(Wb, u, h);
+      if (a.drop_thr) dropout_row(h, (uint64_t)ro, a.drop_thr, a.drop_scale, a.key);
+#pragma unroll
+      for (int c = 0; c < GC; ++c) {
+        const float rv = a.has_in_bn ? fmaf(r[c], a.in_scale[c], a.in_shift[c]) : r[c];
+        h[c] += rv;
+      }
+      store_row(a.zout + ro, h);
+      store_row(Y + (size_t)n * GC, h);
+    }
+  } else
   for (int n = tid; n < N; n += GW_THREADS) {
     float u[GC];
     load_row(U + (size_t)n * GC, u);
@@ -686,7 +725,9 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
   const float *fb = a.f + ocol, *gb = a.g + ocol;
 
   if (a.has_gcn) {
-    for (int i = tid; i < 7 * 1024; i += GW_THREADS) {
+    // stage 1 only needs W_0, stage 2 the six support blocks
+    const int i0 = (STAGE == 2) ? 1024 : 0, i1 = (STAGE == 1) ? 1024 : 7 * 1024;
+    for (int i = i0 + tid; i < i1; i += GW_THREADS) {
       const int k = i >> 10, co = (i >> 5) & 31, ci = i & 31;
       Wb[i] = a.w.mlp_w[(size_t)co * 224 + k * 32 + ci];
     }
