@@ -224,7 +224,8 @@ def main():
     if args.no_dropout:
         model.tsformer.dropout_p = 0.0
         model.backend.dropout = 0.0
-    reducer = parallel.FlatGradReducer(model.parameters(), world)    # all trainable grads in one flat buffer
+    # gradients are assigned (not accumulated) by autograd; fc.weight is all-reduced in place, the rest packed
+    reducer = parallel.GradReducer(model.parameters(), world)
 
     torch.manual_seed(1234 + rank)
     n_host = 4                                    # rotate a few distinct host batches (inputs differ step to step)
@@ -241,7 +242,7 @@ def main():
         loss = step_loss(y_hat[..., [0]], future[..., [0]], theta, adj_knn, coeff, null_val=0.0)
         reducer.zero()
         loss.backward()
-        reducer.reduce()                          # one NCCL all-reduce of the flat gradient buffer when world > 1
+        reducer.reduce()                          # NCCL all-reduce (big tensor in place + one packed buffer) when world > 1
         return loss
 
     def barrier():

@@ -95,15 +95,27 @@ class GraphWaveNet(nn.Module):
 
     @torch.no_grad()
     def _update_running_stats(self, bn_stats, batch, num_nodes):
-        t = 13
-        for i in range(self.blocks * self.layers - 1):
-            t -= 1 if i % 2 == 0 else 2
-            m = float(batch * t * num_nodes)
-            bn = self.bn[i]
-            mom = bn.momentum
-            bn.running_mean.mul_(1 - mom).add_(bn_stats[i, 0], alpha=mom)
-            bn.running_var.mul_(1 - mom).add_(bn_stats[i, 1], alpha=mom * m / max(m - 1.0, 1.0))
-            bn.num_batches_tracked += 1
+        """BatchNorm2d running statistics of the 7 live layers from the fused stack's batch statistics
+        (momentum update with the unbiased variance, as nn.BatchNorm2d does) - multi-tensor ops: 6 launches."""
+        n = self.blocks * self.layers - 1
+        key = (batch, num_nodes, bn_stats.device)
+        if getattr(self, "_rs_key", None) != key:          # unbiased-variance factors M / (M - 1), cached on the device
+            t, factors = 13, []
+            for i in range(n):
+                t -= 1 if i % 2 == 0 else 2
+                m = float(batch * t * num_nodes)
+                factors.append(m / max(m - 1.0, 1.0))
+            self._rs_factors = torch.tensor(factors, device=bn_stats.device, dtype=bn_stats.dtype).view(n, 1)
+            self._rs_key = key
+        mom = self.bn[0].momentum
+        var_unb = bn_stats[:n, 1] * self._rs_factors
+        means, variances = list(bn_stats[:n, 0].unbind(0)), list(var_unb.unbind(0))
+        rms, rvs = [self.bn[i].running_mean for i in range(n)], [self.bn[i].running_var for i in range(n)]
+        torch._foreach_mul_(rms, 1 - mom)
+        torch._foreach_add_(rms, means, alpha=mom)
+        torch._foreach_mul_(rvs, 1 - mom)
+        torch._foreach_add_(rvs, variances, alpha=mom)
+        torch._foreach_add_([self.bn[i].num_batches_tracked for i in range(n)], 1)
 
     def forward(self, input, hidden_states, sampled_adj):
         """input [B, L, N, C], hidden_states [B, N, 96], sampled_adj [B, N, N] -> [B, N, 12]."""

@@ -306,6 +306,65 @@ __device__ __forceinline__ void outer_acc_multi(const float *const (&X)[NB], con
   __syncthreads();
 }
 
+// Register-tiled weight-gradient outer products: dst_k[((co)*ldd + ci)*es] += sum_n X_k[n][co] * U[n][ci] for NB blocks
+// sharing U.  Thread = (node quarter q, 4 output rows co4.., 4 columns ci4..): per node one 16-byte load of U and one per
+// block of X feed 8 packed FMAs per block (the one-row form spent 2 shared-memory loads per 2).  The four node quarters
+// and the CTAs combine through the atomics.  tiles: (NB + 1) * 64 * 32 floats.  es: element stride of dst (2 for the
+// [co][ci][tap] conv weights).
+template <int NB>
+__device__ __forceinline__ void outer_acc_tiled(const float *const (&X)[NB], const float *U, int N, float *tiles,
+                                                float *const (&dst)[NB], int ldd, int es) {
+  float *TU = tiles;
+  const int q = threadIdx.x >> 6, co4 = ((threadIdx.x >> 3) & 7) * 4, ci4 = (threadIdx.x & 7) * 4;
+  float acc[NB][4][4];
+#pragma unroll
+  for (int k = 0; k < NB; ++k)
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[k][r][c] = 0.f;
+  for (int n0 = 0; n0 < N; n0 += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * (GC / 4); i += GW_THREADS) {
+      const int n = i >> 3, c4 = (i & 7) * 4;
+      const bool ok = (n0 + n) < N;
+      st4(TU + n * GC + c4, ok ? ld4(U + (size_t)(n0 + n) * GC + c4) : make_float4(0, 0, 0, 0));
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        st4(tiles + (k + 1) * 64 * GC + n * GC + c4, ok ? ld4(X[k] + (size_t)(n0 + n) * GC + c4) : make_float4(0, 0, 0, 0));
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < 16; ++j) {
+      const int n = 4 * j + q;
+      const float4 u = ld4(TU + n * GC + ci4);
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        const float4 x = ld4(tiles + (k + 1) * 64 * GC + n * GC + co4);
+        ffma2(acc[k][0][0], acc[k][0][1], u.x, u.y, x.x, x.x); ffma2(acc[k][0][2], acc[k][0][3], u.z, u.w, x.x, x.x);
+        ffma2(acc[k][1][0], acc[k][1][1], u.x, u.y, x.y, x.y); ffma2(acc[k][1][2], acc[k][1][3], u.z, u.w, x.y, x.y);
+        ffma2(acc[k][2][0], acc[k][2][1], u.x, u.y, x.z, x.z); ffma2(acc[k][2][2], acc[k][2][3], u.z, u.w, x.z, x.z);
+        ffma2(acc[k][3][0], acc[k][3][1], u.x, u.y, x.w, x.w); ffma2(acc[k][3][2], acc[k][3][3], u.z, u.w, x.w, x.w);
+      }
+    }
+  }
+  // combine the four node quarters through shared memory (the staging tiles are free now): one atomic per entry and CTA
+  __syncthreads();
+  float *R = tiles;                                    // [4 quarters][32 x 32]
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      st4(R + q * 1024 + (co4 + r) * GC + ci4, make_float4(acc[k][r][0], acc[k][r][1], acc[k][r][2], acc[k][r][3]));
+    __syncthreads();
+    const int o = threadIdx.x * 4;
+    const float4 v = add4(add4(ld4(R + o), ld4(R + 1024 + o)), add4(ld4(R + 2048 + o), ld4(R + 3072 + o)));
+    float *d = dst[k] + ((size_t)(o >> 5) * ldd + (o & 31)) * es;
+    atomicAdd(d, v.x); atomicAdd(d + es, v.y); atomicAdd(d + 2 * es, v.z); atomicAdd(d + 3 * es, v.w);
+    __syncthreads();
+  }
+}
+
 __device__ __forceinline__ void dropout_row(float (&h)[GC], uint64_t elem0, uint32_t thr, float scale, uint64_t key) {
   // elem0: flat index of channel 0 of this row (multiple of 32)
 #pragma unroll
@@ -791,7 +850,11 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
       }
       __syncthreads();
     }
-    outer_acc(DH, U, N, tiles, a.gr.mlp_w, 224);  // block 0: dW0[co][ci] += dh[n][co] u[n][ci]
+    {
+      const float *const Xs[1] = {DH};
+      float *const Ds[1] = {a.gr.mlp_w};
+      outer_acc_tiled<1>(Xs, U, N, tiles, Ds, 224, 1);   // block 0: dW0[co][ci] += dh[n][co] u[n][ci]
+    }
   }
   if (STAGE == 1) return;
   if (a.has_gcn && STAGE == 2) {
@@ -812,10 +875,12 @@ __global__ void __launch_bounds__(GW_THREADS) gw_layer_bwd_kernel(GwBwdArgs a) {
       store_row(DU + (size_t)n * GC, du);
     }
     {
-      const float *const Xs[6] = {a.DQ[0] + ocol, a.DA3[0] + ocol, a.DQ[1] + ocol, a.DA3[1] + ocol, a.DQ[2] + ocol, a.DA3[2] + ocol};
-      float *const Ds[6] = {a.gr.mlp_w + 1 * 32, a.gr.mlp_w + 2 * 32, a.gr.mlp_w + 3 * 32,
-                            a.gr.mlp_w + 4 * 32, a.gr.mlp_w + 5 * 32, a.gr.mlp_w + 6 * 32};
-      outer_acc_multi<6>(Xs, U, N, tiles, Ds, 224);
+      const float *const Xa[3] = {a.DQ[0] + ocol, a.DA3[0] + ocol, a.DQ[1] + ocol};
+      float *const Da[3] = {a.gr.mlp_w + 1 * 32, a.gr.mlp_w + 2 * 32, a.gr.mlp_w + 3 * 32};
+      outer_acc_tiled<3>(Xa, U, N, tiles, Da, 224, 1);
+      const float *const Xb[3] = {a.DA3[1] + ocol, a.DQ[2] + ocol, a.DA3[2] + ocol};
+      float *const Db[3] = {a.gr.mlp_w + 4 * 32, a.gr.mlp_w + 5 * 32, a.gr.mlp_w + 6 * 32};
+      outer_acc_tiled<3>(Xb, U, N, tiles, Db, 224, 1);
     }
   }
   if (a.has_gcn && STAGE == 0) {
@@ -951,8 +1016,8 @@ __global__ void __launch_bounds__(GW_THREADS, 2) gw_layer_bwd_in_kernel(GwBwdInA
   const int N = a.N, tid = threadIdx.x, tau = blockIdx.x, b = blockIdx.y;
   float *Y = smem;                       // r (normalised input) [N][32]
   float *Wb = smem + (size_t)N * GC;     // 4*1024 conv weights
-  float *tiles = Wb + 4 * 1024;          // 2*64*33
-  float *red = tiles + 2 * 64 * 33;      // 128 floats
+  float *tiles = Wb + 4 * 1024;          // 3*64*32 (outer_acc_tiled<2>)
+  float *red = tiles + 3 * 64 * 32;      // 128 floats
   const size_t col = (size_t)N * GC;
   const bool has0 = tau < a.Tout, has1 = (tau - a.dil) >= 0;
   const size_t c0 = ((size_t)b * a.Tout + tau) * col, c1 = ((size_t)b * a.Tout + (tau - a.dil)) * col;
@@ -1035,37 +1100,17 @@ __global__ void __launch_bounds__(GW_THREADS, 2) gw_layer_bwd_in_kernel(GwBwdInA
       atomicAdd(a.gr.gate_b + tid, red[96 + tid]);
     }
   }
-  // conv weight grads: dW[co][ci][tap] += sum_n dpre[tau - tap*dil][n][co] * r[tau][n][ci]
-  // r rows live in Y (smem); outer_acc wants global operands, so route Y through the U-like path:
-  // second operand read from smem directly.
-  auto outer_from_smem = [&](const float *X, float *dst, int tap) {
-    float *T1 = tiles;
-    const int co = tid >> 3, ci4 = (tid & 7) * 4;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int n0 = 0; n0 < N; n0 += 64) {
-      __syncthreads();
-      for (int i = tid; i < 64 * GC; i += GW_THREADS) {
-        const int n = i >> 5, c = i & 31;
-        T1[n * 33 + c] = ((n0 + n) < N) ? X[(size_t)(n0 + n) * GC + c] : 0.f;
-      }
-      __syncthreads();
-      const int nmax = (N - n0 < 64) ? (N - n0) : 64;
-      for (int n = 0; n < nmax; ++n) {
-        const float xv = T1[n * 33 + co];
-        const float4 r = *reinterpret_cast<const float4 *>(Y + (size_t)(n0 + n) * GC + ci4);
-        a0 = fmaf(xv, r.x, a0); a1 = fmaf(xv, r.y, a1); a2 = fmaf(xv, r.z, a2); a3 = fmaf(xv, r.w, a3);
-      }
-    }
-    float *d = dst + ((size_t)co * GC + ci4) * 2 + tap;
-    atomicAdd(d, a0); atomicAdd(d + 2, a1); atomicAdd(d + 4, a2); atomicAdd(d + 6, a3);
-  };
+  // conv weight grads: dW[co][ci][tap] += sum_n dpre[tau - tap*dil][n][co] * r[tau][n][ci]  (r rows live in Y)
+  __syncthreads();
   if (has0) {
-    outer_from_smem(a.DPF + c0, a.gr.filter_w, 0);
-    outer_from_smem(a.DPG + c0, a.gr.gate_w, 0);
+    const float *const Xs[2] = {a.DPF + c0, a.DPG + c0};
+    float *const Ds[2] = {a.gr.filter_w, a.gr.gate_w};
+    outer_acc_tiled<2>(Xs, Y, N, tiles, Ds, GC, 2);
   }
   if (has1) {
-    outer_from_smem(a.DPF + c1, a.gr.filter_w, 1);
-    outer_from_smem(a.DPG + c1, a.gr.gate_w, 1);
+    const float *const Xs[2] = {a.DPF + c1, a.DPG + c1};
+    float *const Ds[2] = {a.gr.filter_w + 1, a.gr.gate_w + 1};
+    outer_acc_tiled<2>(Xs, Y, N, tiles, Ds, GC, 2);
   }
 }
 
@@ -1100,7 +1145,7 @@ static bool gw_use_tc(int N) {
 
 static size_t fwd_smem_bytes(int N) { return ((size_t)N * GC + 7 * 1024) * sizeof(float); }
 static size_t bwd_smem_bytes(int N) { return ((size_t)N * GC + 7 * 1024 + 7 * 64 * 32) * sizeof(float); }
-static size_t bwd_in_smem_bytes(int N) { return ((size_t)N * GC + 4 * 1024 + 2 * 64 * 33 + 128) * sizeof(float); }
+static size_t bwd_in_smem_bytes(int N) { return ((size_t)N * GC + 4 * 1024 + 3 * 64 * 32 + 128) * sizeof(float); }
 
 static int gw_prepare(int N) {
   if (bwd_smem_bytes(N) > 227 * 1024)

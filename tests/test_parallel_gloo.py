@@ -62,6 +62,52 @@ def test_flat_grad_reducer_world2():
     assert sorted(res) == [(0, True), (1, True)]
 
 
+def _worker_assign(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from step_b200 import parallel
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    unused = torch.nn.Parameter(torch.ones(5))
+    frozen = torch.nn.Parameter(torch.ones(2), requires_grad=False)
+    red = parallel.GradReducer(list(model.parameters()) + [unused, frozen], big_numel=10)   # Linear(4,3).weight is "big"
+    x = torch.arange(8, dtype=torch.float32).view(2, 4) + 10.0 * rank
+    for _ in range(2):
+        red.zero()
+        assert all(p.grad is None for p in model.parameters())
+        model(x).square().sum().backward()
+        red.reduce()
+    got = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    grads = []
+    for rr in range(world):
+        m2 = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+        m2.load_state_dict(model.state_dict())
+        xx = torch.arange(8, dtype=torch.float32).view(2, 4) + 10.0 * rr
+        m2(xx).square().sum().backward()
+        grads.append(torch.cat([p.grad.reshape(-1) for p in m2.parameters()]))
+    ok = torch.allclose(got, (grads[0] + grads[1]) / 2, rtol=1e-5, atol=1e-5) and unused.grad is None
+    out.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_reducer_assign_mode_world2():
+    """GradReducer: gradients assigned by autograd (grad = None before backward), big tensors all-reduced in place,
+    small ones packed; result = the average over ranks; parameters without a gradient stay None."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_assign, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 def test_shard_batch():
     from step_b200.parallel import shard_batch
     for gb, w in ((32, 8), (33, 8), (4, 8), (7, 2)):
