@@ -43,15 +43,19 @@ __global__ void __launch_bounds__(256) trunk_conv1_stats_kernel(const float *__r
   __shared__ float xs[1024 + HALO];
   __shared__ float ws[C1 * TK + C1];
   __shared__ float red[32];
-  const int n = blockIdx.y, t0 = blockIdx.x * 1024, tid = threadIdx.x;
+  // grid (gx, N): each CTA loops over 1024-position tiles of its node and reduces ONCE at the end (one CTA per tile
+  // put ~5000 CTAs x 16 double atomics on two cache lines: the atomics, not the math, set the run time)
+  const int n = blockIdx.y, tid = threadIdx.x;
   const float *xr = x + (size_t)n * d.L0;
-  for (int i = tid; i < 1024 + HALO; i += 256) xs[i] = (t0 + i < d.L0) ? xr[t0 + i] : 0.f;
   if (tid < C1 * TK) ws[tid] = w1[tid];
   if (tid < C1) ws[C1 * TK + tid] = b1[tid];
-  __syncthreads();
   float s[C1], q[C1];
 #pragma unroll
   for (int c = 0; c < C1; ++c) { s[c] = 0.f; q[c] = 0.f; }
+  for (int t0 = blockIdx.x * 1024; t0 < d.L1; t0 += gridDim.x * 1024) {
+  __syncthreads();
+  for (int i = tid; i < 1024 + HALO; i += 256) xs[i] = (t0 + i < d.L0) ? xr[t0 + i] : 0.f;
+  __syncthreads();
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int p = tid + 256 * j;
@@ -70,6 +74,7 @@ __global__ void __launch_bounds__(256) trunk_conv1_stats_kernel(const float *__r
       }
     }
   }
+  }  // tile loop
 #pragma unroll
   for (int c = 0; c < C1; ++c) {
     block_reduce_add_double(s[c], sums + c, red);
@@ -486,12 +491,15 @@ __global__ void __launch_bounds__(256) trunk_conv1_bwd_kernel(const float *__res
   __shared__ float xs[1024 + HALO];
   __shared__ float ws[C1 * TK + C1];
   __shared__ float accs[C1 * TK + C1];
-  const int n = blockIdx.y, t0 = blockIdx.x * 1024, tid = threadIdx.x;
+  // grid (gx, N): tile loop per CTA, shared-memory accumulators flushed once (see trunk_conv1_stats_kernel)
+  const int n = blockIdx.y, tid = threadIdx.x;
   const float *xr = x + (size_t)n * d.L0;
-  for (int i = tid; i < 1024 + HALO; i += 256) xs[i] = (t0 + i < d.L0) ? xr[t0 + i] : 0.f;
   if (tid < C1 * TK) ws[tid] = w1[tid];
   if (tid < C1) ws[C1 * TK + tid] = b1[tid];
   if (tid < C1 * TK + C1) accs[tid] = 0.f;
+  for (int t0 = blockIdx.x * 1024; t0 < d.L1; t0 += gridDim.x * 1024) {
+  __syncthreads();
+  for (int i = tid; i < 1024 + HALO; i += 256) xs[i] = (t0 + i < d.L0) ? xr[t0 + i] : 0.f;
   __syncthreads();
   // one channel at a time keeps the register footprint small: 10 weight-grad accumulators + 1 bias-grad
 #pragma unroll 1
@@ -527,6 +535,7 @@ __global__ void __launch_bounds__(256) trunk_conv1_bwd_kernel(const float *__res
     gb = warp_sum(gb);
     if ((tid & 31) == 0) atomicAdd(&accs[C1 * TK + c], gb);
   }
+  }  // tile loop
   __syncthreads();
   if (tid < C1 * TK) atomicAdd(dw1 + tid, accs[tid]);
   else if (tid < C1 * TK + C1) atomicAdd(db1 + (tid - C1 * TK), accs[tid]);
@@ -580,7 +589,8 @@ extern "C" int step_dgl_conv_fwd(const float *x, int N, int L0, const float *w1,
   if (training) {
     cudaError_t e = cudaMemsetAsync(sums, 0, 48 * sizeof(double), st);
     if (e != cudaSuccess) return fail_msg((int)e, cudaGetErrorString(e));
-    trunk_conv1_stats_kernel<<<dim3((d.L1 + 1023) / 1024, N), 256, 0, st>>>(x, d, w1, b1, sums);
+    trunk_conv1_stats_kernel<<<dim3(wave_aware_ctas(trunk_conv1_stats_kernel, 0, (d.L1 + 1023) / 1024, N, 6), N), 256, 0, st>>>(
+        x, d, w1, b1, sums);
     STEP_LAUNCH_CHECK("trunk_conv1_stats_kernel");
     trunk_bn_finalize_kernel<<<1, 32, 0, st>>>(sums, (double)N * d.L1, C1, g1, be1, eps, bn1_stats);
     STEP_LAUNCH_CHECK("trunk_bn_finalize_kernel");
@@ -628,6 +638,7 @@ extern "C" int step_dgl_conv_bwd(const float *dy2n, const float *x, int N, int L
   STEP_LAUNCH_CHECK("trunk_conv2_bwd_kernel");
   trunk_bn_bwd_finalize_kernel<<<1, 32, 0, st>>>(sums, (double)N * d.L1, C1, g1, bn1_stats, eps, coef1, dg1, dbe1);
   STEP_LAUNCH_CHECK("trunk_bn_bwd_finalize_kernel");
-  trunk_conv1_bwd_kernel<<<dim3((d.L1 + 1023) / 1024, N), 256, 0, st>>>(x, d, w1, b1, dy1n_scratch, coef1, dw1, db1);
+  trunk_conv1_bwd_kernel<<<dim3(wave_aware_ctas(trunk_conv1_bwd_kernel, 0, (d.L1 + 1023) / 1024, N, 6), N), 256, 0, st>>>(
+      x, d, w1, b1, dy1n_scratch, coef1, dw1, db1);
   return check_launch("trunk_conv1_bwd_kernel");
 }
