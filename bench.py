@@ -371,10 +371,13 @@ def main():
                               "P=%d, head dim 24)" % (PATCHES, 1 if drop > 0 else 0, S_seq, PATCHES),
                     "bound": "tensor", "achieved": att_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": att_tflops / pk["bf16_tflops"], "ms": att_ms, "useful_flops": att_flops,
-                    "traffic": 970.5e6, "traffic_source": "profiles/r01_ncu_full_attn.txt (dram read+write per launch)",
+                    "traffic": 968.8e6 if DATASET == "METR-LA" and B == 32 else None,
+                    "traffic_source": "profiles/r01_ncu_full_v5_attn.txt (dram read + write per launch; algorithmic q,k,v,o "
+                                      "bf16 bytes = 855 MB, the rest is row-tile / key padding of the operand images)",
                     "peak_source": pk["source"] + " (burst cuBLAS bf16, kernel timed alone)",
-                    "note": "head dim 24 makes this kernel exp/issue-bound, not MMA-bound (SURVEY section 7): the XU pipe is at 27% "
-                            "and the tensor pipe at 8% in the ncu capture"}
+                    "note": "head dim 24 makes this kernel exp/issue-bound, not MMA-bound (SURVEY section 7): XU pipe 31%, issue slots "
+                            "47%, tensor pipe 11% in the ncu capture; ~29% of the softmax warps' time is waiting on the MMA "
+                            "round trip (one S accumulator per group fits in TMEM)"}
         roofline_other.append({"kernel": "tc_linear_kernel<1,0> (FFN1 [T,96]x[96,384] + bias + ReLU -> bf16 image)", "bound": "hbm",
                                "achieved": ffn_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ffn_gbs / pk["hbm_gbs"],
                                "ms": ffn_ms, "algorithmic_bytes": ffn_bytes})
