@@ -225,7 +225,10 @@ def main():
         model.tsformer.dropout_p = 0.0
         model.backend.dropout = 0.0
     # gradients are assigned (not accumulated) by autograd; fc.weight is all-reduced in place, the rest packed
-    reducer = parallel.GradReducer(model.parameters(), world)
+    if os.environ.get("STEP_B200_REDUCER", "assign") == "flat":
+        reducer = parallel.FlatGradReducer(model.parameters(), world)     # single flat buffer, gradients accumulate into views
+    else:
+        reducer = parallel.GradReducer(model.parameters(), world)
 
     torch.manual_seed(1234 + rank)
     n_host = 4                                    # rotate a few distinct host batches (inputs differ step to step)
