@@ -484,58 +484,70 @@ __global__ void __launch_bounds__(256) trunk_conv2_bwd_kernel(const float *__res
 // ---------------------------------------------------------------------------
 // B3: backward through BN1 -> ReLU -> conv1: dW1 [8][10], db1 [8].  grid (ceil(L1/1024), N), 256 threads.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) trunk_conv1_bwd_kernel(const float *__restrict__ x, TrunkDims d,
+__global__ void __launch_bounds__(256, 2) trunk_conv1_bwd_kernel(const float *__restrict__ x, TrunkDims d,
                                                               const float *__restrict__ w1, const float *__restrict__ b1,
                                                               const float *__restrict__ dy1n, const float *__restrict__ coef1 /*[5][8]*/,
                                                               float *__restrict__ dw1, float *__restrict__ db1) {
   __shared__ float xs[1024 + HALO];
   __shared__ float ws[C1 * TK + C1];
   __shared__ float accs[C1 * TK + C1];
+  __shared__ float cf[5 * C1];           // BN1 backward coefficients
   // grid (gx, N): tile loop per CTA, shared-memory accumulators flushed once (see trunk_conv1_stats_kernel)
   const int n = blockIdx.y, tid = threadIdx.x;
   const float *xr = x + (size_t)n * d.L0;
   if (tid < C1 * TK) ws[tid] = w1[tid];
   if (tid < C1) ws[C1 * TK + tid] = b1[tid];
   if (tid < C1 * TK + C1) accs[tid] = 0.f;
+  if (tid < 5 * C1) cf[tid] = coef1[tid];
+  float gw[C1][TK], gb[C1];
+#pragma unroll
+  for (int c = 0; c < C1; ++c) {
+    gb[c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < TK; ++k) gw[c][k] = 0.f;
+  }
   for (int t0 = blockIdx.x * 1024; t0 < d.L1; t0 += gridDim.x * 1024) {
   __syncthreads();
   for (int i = tid; i < 1024 + HALO; i += 256) xs[i] = (t0 + i < d.L0) ? xr[t0 + i] : 0.f;
   __syncthreads();
-  // one channel at a time keeps the register footprint small: 10 weight-grad accumulators + 1 bias-grad
-#pragma unroll 1
-  for (int c = 0; c < C1; ++c) {
-    float gw[TK], gb = 0.f;
+  // per-thread partials for all 8 channels stay in registers across this CTA's tiles (88 accumulators); the warp
+  // reductions run ONCE per CTA - doing them per tile and channel made the kernel shuffle-throughput-bound
 #pragma unroll
-    for (int k = 0; k < TK; ++k) gw[k] = 0.f;
-    const float a1 = coef1[c], s1m = coef1[C1 + c], s2m = coef1[2 * C1 + c], mean = coef1[3 * C1 + c], rstd = coef1[4 * C1 + c];
+  for (int j = 0; j < 4; ++j) {
+    const int p = tid + 256 * j;
+    if (t0 + p < d.L1) {
+      float xv[TK];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int p = tid + 256 * j;
-      if (t0 + p < d.L1) {
-        float xv[TK];
+      for (int k = 0; k < TK; ++k) xv[k] = xs[p + k];
+      float dy[C1];
 #pragma unroll
-        for (int k = 0; k < TK; ++k) xv[k] = xs[p + k];
+      for (int c = 0; c < C1; ++c) dy[c] = dy1n[((size_t)n * C1 + c) * d.L1 + t0 + p];     // 8 independent loads
+#pragma unroll
+      for (int c = 0; c < C1; ++c) {
         float a = ws[C1 * TK + c];
 #pragma unroll
         for (int k = 0; k < TK; ++k) a = fmaf(ws[c * TK + k], xv[k], a);
         if (a > 0.f) {
-          const float xhat = (a - mean) * rstd;
-          const float g = a1 * (dy1n[((size_t)n * C1 + c) * d.L1 + t0 + p] - s1m - xhat * s2m);
-          gb += g;
+          const float xhat = (a - cf[3 * C1 + c]) * cf[4 * C1 + c];
+          const float g = cf[c] * (dy[c] - cf[C1 + c] - xhat * cf[2 * C1 + c]);
+          gb[c] += g;
 #pragma unroll
-          for (int k = 0; k < TK; ++k) gw[k] = fmaf(g, xv[k], gw[k]);
+          for (int k = 0; k < TK; ++k) gw[c][k] = fmaf(g, xv[k], gw[c][k]);
         }
       }
     }
-#pragma unroll
-    for (int k = 0; k < TK; ++k) {
-      const float v = warp_sum(gw[k]);
-      if ((tid & 31) == 0) atomicAdd(&accs[c * TK + k], v);
-    }
-    gb = warp_sum(gb);
-    if ((tid & 31) == 0) atomicAdd(&accs[C1 * TK + c], gb);
   }
   }  // tile loop
+#pragma unroll
+  for (int c = 0; c < C1; ++c) {
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const float v = warp_sum(gw[c][k]);
+      if ((tid & 31) == 0) atomicAdd(&accs[c * TK + k], v);
+    }
+    const float vb = warp_sum(gb[c]);
+    if ((tid & 31) == 0) atomicAdd(&accs[C1 * TK + c], vb);
+  }
   __syncthreads();
   if (tid < C1 * TK) atomicAdd(dw1 + tid, accs[tid]);
   else if (tid < C1 * TK + C1) atomicAdd(db1 + (tid - C1 * TK), accs[tid]);
