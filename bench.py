@@ -274,9 +274,12 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    k0 = ops.launch_counter["kernels"]
+    # kernels of libstep_b200.so enqueued inside the timed region, counted by the library itself (every launch site
+    # goes through its check_launch); torch's own glue kernels are not included
+    from step_b200 import lib as _lib
+    k0 = int(_lib.load().step_launch_count())
     ms_res = timed(lambda i: train_step(*resident[i % 2]), args.steps)
-    launches = ops.launch_counter["kernels"] - k0
+    launches = int(_lib.load().step_launch_count()) - k0
     if args.only_resident:
         if rank == 0:
             sampler.stop()

@@ -42,6 +42,10 @@ int step_set_device(int device);
 /* Text of the last error raised on the calling thread ("" if none). */
 const char *step_last_error_string(void);
 
+/* Number of CUDA kernels this library has enqueued since it was loaded (all streams / devices; memsets are not
+ * kernels and are not counted).  bench.py reports the difference across its timed region as `gpu_launches`. */
+unsigned long long step_launch_count(void);
+
 /* ------------------------------------------------------------------------ *
  * TSFormer encoder, forecasting mode (frozen, forward only)
  *   step/step_arch/tsformer/tsformer.py:86-105,189-191

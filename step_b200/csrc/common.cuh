@@ -11,6 +11,7 @@ namespace stepk {
 
 // ---- error plumbing -------------------------------------------------------
 extern thread_local char g_last_error[512];
+extern unsigned long long g_launch_count;      // kernels enqueued by this library (every launch site calls check_launch)
 
 // fmt may use up to two %lld
 inline int fail(int code, const char *fmt, long long x = 0, long long y = 0) {
@@ -23,6 +24,7 @@ inline int fail_msg(int code, const char *msg) {
 }
 
 inline int check_launch(const char *what) {
+  __sync_fetch_and_add(&g_launch_count, 1ull);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));

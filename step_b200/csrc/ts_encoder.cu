@@ -13,6 +13,7 @@
 namespace stepk {
 
 thread_local char g_last_error[512] = {0};
+unsigned long long g_launch_count = 0;
 
 constexpr int D_MODEL = 96;
 constexpr int PATCH = 12;
@@ -398,6 +399,7 @@ using namespace stepk;
 
 extern "C" int step_abi_version(void) { return STEP_B200_ABI_VERSION; }
 extern "C" const char *step_last_error_string(void) { return g_last_error; }
+extern "C" unsigned long long step_launch_count(void) { return g_launch_count; }
 extern "C" int step_set_device(int device) {
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return fail_msg((int)e, cudaGetErrorString(e));

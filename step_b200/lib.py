@@ -42,6 +42,7 @@ SIGNATURES = {
     "step_abi_version": (C.c_int, []),
     "step_set_device": (C.c_int, [C.c_int]),
     "step_last_error_string": (C.c_char_p, []),
+    "step_launch_count": (C.c_ulonglong, []),
     "step_ts_embed_fwd": (C.c_int, [f32p, ll, ll, ll, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, f32p, C.c_float, ull, vp]),
     "step_linear_f32": (C.c_int, [f32p, f32p, f32p, f32p, ll, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, C.c_float, ull,
                                   C.c_uint, vp]),
