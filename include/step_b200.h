@@ -291,7 +291,8 @@ int step_gwnet_stack_fwd(const float *x0, const float *P1, const float *P2, cons
                          int training, float drop_p, unsigned long long seed,
                          float *skip_out, float *bn_stats, float *stash, void *stream);
 
-/* Backward of the layer stack (training mode).  dskip: [B,N,256].  P1t/P2t/P3t are the
+/* Backward of the layer stack (training mode), to be called after step_gwnet_stack_fwd on the same stash (which
+ * holds z, f, g, q_s and - on the tensor-core mix path - a_s of every layer).  dskip: [B,N,256].  P1t/P2t/P3t are the
  * transposed supports.  Outputs: dx0 [B,13,N,32], dP1,dP2 [B,N,N], dP3 [N,N], per-layer
  * parameter gradients (all overwritten). */
 int step_gwnet_stack_bwd(const float *dskip, const float *x0, const float *P1, const float *P2, const float *P3,
