@@ -1,3 +1,4 @@
+"""Sliding-window dataset over the pre-processed BasicTS pickle (history, long history and future windows)."""
 from .forecasting_dataset import ForecastingDataset
 
 __all__ = ["ForecastingDataset"]

@@ -1,3 +1,4 @@
+"""Runner glue with the BasicTS contract (host tuple in, 4-tuple out, loss splat) - see step_runner.py."""
 from .step_runner import STEPRunner
 
 __all__ = ["STEPRunner"]
