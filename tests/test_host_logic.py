@@ -61,3 +61,28 @@ def test_mask_generator_reproduces_the_reference_draw():
     assert unmasked == fx["unmasked"] and masked == fx["masked"]
     mg.fixed = ([1, 2], [0, 3])
     assert mg() == ([1, 2], [0, 3])
+
+
+def test_device_window_loader_matches_dataset_items():
+    """DeviceWindowLoader (device-resident series, windows gathered from the index) serves exactly the items of
+    ForecastingDataset.__getitem__ stacked over the batch, including the all-zero long history of early windows."""
+    from step.step_data import DeviceWindowLoader, ForecastingDataset
+    ds = ForecastingDataset(synthetic=True, num_nodes=7, seq_len=48, length=40, seed=3)
+    ds.index = [(i, i + 12, i + 24) for i in range(20, 60)]          # the first windows start before seq_len
+    loader = DeviceWindowLoader(ds, "cpu", batch_size=16, shuffle=True, seed=5)
+    assert len(loader) == 3
+    seen = 0
+    g = torch.Generator().manual_seed(5)
+    order = torch.randperm(40, generator=g)
+    for bi, (future, history, long_history) in enumerate(loader):
+        ids = order[bi * 16:(bi + 1) * 16]
+        ref = [ds[int(i)] for i in ids]
+        assert torch.equal(future, torch.stack([r[0] for r in ref]))
+        assert torch.equal(history, torch.stack([r[1] for r in ref]))
+        assert torch.equal(long_history, torch.stack([r[2] for r in ref]))
+        seen += len(ids)
+    assert seen == 40
+    assert any(float(ds[i][2].abs().sum()) == 0.0 for i in range(5))          # the zero-window branch was exercised
+    only0 = DeviceWindowLoader(ds, "cpu", batch_size=8, long_channels=[0])
+    f, h, lh = next(iter(only0))
+    assert lh.shape == (8, 48, 7, 1) and torch.equal(lh[..., 0], torch.stack([ds[i][2][..., 0] for i in range(8)]))
