@@ -74,3 +74,21 @@ class STEPRunner:
             pred, real = pred[:, :cl], real[:, :cl]
         ret[0], ret[1] = pred, real
         return self.loss(*ret, null_val=self.null_val)
+
+    # ---- reference: base_tsf_runner.py:275-318 (test): per-horizon and overall MAE / RMSE / MAPE on re-scaled values ----
+    @torch.no_grad()
+    def test(self, data_loader, horizons=None) -> dict:
+        """data_loader yields the dataset tuples (future, history, long_history); the model is put in eval() for the
+        pass (running BatchNorm statistics, no dropout, ``epoch=None`` -> gsl_coefficient 0) and restored afterwards."""
+        from . import metrics
+        was_training = self.model.training
+        self.model.eval()
+        try:
+            pairs = []
+            for data in data_loader:
+                ret = self.forward(data=data, epoch=None, iter_num=None, train=False)
+                pairs.append((ret[0], ret[1]))
+        finally:
+            self.model.train(was_training)
+        return metrics.evaluate(pairs, scaler_mean=self.scaler["mean"], scaler_std=self.scaler["std"], null_val=self.null_val,
+                                horizons=horizons)

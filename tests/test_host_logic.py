@@ -86,3 +86,28 @@ def test_device_window_loader_matches_dataset_items():
     only0 = DeviceWindowLoader(ds, "cpu", batch_size=8, long_channels=[0])
     f, h, lh = next(iter(only0))
     assert lh.shape == (8, 48, 7, 1) and torch.equal(lh[..., 0], torch.stack([ds[i][2][..., 0] for i in range(8)]))
+
+
+def test_metrics_match_reference_golden():
+    """step_runner.metrics (MAE / RMSE / MAPE with missing values, per-horizon summary) vs values computed by the
+    reference's own metric functions (tests/golden/make_golden_metrics.py)."""
+    import importlib.util
+    from step.step_runner import metrics as M
+    spec = importlib.util.spec_from_file_location("mgm", os.path.join(GOLDEN, "make_golden_metrics.py"))
+    mgm = importlib.util.module_from_spec(spec); spec.loader.exec_module(mgm)
+    fx = torch.load(os.path.join(GOLDEN, "metrics_reference.pt"), weights_only=False)
+    for seed, want in fx.items():
+        pred, real = mgm.inputs(seed)
+        assert abs(float(M.masked_mae(pred, real, 0.0)) - want["MAE0"]) < 1e-5 * max(1.0, abs(want["MAE0"]))
+        assert abs(float(M.masked_rmse(pred, real, 0.0)) - want["RMSE0"]) < 1e-5 * max(1.0, abs(want["RMSE0"]))
+        assert abs(float(M.masked_mape(pred, real, 0.0)) - want["MAPE"]) < 1e-5 * max(1.0, abs(want["MAPE"]))
+        nan_real = torch.where(real == 0, torch.full_like(real, float("nan")), real)
+        assert abs(float(M.masked_mae(pred, nan_real)) - want["MAEnan"]) < 1e-5 * max(1.0, abs(want["MAEnan"]))
+        rep = M.evaluate([(pred[:2], real[:2]), (pred[2:], real[2:])], null_val=0.0)
+        got = rep["horizon"][3]
+        for v, w in zip((got["MAE"], got["RMSE"], got["MAPE"]), want["h3"]):
+            assert abs(v - w) < 1e-5 * max(1.0, abs(w))
+        assert abs(rep["overall"]["MAE"] - want["MAE0"]) < 1e-5 * max(1.0, abs(want["MAE0"]))
+    # an all-missing slice contributes zero instead of NaN
+    z = torch.zeros(2, 3)
+    assert float(M.masked_mae(torch.ones(2, 3), z, 0.0)) == 0.0
