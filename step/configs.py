@@ -8,7 +8,7 @@ import os
 from .easydict_lite import EasyDict
 from .step_arch import STEP
 from .step_loss import step_loss
-from .step_runner import STEPRunner
+from .step_runner import STEPRunner, TSFormerRunner
 from .step_data import ForecastingDataset
 
 _NODES = {"METR-LA": 207, "PEMS-BAY": 325, "PEMS03": 358, "PEMS04": 307, "PEMS07": 883, "PEMS08": 170}
@@ -60,5 +60,49 @@ def step_config(name: str, gpu_num: int = 1) -> EasyDict:
         CFG.TRAIN.CL = EasyDict(_CL[name])
     for split in ("VAL", "TEST"):
         CFG[split] = EasyDict(INTERVAL=1, DATA=EasyDict(DIR="datasets/" + name, BATCH_SIZE=_BATCH[name], PREFETCH=False,
+                                                        SHUFFLE=False, NUM_WORKERS=2, PIN_MEMORY=True))
+    return CFG
+
+
+# ---- stage 1: TSFormer pre-training configs (reference step/TSFormer_<NAME>.py) ------------------------------------
+_TS_BATCH = {"METR-LA": 8, "PEMS-BAY": 16, "PEMS03": 3, "PEMS04": 6, "PEMS07": 3, "PEMS08": 6}
+_TS_LR = {"METR-LA": 0.0005, "PEMS-BAY": 0.001, "PEMS03": 0.001, "PEMS04": 0.001, "PEMS07": 0.001, "PEMS08": 0.001}
+
+
+def tsformer_config(name: str, gpu_num: int = 1) -> EasyDict:
+    """Masked-patch pre-training of TSFormer: history of _SEQ[name] steps, channel 0 only, 75 % of the 12-step patches
+    masked, objective masked MAE (null value 0) between the reconstructed and the true masked patches."""
+    from .step_arch import TSFormer
+    from .step_runner.metrics import masked_mae
+    CFG = EasyDict()
+    CFG.DESCRIPTION = f"TSFormer({name}) configuration"
+    CFG.RUNNER = TSFormerRunner
+    CFG.DATASET_CLS = ForecastingDataset
+    CFG.DATASET_NAME = name
+    CFG.DATASET_INPUT_LEN = _SEQ[name]
+    CFG.DATASET_OUTPUT_LEN = 12
+    CFG.DATASET_ARGS = {"seq_len": _SEQ[name]}
+    CFG.GPU_NUM = gpu_num
+    CFG.ENV = EasyDict(SEED=0, CUDNN=EasyDict(ENABLED=True))
+    CFG.MODEL = EasyDict()
+    CFG.MODEL.NAME = "TSFormer"
+    CFG.MODEL.ARCH = TSFormer
+    CFG.MODEL.PARAM = {"patch_size": 12, "in_channel": 1, "embed_dim": 96, "num_heads": 4, "mlp_ratio": 4, "dropout": 0.1,
+                       "num_token": _SEQ[name] / 12, "mask_ratio": 0.75, "encoder_depth": 4, "decoder_depth": 1,
+                       "mode": "pre-train"}
+    CFG.MODEL.FORWARD_FEATURES = [0]
+    CFG.MODEL.TARGET_FEATURES = [0]
+    CFG.TRAIN = EasyDict()
+    CFG.TRAIN.LOSS = masked_mae
+    CFG.TRAIN.OPTIM = EasyDict(TYPE="Adam", PARAM={"lr": _TS_LR[name], "weight_decay": 0, "eps": 1.0e-8, "betas": (0.9, 0.95)})
+    CFG.TRAIN.LR_SCHEDULER = EasyDict(TYPE="MultiStepLR", PARAM={"milestones": [50], "gamma": 0.5})
+    CFG.TRAIN.CLIP_GRAD_PARAM = {"max_norm": 5.0}
+    CFG.TRAIN.NUM_EPOCHS = 100
+    CFG.TRAIN.CKPT_SAVE_DIR = os.path.join("checkpoints", "TSFormer_100")
+    CFG.TRAIN.NULL_VAL = 0.0
+    CFG.TRAIN.DATA = EasyDict(DIR="datasets/" + name, BATCH_SIZE=_TS_BATCH[name], PREFETCH=False, SHUFFLE=True, NUM_WORKERS=2,
+                              PIN_MEMORY=True)
+    for split in ("VAL", "TEST"):
+        CFG[split] = EasyDict(INTERVAL=1, DATA=EasyDict(DIR="datasets/" + name, BATCH_SIZE=_TS_BATCH[name], PREFETCH=False,
                                                         SHUFFLE=False, NUM_WORKERS=2, PIN_MEMORY=True))
     return CFG

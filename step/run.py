@@ -24,11 +24,39 @@ def parse_args():
     return parser.parse_args()
 
 
+def pretrain_forward(args, mod):
+    """`--cfg step/TSFormer_<NAME>.py`: stage-1 config.  The masked encoder/decoder run forward-only on the B200 kernels
+    (DESIGN.md section 8), so this evaluates the pre-training objective on synthetic windows instead of training."""
+    from step.step_data import ForecastingDataset
+    CFG = importlib.import_module(mod).CFG
+    name = CFG.DATASET_NAME
+    from step.configs import _NODES
+    torch.manual_seed(CFG.ENV.SEED)
+    runner = CFG.RUNNER(CFG)
+    runner.model.train()                                   # dropout live, as in the reference's training iterations
+    ds = ForecastingDataset(mode="train", seq_len=CFG.DATASET_INPUT_LEN, synthetic=True, num_nodes=_NODES[name],
+                            length=CFG.TRAIN.DATA.BATCH_SIZE * 4)
+    loader = torch.utils.data.DataLoader(ds, batch_size=CFG.TRAIN.DATA.BATCH_SIZE, shuffle=True, drop_last=True, pin_memory=True)
+    it, t0 = 0, time.perf_counter()
+    while it < args.steps:
+        for data in loader:
+            loss = runner.loss_iters(1, it, data)
+            it += 1
+            if it % 5 == 0 or it == args.steps:
+                torch.cuda.synchronize()
+                print(f"iter {it:4d}  reconstruction MAE {loss.item():.5f}  "
+                      f"{it * CFG.TRAIN.DATA.BATCH_SIZE / (time.perf_counter() - t0):.1f} samples/s (forward only)")
+            if it >= args.steps:
+                break
+
+
 def main():
     args = parse_args()
     os.environ.setdefault("CUDA_VISIBLE_DEVICES", args.gpus)
     mod = "step." + os.path.splitext(os.path.basename(args.cfg))[0]
     from step.step_data import ForecastingDataset
+    if os.path.basename(args.cfg).startswith("TSFormer_"):
+        return pretrain_forward(args, mod)
     name = os.path.basename(args.cfg)[len("STEP_"):-3]
     from step.configs import _NODES, _SEQ
     n, seq = _NODES[name], _SEQ[name]

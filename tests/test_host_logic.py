@@ -111,3 +111,24 @@ def test_metrics_match_reference_golden():
     # an all-missing slice contributes zero instead of NaN
     z = torch.zeros(2, 3)
     assert float(M.masked_mae(torch.ones(2, 3), z, 0.0)) == 0.0
+
+
+def test_tsformer_pretrain_config_and_runner_contract():
+    """Stage-1 config layout (reference step/TSFormer_<NAME>.py) and the TSFormerRunner glue: constructor arguments the
+    reference passes, 72 checkpoint keys, masked-MAE objective, forward-only status stated loudly."""
+    import importlib
+    from step.step_runner import TSFormerRunner
+    from step.step_runner.metrics import masked_mae
+    for name, batch, lr, tokens in (("METR-LA", 8, 0.0005, 168.0), ("PEMS04", 6, 0.001, 336.0)):
+        CFG = importlib.import_module(f"step.TSFormer_{name}").CFG
+        assert CFG.RUNNER is TSFormerRunner and CFG.TRAIN.LOSS is masked_mae and CFG.TRAIN.NULL_VAL == 0.0
+        assert CFG.TRAIN.DATA.BATCH_SIZE == batch and CFG.TRAIN.OPTIM.PARAM["lr"] == lr
+        assert CFG.MODEL.PARAM["mode"] == "pre-train" and CFG.MODEL.PARAM["num_token"] == tokens
+        assert CFG.MODEL.FORWARD_FEATURES == [0] and CFG.DATASET_INPUT_LEN == int(tokens) * 12
+    runner = TSFormerRunner(CFG, device="cpu")
+    assert len(runner.model.state_dict()) == 72 and runner.model.mode == "pre-train"
+    with pytest.raises(NotImplementedError):
+        runner.train_iters(1, 0, (torch.zeros(1, 12, 3, 3), torch.zeros(1, 4032, 3, 3)))
+    from step_b200.lib import StepB200Error
+    with pytest.raises(StepB200Error):                     # CPU tensors never run silently
+        runner.loss_iters(1, 0, (torch.zeros(1, 12, 3, 3), torch.zeros(1, 4032, 3, 3)))
