@@ -132,3 +132,33 @@ def test_tsformer_pretrain_config_and_runner_contract():
     from step_b200.lib import StepB200Error
     with pytest.raises(StepB200Error):                     # CPU tensors never run silently
         runner.loss_iters(1, 0, (torch.zeros(1, 12, 3, 3), torch.zeros(1, 4032, 3, 3)))
+
+
+def test_step_forward_orchestration_with_stub_submodules(tmp_path):
+    """STEP.forward wiring (reference step.py:37-72) checked on CPU with stub sub-modules: last-patch hidden state to the
+    backend, [B,N,12] -> [B,12,N,1], theta as a stride-0 [B,N,N] view, gsl coefficient 1/(epoch//6+1) or 0."""
+    model, _, _ = build_step_model(tmp_path, "PEMS08")
+    B, N, P = 2, 170, 3
+    hidden = torch.randn(B, N, P, 96)
+    seen = {}
+
+    class FakeDGL(torch.nn.Module):
+        theta = torch.rand(N, N)
+
+        def forward(self, long_history, tsformer):
+            seen["long"] = long_history.shape
+            return torch.zeros(B, N * N, 2), hidden, torch.ones(B, N, N), torch.zeros(B, N, N)
+
+    class FakeBackend(torch.nn.Module):
+        def forward(self, x, hidden_states, sampled_adj):
+            seen["hidden_last"] = hidden_states
+            return torch.arange(B * N * 12, dtype=torch.float32).view(B, N, 12)
+
+    model.discrete_graph_learning, model.backend = FakeDGL(), FakeBackend()
+    history, long_history = torch.zeros(B, 12, N, 3), torch.zeros(B, P * 12, N, 3)
+    y, theta, knn, coeff = model(history_data=history, long_history_data=long_history, future_data=None, batch_seen=0, epoch=13)
+    assert torch.equal(seen["hidden_last"], hidden[:, :, -1, :]) and tuple(seen["long"]) == (B, P * 12, N, 3)
+    assert y.shape == (B, 12, N, 1) and float(y[1, 3, 5, 0]) == float((1 * N + 5) * 12 + 3)
+    assert theta.shape == (B, N, N) and theta.stride(0) == 0 and torch.equal(theta[1], FakeDGL.theta)
+    assert coeff == 1 / 3 and knn.shape == (B, N, N)
+    assert model(history_data=history, long_history_data=long_history, future_data=None, batch_seen=0, epoch=None)[3] == 0
