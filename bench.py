@@ -126,8 +126,8 @@ def write_dataset(tmp, node_feats):
 
 def ts_state():
     if DATASET != "METR-LA":        # only the METR-LA checkpoint is small enough to ship as a fixture
-        from oracle import step_oracle as O
-        return O.synthetic_tsformer_params(1)
+        from step_b200 import synth
+        return synth.synthetic_tsformer_params(1)
     return torch.load(os.path.join(ROOT, "tests", "golden", "tsformer_METR-LA_state.pt"))
 
 
@@ -199,7 +199,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     parallel.init_from_env("nccl")
 
-    from oracle import step_oracle as O          # only for the deterministic synthetic tensors + the CPU leg
+    from step_b200 import synth as O             # deterministic synthetic tensors (the oracle is imported by the CPU leg only)
     from step.step_arch import STEP
     from step.step_loss import step_loss
     from step_b200 import ops
