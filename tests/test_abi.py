@@ -33,3 +33,25 @@ def test_sass_is_sm100a():
     from step_b200 import build
     out = subprocess.run(["cuobjdump", "-lelf", build.build()], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_argument_validation_returns_status_and_message():
+    """Error conventions of the C ABI (include/step_b200.h): bad arguments are rejected before any CUDA call with a
+    negative status and a message retrievable through step_last_error_string(); pure size queries work without a GPU."""
+    from step_b200 import lib
+    h = lib.load()
+    # null pointers -> STEP_EINVAL (-1) and a message naming the entry point
+    rc = h.step_tc_attention(None, None, None, None, 4, 168, 0.0, 0, None)
+    assert rc < 0 and b"tc_attention" in h.step_last_error_string()
+    rc = h.step_layernorm96_f32(None, None, None, None, 10, None)
+    assert rc < 0 and b"layernorm" in h.step_last_error_string()
+    rc = h.step_ts_layers_fwd(None, 1, 1, None, 1, None, None, None, 0, 0.0, 0, None)
+    assert rc < 0 and b"ts_layers" in h.step_last_error_string()
+    # workspace / image size queries are host-only arithmetic
+    assert h.step_ts_encoder_workspace_bytes(10, 168) >= 10 * 168 * (96 * 3 + 384) * 4
+    q, kv = h.step_tc_attn_image_bytes(3, 168, 0), h.step_tc_attn_image_bytes(3, 168, 1)
+    assert q == 3 * 4 * 2 * 6144 and kv == 3 * 4 * 3 * 176 * 16          # 2 row tiles of 128; keys padded to 176
+    assert h.step_tc_attn_image_bytes(1, 336, 1) == 4 * 3 * 336 * 16
+    assert h.step_tc_seq_image_bytes(2, 207, 168) == 2 * 168 * 12 * 256 * 16
+    assert h.step_gwnet_stash_floats(2, 207, 8) > 9 * 2 * 51 * 207 * 32
+    assert h.step_launch_count() == 0                                      # nothing was launched by the rejected calls
