@@ -40,6 +40,7 @@ def test_argument_validation_returns_status_and_message():
     negative status and a message retrievable through step_last_error_string(); pure size queries work without a GPU."""
     from step_b200 import lib
     h = lib.load()
+    launched = h.step_launch_count()
     # null pointers -> STEP_EINVAL (-1) and a message naming the entry point
     rc = h.step_tc_attention(None, None, None, None, 4, 168, 0.0, 0, None)
     assert rc < 0 and b"tc_attention" in h.step_last_error_string()
@@ -54,4 +55,4 @@ def test_argument_validation_returns_status_and_message():
     assert h.step_tc_attn_image_bytes(1, 336, 1) == 4 * 3 * 336 * 16
     assert h.step_tc_seq_image_bytes(2, 207, 168) == 2 * 168 * 12 * 256 * 16
     assert h.step_gwnet_stash_floats(2, 207, 8) > 9 * 2 * 51 * 207 * 32
-    assert h.step_launch_count() == 0                                      # nothing was launched by the rejected calls
+    assert h.step_launch_count() == launched                               # nothing was launched by the rejected calls
