@@ -17,14 +17,31 @@ def unpack(bits, n):
     return torch.from_numpy(np.unpackbits(bits.numpy(), axis=1)[:, : n * n].astype(np.float32)).reshape(-1, n, n)
 
 
-@pytest.mark.parametrize("name", ["step_PEMS08_b1.pt", "step_METR-LA_b2.pt"])
-def test_step_forward_backward_matches_reference_golden(name, tmp_path):
+ALL_GOLDEN = ["step_PEMS08_b1.pt", "step_METR-LA_b2.pt", "step_PEMS04_b1.pt", "step_PEMS-BAY_b1.pt", "step_PEMS07_b1.pt"]
+
+# Tolerances per precision.  fp32 = the BASELINE bar (y_hat MAE <= 1e-4) with everything else at fp32 summation-order
+# noise.  bf16 = the benchmarked mode: encoder + Gram on bf16 tensor cores (everything downstream, incl. the trunk
+# Linear on split-bf16 tcgen05, is fp32-accurate), so y_hat is held to the SAME 1e-4 MAE bar, the hidden states to
+# bf16 rounding (2^-9 relative, |h| <= ~4), and gradients to 3e-2 of each tensor's max (they see the bf16 hidden
+# state only through fc_his).
+TOL = {"fp32": dict(y=1e-4, theta=2e-4, hidden=2e-4, hsum=1e-5, bern=1e-4, knn=8, sampled=2, loss=5e-5, grad=1e-2, gnorm=1e-2),
+       "bf16": dict(y=1e-4, theta=2e-4, hidden=6e-2, hsum=2e-3, bern=1e-4, knn=None, sampled=2, loss=5e-4, grad=3e-2, gnorm=3e-2)}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ALL_GOLDEN)
+def test_step_forward_backward_matches_reference_golden(name, precision, tmp_path):
+    """Every BASELINE config shape (METR-LA N=207; PEMS04 N=307 P=336; PEMS-BAY N=325; PEMS07 N=883; + PEMS08 N=170
+    P=336) against outputs of THE REFERENCE (tests/golden/make_golden.py): forward, loss and every parameter gradient,
+    in both precisions of the CUDA path."""
     from step.step_loss import step_loss
+    tol = TOL[precision]
     fx = torch.load(os.path.join(GOLDEN, name), weights_only=False)
     ds, n = fx["dataset"], O.NUM_NODES[fx["dataset"]]
+    rs = fx.get("row_stride", 1)
     model, _, _ = build_step_model(tmp_path, ds, fx["seed"], real_ckpt=fx["real_ckpt"])
     model = model.to(DEV).train()
-    model.tsformer.precision = "fp32"       # the 1e-4 parity bar is defined for the fp32 kernels
+    model.tsformer.precision = precision
     model.tsformer.dropout_p = 0.0          # parity suite B (SURVEY Appx D.4): train() everywhere, dropout off
     model.backend.dropout = 0.0
     history, long_history, future, uniform = O.synthetic_batch(ds, fx["batch"], fx["patches"], fx["seed"])
@@ -32,32 +49,45 @@ def test_step_forward_backward_matches_reference_golden(name, tmp_path):
     y_hat, theta, adj_knn, coeff = model(history_data=history.to(DEV), long_history_data=long_history.to(DEV),
                                          future_data=None, batch_seen=0, epoch=1)
     assert list(y_hat.shape) == [fx["batch"], 12, n, 1] and coeff == 1.0
-    # --- forward parity (BASELINE.json: fp32 MAE <= 1e-4 vs the reference)
-    assert (y_hat.detach().cpu() - fx["y_hat"]).abs().mean().item() <= 1e-4
-    th_err = (theta[0].detach().cpu() - fx["theta0"]).abs().max().item()
-    print(f"fp32 mode: theta max err {th_err:.2e}")
-    assert th_err < 2e-4
+    # --- forward parity (BASELINE.json: MAE <= 1e-4 vs the reference)
+    mae = (y_hat.detach().cpu() - fx["y_hat"]).abs().mean().item()
+    th_err = (theta[0].detach().cpu()[::rs] - fx["theta0"]).abs().max().item()
     ref_knn = unpack(fx["adj_knn_bits"], n)
-    assert int((adj_knn.cpu() != ref_knn).sum()) <= 8          # threshold ties are implementation-defined
+    mism = int((adj_knn.cpu() != ref_knn).sum())
+    print(f"{ds} {precision}: y_hat MAE {mae:.3e}, theta max err {th_err:.2e}, adj_knn mismatches {mism} of {int(ref_knn.sum())}")
+    assert mae <= tol["y"]
+    assert th_err < tol["theta"]
+    # threshold ties are implementation-defined (fp32); in bf16 the global top-k threshold cuts through near-ties: <= 2 %
+    assert mism <= (tol["knn"] if tol["knn"] is not None else 0.02 * 2 * float(ref_knn.sum()))
     with torch.no_grad():
         bern, hidden, _, sampled = model.discrete_graph_learning(long_history.to(DEV), model.tsformer)
-    assert (hidden[:, :, -1, :].cpu() - fx["hidden_last"]).abs().max().item() < 2e-4
-    assert (hidden[:, ::23, ::17, :].cpu() - fx["hidden_slice"]).abs().max().item() < 2e-4
-    assert abs(hidden.double().sum().item() - fx["hidden_sum"]) / fx["hidden_abs_sum"] < 1e-5
-    assert (bern[0].cpu() - fx["bernoulli_unnorm0"]).abs().max().item() < 1e-4
-    assert int((sampled.cpu() != unpack(fx["sampled_adj_bits"], n)).sum()) <= 2
+    h_last = (hidden[:, :, -1, :].cpu() - fx["hidden_last"]).abs().max().item()
+    h_slice = (hidden[:, ::23, ::17, :].cpu() - fx["hidden_slice"]).abs().max().item()
+    h_sum = abs(hidden.double().sum().item() - fx["hidden_sum"]) / fx["hidden_abs_sum"]
+    b_err = (bern[0].view(n, n, 2)[::rs].reshape(-1, 2).cpu() - fx["bernoulli_unnorm0"]).abs().max().item()
+    s_flips = int((sampled.cpu() != unpack(fx["sampled_adj_bits"], n)).sum())
+    print(f"{ds} {precision}: hidden max err last {h_last:.2e} slice {h_slice:.2e} sum {h_sum:.2e}; logits {b_err:.2e}; "
+          f"sampled_adj flips {s_flips}")
+    assert h_last < tol["hidden"] and h_slice < tol["hidden"] and h_sum < tol["hsum"]
+    assert b_err < tol["bern"]
+    assert s_flips <= tol["sampled"]
     # --- loss + gradients (use the reference's kNN graph so that tie-breaks do not leak into the loss)
     loss = step_loss(y_hat[..., [0]], future.to(DEV)[..., [0]], theta, ref_knn.to(DEV), coeff, null_val=0.0)
-    assert abs(loss.item() - fx["loss"].item()) < 5e-5
+    print(f"{ds} {precision}: loss {loss.item():.6f} vs reference {fx['loss'].item():.6f}")
+    assert abs(loss.item() - fx["loss"].item()) < tol["loss"]
     loss.backward()
     named = dict(model.named_parameters())
+    errs, nerrs = {}, {}
     for k, g in fx["grads"].items():
         mine = named[k].grad
         assert mine is not None, k
         got = mine.reshape(-1)[g["idx"].to(DEV)].cpu()
-        scale = max(g["absmax"], 1e-6)
-        assert (got - g["val"]).abs().max().item() / scale < 1e-2, k
-        assert abs(float(mine.double().norm()) - g["norm"]) / max(g["norm"], 1e-9) < 1e-2 or g["absmax"] < 1e-8, k
+        errs[k] = (got - g["val"]).abs().max().item() / max(g["absmax"], 1e-6)
+        nerrs[k] = 0.0 if g["absmax"] < 1e-8 else abs(float(mine.double().norm()) - g["norm"]) / max(g["norm"], 1e-9)
+    wk, wn = max(errs, key=errs.get), max(nerrs, key=nerrs.get)
+    print(f"{ds} {precision}: worst sampled-gradient error {errs[wk]:.2e} of max at {wk}; worst norm error {nerrs[wn]:.2e} at {wn}")
+    assert errs[wk] < tol["grad"], (wk, errs[wk])
+    assert nerrs[wn] < tol["gnorm"], (wn, nerrs[wn])
     for k in fx["no_grad"]:
         assert named[k].grad is None or float(named[k].grad.abs().max()) == 0.0, k
 
@@ -105,41 +135,12 @@ def test_full_size_properties_metr_la(tmp_path):
             assert p.grad is not None and torch.isfinite(p.grad).all(), k
 
 
-@pytest.mark.parametrize("name", ["step_METR-LA_b2.pt", "step_PEMS08_b1.pt"])      # P = 168 and P = 336 (key-split attention)
-def test_step_bf16_encoder_against_reference_golden(name, tmp_path):
-    """Performance precision: TSFormer on the tensor cores in bf16 (everything downstream fp32).  Stated tolerance
-    for this mode: y_hat MAE <= 5e-3, adj_knn differs in <= 2% of the selected edges (the top-k threshold cuts through
-    near-ties), theta within 2e-4 (it does not depend on the encoder; the trunk Linear is TF32 in this mode)."""
-    fx = torch.load(os.path.join(GOLDEN, name), weights_only=False)
-    ds, n = fx["dataset"], O.NUM_NODES[fx["dataset"]]
-    model, _, _ = build_step_model(tmp_path, ds, fx["seed"], real_ckpt=fx["real_ckpt"])
-    model = model.to(DEV).train()
-    model.tsformer.precision = "bf16"
-    model.tsformer.dropout_p = 0.0
-    model.backend.dropout = 0.0
-    history, long_history, future, uniform = O.synthetic_batch(ds, fx["batch"], fx["patches"], fx["seed"])
-    model.discrete_graph_learning.gumbel_uniform = uniform.to(DEV)
-    y_hat, theta, adj_knn, coeff = model(history_data=history.to(DEV), long_history_data=long_history.to(DEV),
-                                         future_data=None, batch_seen=0, epoch=1)
-    mae = (y_hat.detach().cpu() - fx["y_hat"]).abs().mean().item()
-    ref_knn = unpack(fx["adj_knn_bits"], n)
-    mism = int((adj_knn.cpu() != ref_knn).sum())
-    print(f"bf16 encoder: y_hat MAE {mae:.3e}, adj_knn mismatches {mism} of {int(ref_knn.sum())} edges")
-    assert mae <= 5e-3
-    assert mism <= 0.02 * 2 * float(ref_knn.sum())
-    th_err = (theta[0].detach().cpu() - fx["theta0"]).abs().max().item()
-    print(f"bf16 mode: theta max err {th_err:.2e}")
-    assert th_err < 2e-4       # the trunk's Linear runs in TF32 in this mode
-
-
-@pytest.mark.parametrize("dataset,B,P", [("PEMS07", 2, 168), ("PEMS04", 2, 336)])
-def test_large_graph_shapes_run_and_stay_consistent(dataset, B, P, tmp_path):
-    """BASELINE configs[2]/[4] shapes (N=307 with 336 patches; N=883): the same kernels, other tiling branches
-    (several row tiles, P > 176 -> key-split attention, N > 256 -> CUDA-core dP).  Checks: finite fwd+bwd,
-    adjacency invariants, and tensor-core vs CUDA-core node mixing agree (split-bf16 mix is fp32-accurate)."""
-    import subprocess, sys, json
+@pytest.mark.parametrize("dataset,B,P", [("PEMS04", 1, 336)])
+def test_tensor_core_and_cuda_core_node_mixing_agree(dataset, B, P, tmp_path):
+    """The split-bf16 tcgen05 node mixes (default) and the all-CUDA-core fused layer kernel (STEP_B200_GW_MIX=simt)
+    are two implementations of the same fp32 math: forward and gradients must agree (the oracle comparison of this
+    shape is test_step_forward_backward_matches_reference_golden)."""
     from step.step_loss import step_loss
-    n = O.NUM_NODES[dataset]
     model, _, _ = build_step_model(tmp_path, dataset, 0, real_ckpt=False)
     model = model.to(DEV).train()
     model.tsformer.dropout_p = 0.0
@@ -156,8 +157,6 @@ def test_large_graph_shapes_run_and_stay_consistent(dataset, B, P, tmp_path):
         loss = step_loss(y[..., [0]], future.to(DEV)[..., [0]], theta, knn, coeff, null_val=0.0)
         loss.backward()
         outs[mix] = (y.detach().clone(), model.backend.nodevec1.grad.clone(), model.discrete_graph_learning.fc_cat.weight.grad.clone())
-        assert torch.isfinite(y).all() and torch.isfinite(loss)
-        assert set(knn.unique().tolist()) <= {0.0, 1.0} and knn.diagonal(dim1=1, dim2=2).sum().item() == 0
     os.environ.pop("STEP_B200_GW_MIX", None)
     assert (outs["tc"][0] - outs["simt"][0]).abs().mean().item() < 1e-5
     for a, b in zip(outs["tc"][1:], outs["simt"][1:]):
