@@ -126,6 +126,25 @@ int step_ts_layers_fwd(float *x, int S, int P, const step_ts_layer_weights *L, i
 
 
 /* ------------------------------------------------------------------------ *
+ * TSFormer pre-training (stage 1): backward building blocks of the masked auto-encoder
+ *   step/step_arch/tsformer/tsformer.py:71-160, transformer_layers.py:10-20 (the reference differentiates through autograd)
+ * ------------------------------------------------------------------------ */
+/* Backward of step_attn_fwd_f32: dqkv [S*P, 288] from dout [S*P, 96]; out = the forward's output; the dropout mask is
+ * regenerated from (seed, drop_site).  scratch: S*4*P*2 floats. */
+int step_attn_bwd_f32(const float *qkv, const float *out, const float *dout, int S, int P, float drop_p, unsigned long long seed,
+                      unsigned drop_site, float *scratch, float *dqkv, void *stream);
+/* y = LayerNorm96(x + r) * w + b (r may be NULL); sum [M,96] = x + r and stat [M,2] = (mean, rstd) are kept for backward
+ * (either may be NULL for inference). */
+int step_add_layernorm96_fwd(const float *x, const float *r, const float *w, const float *b, long long M, float *sum, float *stat,
+                             float *y, void *stream);
+/* dx [M,96] (the gradient of both x and r), dw [96], db [96]. */
+int step_add_layernorm96_bwd(const float *dy, const float *sum, const float *stat, const float *w, long long M, float *dx,
+                             float *dw, float *db, void *stream);
+/* Inverted dropout with the counter-based generator: y = x * keep / (1 - p); calling it on dy with the same
+ * (seed, site) is the backward.  n must be a multiple of 4. */
+int step_dropout_f32(const float *x, long long n, float drop_p, unsigned long long seed, unsigned site, float *y, void *stream);
+
+/* ------------------------------------------------------------------------ *
  * TSFormer encoder, bf16 tensor-core path (tcgen05.mma + TMEM + TMA bulk copies)
  * Same reference spans as the fp32 path above.  Activations travel between kernels as
  * "tile images": a [T, K] bf16 matrix stored as [T/128][K/8][128 rows][8] (the UMMA K-major
@@ -148,6 +167,12 @@ int step_tc_image_to_rows(const void *img, long long T, int K, float *x, void *s
  *   mode 2 (Nout == 96): LayerNorm(residual image + .) -> out_img and/or out_f32 [T][96]. */
 int step_tc_linear(const void *a_img, const void *w_img, const float *bias, long long T, int K, int Nout, int mode,
                    const void *res_img, const float *ln_w, const float *ln_b, void *out_img, float *out_f32, void *stream);
+/* Same as step_tc_linear for modes 1 and 2 with the dropout site of that epilogue live (inverted dropout on the ReLU
+ * output / on the GEMM result before the residual add; transformer_layers.py:10-11 -> nn.TransformerEncoderLayer's
+ * dropout, dropout1, dropout2), drawn from the counter-based generator keyed by `seed`. */
+int step_tc_linear_drop(const void *a_img, const void *w_img, const float *bias, long long T, int K, int Nout, int mode,
+                        const void *res_img, const float *ln_w, const float *ln_b, void *out_img, float *out_f32,
+                        float drop_p, unsigned long long seed, void *stream);
 /* Bytes of the per-(sequence, head) attention operand images: which = 0 -> Q, 1 -> K (== V). */
 size_t step_tc_attn_image_bytes(int S, int P, int which);
 /* QKV projection of an X image [S*P, 96] straight into the attention operand images (Q pre-scaled by
@@ -249,6 +274,67 @@ int step_dgl_conv_bwd(const float *dy2n, const float *x, int N, int L0, const fl
                       const float *w2, const float *g2, float eps, const float *bn1_stats, const float *bn2_stats,
                       const float *y2, float *dy1n_scratch, float *dw1, float *db1, float *dg1, float *dbe1, float *dw2,
                       float *db2, float *dg2, float *dbe2, void *scratch, void *stream);
+
+/* ------------------------------------------------------------------------ *
+ * Discrete graph learning: dense part of the trunk, feat = BN3(relu(y2n W^T + b))  [N,100]
+ *   step/step_arch/discrete_graph_learning.py:66,134-135 (self.fc, self.bn3; BatchNorm1d over the N nodes)
+ * The three GEMMs (forward, dX, dW) run on tcgen05 with split-bf16 operands (fp32-class accuracy) and stream
+ * y2n / fc.weight exactly once.  [k_begin, k_end) selects the slice of the K axis this call covers (the whole
+ * [0, K) on one GPU; a rank's shard when the trunk is partitioned): x and w are always the full row-major
+ * matrices with row stride K.
+ * ------------------------------------------------------------------------ */
+/* Number of split-K partials step_dgl_fc_fwd writes: partial must hold splits * N * 100 floats. */
+int step_dgl_fc_splits(int N, long long k_begin, long long k_end);
+/* z_raw[n][j] = sum_{k in range} x[n][k] w[j][k]   (no bias: a sharded caller all-reduces z_raw first). */
+int step_dgl_fc_fwd(const float *x /*[N,K]*/, const float *w /*[100,K]*/, int N, long long K, long long k_begin,
+                    long long k_end, float *partial, float *z_raw /*[N,100]*/, void *stream);
+/* z = z_raw + bias (in place), feat = BN(relu(z)).  stats [3][100] = mean, biased var, rstd: written when
+ * training != 0 (batch statistics over the N nodes); when training == 0 rows 0/1 hold the running statistics. */
+int step_dgl_fc_bn_fwd(float *z, const float *bias, const float *gamma, const float *beta, int N, float eps, int training,
+                       float *stats, float *feat /*[N,100]*/, void *stream);
+/* Backward of step_dgl_fc_bn_fwd (training mode): g = dL/dz_raw [N,100], dgamma/dbeta/dbias [100]. */
+int step_dgl_fc_bn_bwd(const float *dfeat, const float *z, const float *gamma, const float *stats, int N, float *g,
+                       float *dgamma, float *dbeta, float *dbias, void *stream);
+/* dx[n][k] = sum_j g[n][j] w[j][k],  dw[j][k] = dw_scale * sum_n g[n][j] x[n][k]   for k in [k_begin, k_end)
+ * (k_begin a multiple of 64; entries outside the range are left untouched). */
+int step_dgl_fc_bwd(const float *g, const float *x, const float *w, int N, long long K, long long k_begin, long long k_end,
+                    float dw_scale, float *dx /*[N,K]*/, float *dw /*[100,K]*/, void *stream);
+
+/* ------------------------------------------------------------------------ *
+ * General fp32 GEMM on tcgen05 with split-bf16 operands (fp32-class accuracy) for the mid-size dense products the
+ * reference runs through nn.Linear / Conv2d(1x1) / torch.matmul on cuBLAS:
+ *   Graph WaveNet epilogue fc_his / end_conv_1 / end_conv_2 (graphwavenet/model.py:215-220), the fc_out halves of
+ *   discrete graph learning (discrete_graph_learning.py:148-151), TSFormer pre-training backward (tsformer.py:71-160).
+ *   C[M,N] (+)= alpha * sum_k opA(m,k) opB(n,k) [+ bias[n]] [epilogue]
+ *   transA == 0: A row-major [M][K];  transA != 0: A row-major [K][M]
+ *   transB == 0: B row-major [N][K] (an nn.Linear weight);  transB != 0: B row-major [K][N]
+ *   epilogue 0 none, 1 ReLU, 2 mask: C = acc * (aux > 0), 3: C = relu(relu(acc + bias) + aux), aux_out = relu(acc + bias)
+ *   ksplit > 1: the K range is split over grid.z and accumulated with fp32 atomics (epilogue 0 only).
+ * ------------------------------------------------------------------------ */
+int step_gemm_f32(const float *A, long long lda, int transA, const float *B, long long ldb, int transB, int M, int N, int K,
+                  float alpha, const float *bias, int epilogue, const float *aux, long long ldaux, float *aux_out, int accumulate,
+                  int ksplit, float *C, long long ldc, void *stream);
+/* out[n] = sum_m x[m][n]  (bias gradients);  dz = dy * (y > 0)  (ReLU backward). */
+int step_colsum_f32(const float *x, long long M, int N, long long ld, float *out, void *stream);
+int step_relu_bwd_f32(const float *dy, const float *y, long long n, float *dz, void *stream);
+
+/* ------------------------------------------------------------------------ *
+ * Graph WaveNet prologue, forward + backward   step/step_arch/graphwavenet/model.py:121-130,144-166
+ * ------------------------------------------------------------------------ */
+/* x0 [B,T+1,N,32] = start_conv(left-padded history[..., 0:2]); history [B,T,N,C], w [32,2], bias [32]. */
+int step_gw_start_fwd(const float *history, int B, int T, int N, int C, const float *w, const float *bias, float *x0, void *stream);
+/* dw_db [96] = (dW [32,2] | db [32]) from dx0 [B,T+1,N,32]. */
+int step_gw_start_bwd(const float *history, int B, int T, int N, int C, const float *dx0, float *dw_db, void *stream);
+/* P1 = D^-1 (A + I), P2 = D'^-1 (A^T + I) for adj [B,N,N]; deg [2,B,N] (row / column degrees + 1) is kept for backward. */
+int step_gw_supports_fwd(const float *adj, int B, int N, float *deg, float *P1, float *P2, void *stream);
+/* dadj [B,N,N] from dP1, dP2; dots: [2,B,N] scratch. */
+int step_gw_supports_bwd(const float *dP1, const float *dP2, const float *P1, const float *P2, const float *deg, int B, int N,
+                         float *dots, float *dadj, void *stream);
+/* P3 [N,N] = softmax_row(relu(E1 E2)), E1 [N,R], E2 [R,N] (R = 10). */
+int step_gw_adp_fwd(const float *E1, const float *E2, int N, int R, float *P3, void *stream);
+/* dE1 [N,R], dE2 [R,N] from dP3; scratch: [N,N] floats. */
+int step_gw_adp_bwd(const float *E1, const float *E2, const float *P3, const float *dP3, int N, int R, float *scratch, float *dE1,
+                    float *dE2, void *stream);
 
 /* ------------------------------------------------------------------------ *
  * Graph WaveNet layer stack (8 x gated dilated conv + skip + diffusion GCN + BN)

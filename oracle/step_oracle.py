@@ -52,6 +52,10 @@ def _drop(x: Tensor, p: float) -> Tensor:
     return F.dropout(x, p, training=True) if p > 0.0 else x
 
 
+USE_SDPA = False      # bench.py's GPU-eager comparator sets this: torch's nn.TransformerEncoderLayer (what the reference
+                      # instantiates, transformer_layers.py:10-11) reaches F.scaled_dot_product_attention in train mode
+
+
 def encoder_layer(sd: SD, pre: str, z: Tensor, heads: int, p_drop: float = 0.0) -> Tensor:
     """One post-norm ``nn.TransformerEncoderLayer(d, heads, 4d, dropout)`` with ReLU
     (step/step_arch/tsformer/transformer_layers.py:10-11; formula of the Python
@@ -65,9 +69,12 @@ def encoder_layer(sd: SD, pre: str, z: Tensor, heads: int, p_drop: float = 0.0) 
     q = q.view(S, P, heads, hd).transpose(1, 2)
     k = k.view(S, P, heads, hd).transpose(1, 2)
     v = v.view(S, P, heads, hd).transpose(1, 2)
-    att = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
-    att = _drop(att, p_drop)
-    o = (att @ v).transpose(1, 2).reshape(S, P, d)
+    if USE_SDPA:
+        o = F.scaled_dot_product_attention(q, k, v, dropout_p=p_drop).transpose(1, 2).reshape(S, P, d)
+    else:
+        att = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
+        att = _drop(att, p_drop)
+        o = (att @ v).transpose(1, 2).reshape(S, P, d)
     o = o @ sd[pre + "self_attn.out_proj.weight"].t() + sd[pre + "self_attn.out_proj.bias"]
     z = _layer_norm(z + _drop(o, p_drop), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"])
     f = torch.relu(z @ sd[pre + "linear1.weight"].t() + sd[pre + "linear1.bias"])
@@ -209,7 +216,7 @@ def knn_prior(hidden: Tensor, k_total: int) -> Tensor:
     vals, idx = torch.topk(sim, k_total, dim=-1)
     res = torch.zeros_like(sim).scatter_(-1, idx, vals)
     adj = (res != 0).to(sim.dtype).view(B, N, N)
-    eye = torch.eye(N, dtype=torch.bool)
+    eye = torch.eye(N, dtype=torch.bool, device=sim.device)
     return adj.masked_fill(eye, 0.0).detach()
 
 
@@ -225,7 +232,7 @@ def discrete_graph_learning(sd: SD, long_history: Tensor, node_feats: Tensor, k:
     logits = edge_logits(sd, feat, pre)                               # identical for every sample (Appx D.1)
     bern = logits.unsqueeze(0).expand(B, N * N, 2)
     y = gumbel_hard_sample(bern, uniform)
-    eye = torch.eye(N, dtype=torch.bool)
+    eye = torch.eye(N, dtype=torch.bool, device=y.device)
     sampled = y[..., 0].reshape(B, N, N).masked_fill(eye, 0.0)
     adj_knn = knn_prior(hidden, k * N)
     return bern, hidden, adj_knn, sampled
@@ -237,7 +244,7 @@ def discrete_graph_learning(sd: SD, long_history: Tensor, node_feats: Tensor, k:
 def random_walk(adj: Tensor) -> Tensor:
     """GraphWaveNet._calculate_random_walk_matrix, graphwavenet/model.py:121-130: D^-1 (A + I)."""
     N = adj.shape[1]
-    a = adj + torch.eye(N, dtype=adj.dtype)
+    a = adj + torch.eye(N, dtype=adj.dtype, device=adj.device)
     d = a.sum(2)
     dinv = torch.where(d == 0, torch.zeros_like(d), 1.0 / d)
     return dinv.unsqueeze(-1) * a

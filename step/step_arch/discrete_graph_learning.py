@@ -11,7 +11,6 @@ import pickle
 
 import torch
 from torch import nn
-import torch.nn.functional as F
 
 from step_b200 import ops
 
@@ -29,26 +28,6 @@ def _load_pkl(path):
         except UnicodeDecodeError:
             f.seek(0)
             return pickle.load(f, encoding="latin1")
-
-
-class _Tf32Linear(torch.autograd.Function):
-    """y = x W^T + b with TF32 tensor-core GEMMs in forward AND backward (the flag is re-applied in backward
-    because autograd runs it outside the forward's scope)."""
-
-    @staticmethod
-    def forward(ctx, x, w, b):
-        ctx.save_for_backward(x, w)
-        return torch.addmm(b, x, w.t())
-
-    @staticmethod
-    def backward(ctx, g):
-        x, w = ctx.saved_tensors
-        prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
-        try:
-            return g @ w, g.t() @ x, g.sum(0)
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 class DiscreteGraphLearning(nn.Module):
@@ -81,25 +60,6 @@ class DiscreteGraphLearning(nn.Module):
         self._feats_dev = None
 
     @staticmethod
-    def _batch_norm(x, bn, training):
-        """BatchNorm1d semantics (batch statistics + running-stat update in train(), running statistics in
-        eval()) written as plain reductions: cuDNN's spatial-BN kernels take ~20 ms on the [N, C, 24k] trunk
-        activations, these take <1 ms."""
-        dims = (0, 2) if x.dim() == 3 else (0,)
-        shape = (1, -1, 1) if x.dim() == 3 else (1, -1)
-        if training:
-            var, mean = torch.var_mean(x, dim=dims, unbiased=False)
-            with torch.no_grad():
-                n = x.numel() // x.shape[1]
-                bn.running_mean.mul_(1 - bn.momentum).add_(mean, alpha=bn.momentum)
-                bn.running_var.mul_(1 - bn.momentum).add_(var, alpha=bn.momentum * n / max(n - 1, 1))
-                bn.num_batches_tracked += 1
-        else:
-            mean, var = bn.running_mean, bn.running_var
-        scale = bn.weight * torch.rsqrt(var + bn.eps)
-        return x * scale.view(shape) + (bn.bias - mean * scale).view(shape)
-
-    @staticmethod
     @torch.no_grad()
     def _update_running(bn, mean, var, count):
         bn.running_mean.mul_(1 - bn.momentum).add_(mean, alpha=bn.momentum)
@@ -111,9 +71,9 @@ class DiscreteGraphLearning(nn.Module):
         scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
         return torch.stack([bn.running_mean, bn.running_var, scale, bn.bias - bn.running_mean * scale]).contiguous()
 
-    def _global_feature(self, device, tf32_fc=False):
+    def _global_feature(self, device):
         """Batch-invariant node embedding, reference :131-135.  [N, 100].  conv1/bn1/conv2/bn2 run in the fused
-        trunk kernels (csrc/trunk.cu); the [N, dim_fc] x [dim_fc, 100] Linear is a plain library GEMM."""
+        trunk kernels (csrc/trunk.cu); the [N, dim_fc] x [dim_fc, 100] Linear + ReLU + bn3 in csrc/trunk_fc.cu."""
         if self._feats_dev is None or self._feats_dev.device != device:
             self._feats_dev = self.node_feats.to(device).t().contiguous()          # [N, L], uploaded once
         t = self.training
@@ -125,19 +85,12 @@ class DiscreteGraphLearning(nn.Module):
             n, L0 = self._feats_dev.shape
             self._update_running(self.bn1, s1[0], s1[1], n * (L0 - 9))
             self._update_running(self.bn2, s2[0], s2[1], n * (L0 - 18))
-        if tf32_fc:
-            # performance precision: the [N, dim_fc] x [dim_fc, 100] Linear (and its two backward GEMMs) on the tensor
-            # cores in TF32 (fp32 accumulate); the fp32 parity mode keeps the exact fp32 GEMM
-            prev = torch.backends.cuda.matmul.allow_tf32
-            torch.backends.cuda.matmul.allow_tf32 = True
-            try:
-                x = _Tf32Linear.apply(y2n, self.fc.weight, self.fc.bias)
-            finally:
-                torch.backends.cuda.matmul.allow_tf32 = prev
-            x = F.relu(x)
-        else:
-            x = F.relu(self.fc(y2n))
-        return self._batch_norm(x, self.bn3, t)
+        # fc + ReLU + bn3: split-bf16 tcgen05 GEMMs (fp32-class accuracy in both precision modes), csrc/trunk_fc.cu
+        e3 = None if t else torch.stack([self.bn3.running_mean, self.bn3.running_var]).contiguous()
+        feat, s3 = ops.TrunkFc.apply(y2n, self.fc.weight, self.fc.bias, self.bn3.weight, self.bn3.bias, self.bn3.eps, t, e3, None)
+        if t:
+            self._update_running(self.bn3, s3[0], s3[1], y2n.shape[0])
+        return feat
 
     def get_k_nn_neighbor(self, data, k=11 * 207, metric="cosine"):
         if metric != "cosine":
@@ -148,11 +101,13 @@ class DiscreteGraphLearning(nn.Module):
     def forward(self, long_term_history, tsformer):
         """long_term_history [B, P*L, N, C] -> (bernoulli_unnorm [B,N*N,2], hidden [B,N,P,d], adj_knn, sampled_adj)."""
         batch_size, _, num_nodes, _ = long_term_history.shape
-        feat = self._global_feature(long_term_history.device, tf32_fc=getattr(tsformer, "precision", "fp32") == "bf16")
+        feat = self._global_feature(long_term_history.device)
         hidden_states = tsformer(long_term_history[..., [0]])
         half = self.embedding_dim
-        ut = self.fc_out.weight[:, :half] @ feat.t()                          # [100, N]  sender half (index j)
-        v = feat @ self.fc_out.weight[:, half:].t() + self.fc_out.bias        # [N, 100]  receiver half (index i)
+        # the two halves of fc_out (reference :148-151 after the one-hot gathers), split-bf16 tcgen05 GEMMs
+        w_send, w_recv = self.fc_out.weight[:, :half].contiguous(), self.fc_out.weight[:, half:].contiguous()
+        ut = ops.Linear.apply(w_send, feat, None, False)                      # [100, N]  sender half (index j)
+        v = ops.Linear.apply(feat, w_recv, self.fc_out.bias, False)           # [N, 100]  receiver half (index i)
         logits, theta = ops.EdgeLogits.apply(ut, v, self.fc_cat.weight, self.fc_cat.bias)
         self.theta = theta
         bernoulli_unnorm = logits.view(1, num_nodes * num_nodes, 2).expand(batch_size, -1, -1)

@@ -2,13 +2,13 @@
 
 Constructor / ``forward`` signature and state-dict keys follow
 ``step/step_arch/graphwavenet/model.py:51-224`` of the reference.  The eight gated-TCN + diffusion-GCN
-layers run in ``step_b200.ops.GWNetStack`` (one fused launch per layer, hand-written backward); the
-tiny prologue (2->32 start conv, support normalisation) and epilogue (fc_his, end convs: plain
-matmuls) stay in torch so that autograd chains them to the fused stack.
+layers run in ``step_b200.ops.GWNetStack`` (hand-written forward and backward); the prologue (2->32 start
+conv, support normalisation, adaptive adjacency: ``csrc/gw_glue.cu``) and the epilogue (fc_his, end convs:
+split-bf16 tcgen05 GEMMs, ``csrc/tc_gemm.cu``) are autograd Functions over the same C ABI - no library GEMM
+or eager elementwise kernel is left on the path.
 """
 import torch
 from torch import nn
-import torch.nn.functional as F
 
 from step_b200 import ops
 
@@ -123,12 +123,11 @@ class GraphWaveNet(nn.Module):
         if L + 1 != self.receptive_field:
             raise NotImplementedError("step_b200 GraphWaveNet expects 12 history steps (receptive field 13)")
         n = self.blocks * self.layers
-        # prologue: channels 0:2, one zero step on the left, 2->32 start conv, directly in [B,T,N,32]
-        x = F.pad(input[..., :2], (0, 0, 0, 0, 1, 0))
-        x0 = x @ self.start_conv.weight.view(32, 2).t() + self.start_conv.bias
-        P1 = self._random_walk(sampled_adj)
-        P2 = self._random_walk(sampled_adj.transpose(-1, -2))
-        P3 = F.softmax(F.relu(torch.mm(self.nodevec1, self.nodevec2)), dim=1)
+        # prologue (csrc/gw_glue.cu): start conv on the left-padded history straight into [B,13,N,32], both random-walk
+        # supports of the sampled graph, the adaptive adjacency
+        x0 = ops.GwStart.apply(input, self.start_conv.weight, self.start_conv.bias)
+        P1, P2 = ops.GwSupports.apply(sampled_adj)
+        P3 = ops.GwAdaptive.apply(self.nodevec1, self.nodevec2)
         self._calls += 1
         seed = (torch.initial_seed() + 0x85EBCA77 * self._calls) & (2 ** 63 - 1)
         training = self.training
@@ -137,7 +136,9 @@ class GraphWaveNet(nn.Module):
                                               eval_stats, n, *self._flat_layer_params())
         if training:
             self._update_running_stats(bn_stats, B, N)
-        hs = self.fc_his(hidden_states)                                   # [B,N,256]
-        x = F.relu(skip + hs)
-        x = F.relu(x @ self.end_conv_1.weight.view(512, 256).t() + self.end_conv_1.bias)
-        return x @ self.end_conv_2.weight.view(-1, 512).t() + self.end_conv_2.bias   # [B,N,12]
+        # epilogue (csrc/tc_gemm.cu): fc_his, skip add, end convs as split-bf16 tcgen05 GEMMs with fused bias/ReLU epilogues
+        out = ops.GwEpilogue.apply(hidden_states.reshape(B * N, -1), skip.view(B * N, 256),
+                                   self.fc_his[0].weight, self.fc_his[0].bias, self.fc_his[2].weight, self.fc_his[2].bias,
+                                   self.end_conv_1.weight.view(512, 256), self.end_conv_1.bias,
+                                   self.end_conv_2.weight.view(-1, 512), self.end_conv_2.bias)
+        return out.view(B, N, -1)                                         # [B,N,12]

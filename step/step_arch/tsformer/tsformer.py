@@ -208,8 +208,8 @@ class TSFormer(nn.Module):
         """``mode="pre-train"`` forward (reference tsformer.py:71-160): embed all patches, encode the unmasked 25 %,
         ``enc_2_dec_emb``, append mask tokens (+ positional embedding of the masked positions), one decoder layer,
         ``decoder_norm``, ``output_layer``; returns (reconstruction of the masked patches, their ground truth), both
-        ``[B, r*P*L, N]``.  Forward only on the fp32 kernels: the masked encoder's *backward* (stage-1 training) is
-        listed as next work in DESIGN.md, so the outputs carry no autograd graph.
+        ``[B, r*P*L, N]``.  Inference flavour on the fused fp32 kernels (no autograd graph); training goes through
+        :meth:`pretrain_forward_autograd`.
         history_data: [B, N, 1, P*L] view."""
         B, N, _, T = history_data.shape
         L, d = self.patch_size, self.embed_dim
@@ -243,12 +243,52 @@ class TSFormer(nn.Module):
         label_masked = label.reshape(B, N, -1).transpose(1, 2)
         return recon_masked, label_masked
 
+    def pretrain_forward_autograd(self, history_data):
+        """The same ``mode="pre-train"`` computation as :meth:`pretrain_forward`, built from differentiable ops (every one
+        a hand-written kernel behind ``step_b200.ops``: split-bf16 tcgen05 GEMMs for the dense layers, fp32 attention /
+        LayerNorm / dropout kernels with hand-written backward) so that stage 1 of STEP - the masked auto-encoder of
+        reference tsformer.py:71-160 - trains on the GPU.  Gradients reach all 72 parameters."""
+        B, N, _, T = history_data.shape
+        L, d = self.patch_size, self.embed_dim
+        P = T // L
+        S = B * N
+        drop = self.dropout_p if self.training else 0.0
+        seed = self._next_seed() if drop > 0 else 0
+        emb, pos = self.patch_embedding.input_embedding, self.positional_encoding.position_embedding
+        unmasked, masked = self.mask()
+        dev = history_data.device
+        ui = torch.as_tensor(unmasked, device=dev, dtype=torch.long)
+        mi = torch.as_tensor(masked, device=dev, dtype=torch.long)
+        nu, nm = len(unmasked), len(masked)
+        # --- patch + positional embedding (dropout on every token, positional_encoding.py:32), keep the unmasked 25 %
+        patches = history_data[:, :, self.selected_feature, :].reshape(S * P, L)
+        tok = ops.Linear.apply(patches, emb.weight.view(d, L), emb.bias, False).view(S, P, d) + pos[:P]
+        tok = ops.dropout(tok.reshape(S * P, d), drop, seed, 1).view(S, P, d)
+        z = (tok.index_select(1, ui) * math.sqrt(d)).reshape(S * nu, d)
+        for i, lw in enumerate(self.encoder.kernel_weights()):
+            z = ops.transformer_layer_train(z, S, nu, lw, drop, seed, 16 * (i + 1))
+        z = ops.AddLayerNorm.apply(z, None, self.encoder_norm.weight, self.encoder_norm.bias)
+        # --- decoder over [unmasked | mask tokens + positional embedding of the masked positions]
+        dec_u = ops.Linear.apply(z, self.enc_2_dec_emb.weight, self.enc_2_dec_emb.bias, False).view(S, nu, d)
+        dec_m = (self.mask_token.view(1, 1, d) + pos[mi].unsqueeze(0)).expand(S, nm, d)
+        dec_m = ops.dropout(dec_m.reshape(S * nm, d), drop, seed, 2).view(S, nm, d)
+        z = (torch.cat([dec_u, dec_m], dim=1) * math.sqrt(d)).reshape(S * P, d)
+        for i, lw in enumerate(self.decoder.kernel_weights()):
+            z = ops.transformer_layer_train(z, S, P, lw, drop, seed, 160 + 16 * i)
+        z = ops.AddLayerNorm.apply(z, None, self.decoder_norm.weight, self.decoder_norm.bias)
+        recon = ops.Linear.apply(z, self.output_layer.weight, self.output_layer.bias, False).view(B, N, P, L)
+        recon_masked = recon[:, :, nu:, :].reshape(B, N, -1).transpose(1, 2)
+        label = history_data[:, :, self.selected_feature, :].reshape(B, N, P, L).index_select(2, mi)
+        return recon_masked, label.reshape(B, N, -1).transpose(1, 2)
+
     def forward(self, history_data: torch.Tensor, future_data: torch.Tensor = None, batch_seen: int = None,
                 epoch: int = None, **kwargs) -> torch.Tensor:
         """history_data: [B, L*P, N, 1].  forecasting mode -> [B, N, P, d]."""
         history_data = history_data.permute(0, 2, 3, 1)     # B, N, 1, L*P (view)
         if self.mode == "pre-train":
-            return self.pretrain_forward(history_data)
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                return self.pretrain_forward_autograd(history_data)       # stage-1 training
+            return self.pretrain_forward(history_data)                    # inference: fused kernels, no graph
         with torch.no_grad():
             hidden_states_full, _, _ = self.encoding(history_data, mask=False)
         return hidden_states_full

@@ -2,8 +2,8 @@
 host -> running device -> channel selection -> ``model(history_data=..., future_data=None, batch_seen, epoch)`` -> the
 2-tuple (reconstruction of the masked patches, their ground truth) that the reference hands to ``cfg.TRAIN.LOSS``.
 
-Only the forward direction exists on the B200 kernels so far: ``forward`` / ``loss_iters`` evaluate
-the pre-training objective, ``train_iters`` raises until the masked encoder's backward is built."""
+``train_iters`` returns the differentiable pre-training loss (the masked auto-encoder's backward runs on hand-written
+kernels, ``TSFormer.pretrain_forward_autograd``); ``loss_iters`` evaluates it without a graph on the fused kernels."""
 import torch
 
 
@@ -34,6 +34,9 @@ class TSFormerRunner:
         mean, std = self.scaler["mean"], self.scaler["std"]
         return self.loss(rec * std + mean, label * std + mean, null_val=self.null_val)
 
-    def train_iters(self, epoch: int, iter_index: int, data: tuple):
-        raise NotImplementedError("TSFormer pre-training needs the backward of the masked encoder/decoder, which the B200 "
-                                  "kernels do not provide yet (DESIGN.md section 8); the forward objective is loss_iters()")
+    def train_iters(self, epoch: int, iter_index: int, data: tuple) -> torch.Tensor:
+        """reference base_tsf_runner.py:225-255 for the 2-tuple model: forward, re-scale, ``cfg.TRAIN.LOSS``; the caller
+        (easytorch's ``backward``) calls ``.backward()`` on the returned loss, clips and steps the optimiser."""
+        rec, label = self.forward(data, epoch=epoch, iter_num=(epoch - 1) * self.iter_per_epoch + iter_index, train=True)
+        mean, std = self.scaler["mean"], self.scaler["std"]
+        return self.loss(rec * std + mean, label * std + mean, null_val=self.null_val)

@@ -179,6 +179,16 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---- 256-bit streaming load (sm_100: LDG.E.256): 8 consecutive floats, 32-byte aligned, read-only path, no L1 allocation ----
+struct f8 { float v[8]; };
+__device__ __forceinline__ f8 ld256_nc(const float *p) {
+  f8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+
 // ---- bf16 packing -------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

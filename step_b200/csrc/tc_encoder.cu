@@ -941,6 +941,23 @@ extern "C" int step_tc_linear(const void *a_img, const void *w_img, const float 
   return tc_linear_launch(a, (cudaStream_t)stream);
 }
 
+extern "C" int step_tc_linear_drop(const void *a_img, const void *w_img, const float *bias, long long T, int K, int Nout, int mode,
+                                   const void *res_img, const float *ln_w, const float *ln_b, void *out_img, float *out_f32,
+                                   float drop_p, unsigned long long seed, void *stream) {
+  STEP_REQUIRE(a_img && w_img && bias && T > 0, "tc_linear_drop: bad argument");
+  STEP_REQUIRE(mode == TCM_RELU_IMG || mode == TCM_RESLN, "tc_linear_drop: dropout sites exist in modes 1 and 2 only");
+  STEP_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "tc_linear_drop: drop_p must be in [0, 1)");
+  if (mode == TCM_RESLN) STEP_REQUIRE(res_img && ln_w && ln_b && Nout == 96, "tc_linear_drop: residual+LN needs its operands");
+  TcLinearArgs a{};
+  a.A = (const uint8_t *)a_img; a.W = (const uint8_t *)w_img; a.bias = bias;
+  a.MT = (int)((T + 127) / 128); a.K = K; a.Nout = Nout; a.mode = mode; a.T = T;
+  a.res = (const uint8_t *)res_img; a.ln_w = ln_w; a.ln_b = ln_b;
+  a.out_img = (uint8_t *)out_img; a.out_f32 = out_f32;
+  a.dscale = 1.f;
+  if (drop_p > 0.f) { a.thr16 = (uint32_t)(drop_p * 65536.0f); a.dscale = 1.f / (1.f - drop_p); a.key = rng_key(seed, 0); }
+  return tc_linear_launch(a, (cudaStream_t)stream);
+}
+
 extern "C" size_t step_tc_attn_image_bytes(int S, int P, int which) {
   const int Pk = (P + 15) / 16 * 16, RT = (P + 127) / 128;
   if (which == 0) return (size_t)S * 4 * RT * 6144;

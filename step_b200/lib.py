@@ -48,6 +48,10 @@ SIGNATURES = {
                                   C.c_uint, vp]),
     "step_attn_fwd_f32": (C.c_int, [f32p, f32p, C.c_int, C.c_int, C.c_float, ull, C.c_uint, vp]),
     "step_layernorm96_f32": (C.c_int, [f32p, f32p, f32p, f32p, ll, vp]),
+    "step_attn_bwd_f32": (C.c_int, [f32p, f32p, f32p, C.c_int, C.c_int, C.c_float, ull, C.c_uint, f32p, f32p, vp]),
+    "step_add_layernorm96_fwd": (C.c_int, [f32p, f32p, f32p, f32p, ll, f32p, f32p, f32p, vp]),
+    "step_add_layernorm96_bwd": (C.c_int, [f32p, f32p, f32p, f32p, ll, f32p, f32p, f32p, vp]),
+    "step_dropout_f32": (C.c_int, [f32p, ll, C.c_float, ull, C.c_uint, f32p, vp]),
     "step_ts_encoder_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "step_ts_encoder_fwd": (C.c_int, [f32p, ll, ll, ll, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p,
                                       C.POINTER(TsLayerWeights), C.c_int, f32p, f32p, f32p, vp, C.c_size_t, C.c_int,
@@ -58,6 +62,7 @@ SIGNATURES = {
     "step_tc_rows_to_image": (C.c_int, [f32p, ll, C.c_int, vp, vp]),
     "step_tc_image_to_rows": (C.c_int, [vp, ll, C.c_int, f32p, vp]),
     "step_tc_linear": (C.c_int, [vp, vp, f32p, ll, C.c_int, C.c_int, C.c_int, vp, f32p, f32p, vp, f32p, vp]),
+    "step_tc_linear_drop": (C.c_int, [vp, vp, f32p, ll, C.c_int, C.c_int, C.c_int, vp, f32p, f32p, vp, f32p, C.c_float, ull, vp]),
     "step_tc_attn_image_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "step_tc_qkv": (C.c_int, [vp, vp, f32p, C.c_int, C.c_int, vp, vp, vp, vp]),
     "step_tc_attention": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, ull, vp]),
@@ -78,6 +83,21 @@ SIGNATURES = {
                                     C.c_float, f32p, f32p, f32p, vp, vp]),
     "step_dgl_conv_fwd": (C.c_int, [f32p, C.c_int, C.c_int] + [f32p] * 8 + [C.c_float, C.c_int, f32p, f32p, f32p, f32p, vp, vp]),
     "step_dgl_conv_bwd": (C.c_int, [f32p, f32p, C.c_int, C.c_int] + [f32p] * 5 + [C.c_float] + [f32p] * 12 + [vp, vp]),
+    "step_dgl_fc_splits": (C.c_int, [C.c_int, ll, ll]),
+    "step_dgl_fc_fwd": (C.c_int, [f32p, f32p, C.c_int, ll, ll, ll, f32p, f32p, vp]),
+    "step_dgl_fc_bn_fwd": (C.c_int, [f32p, f32p, f32p, f32p, C.c_int, C.c_float, C.c_int, f32p, f32p, vp]),
+    "step_dgl_fc_bn_bwd": (C.c_int, [f32p, f32p, f32p, f32p, C.c_int, f32p, f32p, f32p, f32p, vp]),
+    "step_dgl_fc_bwd": (C.c_int, [f32p, f32p, f32p, C.c_int, ll, ll, ll, C.c_float, f32p, f32p, vp]),
+    "step_gemm_f32": (C.c_int, [f32p, ll, C.c_int, f32p, ll, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, f32p, C.c_int, f32p, ll,
+                                f32p, C.c_int, C.c_int, f32p, ll, vp]),
+    "step_colsum_f32": (C.c_int, [f32p, ll, C.c_int, ll, f32p, vp]),
+    "step_relu_bwd_f32": (C.c_int, [f32p, f32p, ll, f32p, vp]),
+    "step_gw_start_fwd": (C.c_int, [f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, vp]),
+    "step_gw_start_bwd": (C.c_int, [f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, vp]),
+    "step_gw_supports_fwd": (C.c_int, [f32p, C.c_int, C.c_int, f32p, f32p, f32p, vp]),
+    "step_gw_supports_bwd": (C.c_int, [f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_int, f32p, f32p, vp]),
+    "step_gw_adp_fwd": (C.c_int, [f32p, f32p, C.c_int, C.c_int, f32p, vp]),
+    "step_gw_adp_bwd": (C.c_int, [f32p, f32p, f32p, f32p, C.c_int, C.c_int, f32p, f32p, f32p, vp]),
     "step_gwnet_stash_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "step_gwnet_stack_fwd": (C.c_int, [f32p, f32p, f32p, f32p, C.POINTER(GwLayerParams), C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_float, ull, f32p, f32p, f32p, vp]),

@@ -143,6 +143,102 @@ def attention(qkv: Tensor, S: int, P: int, drop_p: float = 0.0, seed: int = 0) -
 
 
 # --------------------------------------------------------------------------- #
+# differentiable building blocks of the TSFormer pre-training path (stage 1)
+# --------------------------------------------------------------------------- #
+class Attention(torch.autograd.Function):
+    """softmax(q k^T / sqrt(24)) v over S sequences of P tokens, 4 heads (fp32 kernels), with hand-written backward;
+    attention-probability dropout is regenerated in backward from (seed, site 0)."""
+
+    @staticmethod
+    def forward(ctx, qkv, S, P, drop_p, seed):
+        qkv = _f32(qkv, "qkv")
+        out = attention(qkv, S, P, drop_p, seed)
+        ctx.save_for_backward(qkv, out)
+        ctx.cfg = (int(S), int(P), float(drop_p), int(seed))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out = ctx.saved_tensors
+        S, P, drop_p, seed = ctx.cfg
+        dout = _f32(dout, "dout")
+        st = _enter(qkv)
+        scratch = torch.empty(S * 4 * P * 2, device=qkv.device, dtype=torch.float32)
+        dqkv = torch.empty_like(qkv)
+        check(_L().step_attn_bwd_f32(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), S, P, drop_p, seed, 0, scratch.data_ptr(),
+                                     dqkv.data_ptr(), st), "step_attn_bwd_f32")
+        launch_counter["kernels"] += 2
+        return dqkv, None, None, None, None
+
+
+class AddLayerNorm(torch.autograd.Function):
+    """LayerNorm96(x + r) (r may be None): the post-norm residual blocks and the final norms of the transformer."""
+
+    @staticmethod
+    def forward(ctx, x, r, w, b):
+        x, w, b = _f32(x, "x"), _f32(w, "ln.weight"), _f32(b, "ln.bias")
+        r = None if r is None else _f32(r, "r")
+        M = x.shape[0]
+        st = _enter(x)
+        s_, stat, y = torch.empty_like(x), torch.empty(M, 2, device=x.device, dtype=torch.float32), torch.empty_like(x)
+        check(_L().step_add_layernorm96_fwd(x.data_ptr(), _p(r), w.data_ptr(), b.data_ptr(), M, s_.data_ptr(), stat.data_ptr(),
+                                            y.data_ptr(), st), "step_add_layernorm96_fwd")
+        launch_counter["kernels"] += 1
+        ctx.save_for_backward(s_, stat, w)
+        ctx.has_r = r is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        s_, stat, w = ctx.saved_tensors
+        dy = _f32(dy, "dy")
+        st = _enter(dy)
+        dx = torch.empty_like(dy)
+        dw, db = torch.empty(96, device=dy.device, dtype=torch.float32), torch.empty(96, device=dy.device, dtype=torch.float32)
+        check(_L().step_add_layernorm96_bwd(dy.data_ptr(), s_.data_ptr(), stat.data_ptr(), w.data_ptr(), dy.shape[0], dx.data_ptr(),
+                                            dw.data_ptr(), db.data_ptr(), st), "step_add_layernorm96_bwd")
+        launch_counter["kernels"] += 1
+        return dx, (dx if ctx.has_r else None), dw, db
+
+
+class Dropout(torch.autograd.Function):
+    """Inverted dropout from the counter-based generator; the backward is the same kernel on the gradient."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed, site):
+        ctx.cfg = (float(p), int(seed) & (2**64 - 1), int(site))
+        return Dropout._run(_f32(x, "x"), *ctx.cfg)
+
+    @staticmethod
+    def _run(x, p, seed, site):
+        st = _enter(x)
+        y = torch.empty_like(x)
+        check(_L().step_dropout_f32(x.data_ptr(), x.numel(), p, seed, site, y.data_ptr(), st), "step_dropout_f32")
+        launch_counter["kernels"] += 1
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return Dropout._run(_f32(dy, "dy"), *ctx.cfg), None, None, None
+
+
+def dropout(x: Tensor, p: float, seed: int, site: int) -> Tensor:
+    return Dropout.apply(x, p, seed, site) if p > 0.0 else x
+
+
+def transformer_layer_train(z: Tensor, S: int, P: int, lw: Dict[str, Tensor], drop_p: float, seed: int, site: int) -> Tensor:
+    """One post-norm nn.TransformerEncoderLayer(96, 4, 384) on tokens z [S*P, 96] with autograd (stage-1 training path;
+    the forecasting path uses the fused inference kernels)."""
+    qkv = Linear.apply(z, lw["in_proj_w"], lw["in_proj_b"], False)
+    o = Attention.apply(qkv, S, P, drop_p, (seed + 7919 * site) & (2**63 - 1))
+    o = dropout(Linear.apply(o, lw["out_proj_w"], lw["out_proj_b"], False), drop_p, seed, site + 2)
+    z1 = AddLayerNorm.apply(z, o, lw["norm1_w"], lw["norm1_b"])
+    f = dropout(Linear.apply(z1, lw["lin1_w"], lw["lin1_b"], True), drop_p, seed, site + 3)
+    f = dropout(Linear.apply(f, lw["lin2_w"], lw["lin2_b"], False), drop_p, seed, site + 4)
+    return AddLayerNorm.apply(z1, f, lw["norm2_w"], lw["norm2_b"])
+
+
+# --------------------------------------------------------------------------- #
 # kNN prior
 # --------------------------------------------------------------------------- #
 def cosine_gram(x: Tensor) -> Tensor:
@@ -331,6 +427,199 @@ class GWNetStack(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------- #
+# general split-bf16 tcgen05 GEMM + the dense layers built on it
+# --------------------------------------------------------------------------- #
+GE_NONE, GE_RELU, GE_MASK, GE_RELU_ADD_RELU = 0, 1, 2, 3
+
+
+def gemm(A: Tensor, B: Tensor, transA: bool = False, transB: bool = False, alpha: float = 1.0, bias: Optional[Tensor] = None,
+         epilogue: int = GE_NONE, aux: Optional[Tensor] = None, aux_out: Optional[Tensor] = None, out: Optional[Tensor] = None,
+         accumulate: bool = False, ksplit: int = 1) -> Tensor:
+    """C[M,N] = alpha * opA opB^T (+ bias, epilogue) with fp32-class accuracy on tcgen05 (csrc/tc_gemm.cu).
+    A: [M,K] (or [K,M] if transA); B: [N,K] (an nn.Linear weight; or [K,N] if transB)."""
+    A, B = _f32(A, "A"), _f32(B, "B")
+    M, K = (A.shape[1], A.shape[0]) if transA else A.shape
+    N, Kb = (B.shape[1], B.shape[0]) if transB else B.shape
+    if K != Kb:
+        raise _lib.StepB200Error(f"gemm: inner dimensions differ ({K} vs {Kb})")
+    st = _enter(A)
+    C_ = torch.empty(M, N, device=A.device, dtype=torch.float32) if out is None else out
+    if aux is not None:
+        aux = _f32(aux, "aux")
+    check(_L().step_gemm_f32(A.data_ptr(), A.shape[1], int(transA), B.data_ptr(), B.shape[1], int(transB), M, N, K, float(alpha),
+                             _p(None if bias is None else _f32(bias, "bias")), int(epilogue), _p(aux),
+                             0 if aux is None else aux.shape[1], _p(aux_out), int(accumulate), int(ksplit), C_.data_ptr(),
+                             C_.shape[1], st), "step_gemm_f32")
+    launch_counter["kernels"] += 1
+    return C_
+
+
+def _ksplit(M: int, N: int, K: int) -> int:
+    """Split-K factor for weight-gradient GEMMs (tiny M x N, long K): fill ~2 CTAs per SM."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    return max(1, min((K + 255) // 256, 296 // tiles))
+
+
+def colsum(x: Tensor) -> Tensor:
+    x = _f32(x, "x")
+    st = _enter(x)
+    out = torch.empty(x.shape[1], device=x.device, dtype=torch.float32)
+    check(_L().step_colsum_f32(x.data_ptr(), x.shape[0], x.shape[1], x.shape[1], out.data_ptr(), st), "step_colsum_f32")
+    launch_counter["kernels"] += 1
+    return out
+
+
+def relu_bwd(dy: Tensor, y: Tensor) -> Tensor:
+    dy, y = _f32(dy, "dy"), _f32(y, "y")
+    st = _enter(dy)
+    dz = torch.empty_like(dy)
+    check(_L().step_relu_bwd_f32(dy.data_ptr(), y.data_ptr(), dy.numel(), dz.data_ptr(), st), "step_relu_bwd_f32")
+    launch_counter["kernels"] += 1
+    return dz
+
+
+class Linear(torch.autograd.Function):
+    """y = act(x W^T + b) on the split-bf16 tcgen05 GEMM, hand-written backward (dx, dW, db).  x [M,K], W [N,K]."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu):
+        y = gemm(x, w, bias=b, epilogue=GE_RELU if relu else GE_NONE)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.relu, ctx.has_bias = bool(relu), b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dz = relu_bwd(dy, y) if ctx.relu else _f32(dy, "dy")
+        dx = gemm(dz, w, transB=True) if ctx.needs_input_grad[0] else None
+        dw = gemm(dz, x, transA=True, transB=True, ksplit=_ksplit(w.shape[0], w.shape[1], x.shape[0])) if ctx.needs_input_grad[1] else None
+        db = colsum(dz) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db, None
+
+
+class GwEpilogue(torch.autograd.Function):
+    """Graph WaveNet epilogue (graphwavenet/model.py:215-220):  out = end_conv_2(relu(end_conv_1(relu(skip + fc_his(h))))),
+    fc_his = Linear(96,512)-ReLU-Linear(512,256)-ReLU.  h [M,96] (no gradient: frozen TSFormer states), skip [M,256] ->
+    out [M,12].  4 GEMMs forward (the skip add + both ReLUs ride on the second GEMM's epilogue), 7 GEMMs + 5 small
+    kernels backward."""
+
+    @staticmethod
+    def forward(ctx, h, skip, w1, b1, w2, b2, we1, be1, we2, be2):
+        h, skip = _f32(h, "h"), _f32(skip, "skip")
+        h1 = gemm(h, w1, bias=b1, epilogue=GE_RELU)
+        hs = torch.empty(h.shape[0], w2.shape[0], device=h.device, dtype=torch.float32)
+        x2 = gemm(h1, w2, bias=b2, epilogue=GE_RELU_ADD_RELU, aux=skip, aux_out=hs)
+        e1 = gemm(x2, we1, bias=be1, epilogue=GE_RELU)
+        out = gemm(e1, we2, bias=be2)
+        ctx.save_for_backward(h, h1, hs, x2, e1, w1, w2, we1, we2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, h1, hs, x2, e1, w1, w2, we1, we2 = ctx.saved_tensors
+        dout = _f32(dout, "dout")
+        M = h.shape[0]
+        dwe2 = gemm(dout, e1, transA=True, transB=True, ksplit=_ksplit(we2.shape[0], we2.shape[1], M))
+        dbe2 = colsum(dout)
+        de1 = gemm(dout, we2, transB=True, epilogue=GE_MASK, aux=e1)
+        dwe1 = gemm(de1, x2, transA=True, transB=True, ksplit=_ksplit(we1.shape[0], we1.shape[1], M))
+        dbe1 = colsum(de1)
+        dx2 = gemm(de1, we1, transB=True, epilogue=GE_MASK, aux=x2)          # = d skip (the add passes it through)
+        dz2 = relu_bwd(dx2, hs)
+        dw2 = gemm(dz2, h1, transA=True, transB=True, ksplit=_ksplit(w2.shape[0], w2.shape[1], M))
+        db2 = colsum(dz2)
+        dh1 = gemm(dz2, w2, transB=True, epilogue=GE_MASK, aux=h1)
+        dw1 = gemm(dh1, h, transA=True, transB=True, ksplit=_ksplit(w1.shape[0], w1.shape[1], M))
+        db1 = colsum(dh1)
+        return None, dx2, dw1, db1, dw2, db2, dwe1, dbe1, dwe2, dbe2
+
+
+class GwStart(torch.autograd.Function):
+    """x0 [B,13,N,32] = start_conv on the left-padded history channels 0:2 (graphwavenet/model.py:145-155)."""
+
+    @staticmethod
+    def forward(ctx, history, w, b):
+        history, w, b = _f32(history, "history"), _f32(w.reshape(32, 2), "start_conv.weight"), _f32(b, "start_conv.bias")
+        B, T, N, Cc = history.shape
+        st = _enter(history)
+        x0 = torch.empty(B, T + 1, N, 32, device=history.device, dtype=torch.float32)
+        check(_L().step_gw_start_fwd(history.data_ptr(), B, T, N, Cc, w.data_ptr(), b.data_ptr(), x0.data_ptr(), st), "step_gw_start_fwd")
+        launch_counter["kernels"] += 1
+        ctx.save_for_backward(history)
+        ctx.wshape = None
+        return x0
+
+    @staticmethod
+    def backward(ctx, dx0):
+        (history,) = ctx.saved_tensors
+        B, T, N, Cc = history.shape
+        dx0 = _f32(dx0, "dx0")
+        st = _enter(history)
+        g = torch.empty(96, device=history.device, dtype=torch.float32)
+        check(_L().step_gw_start_bwd(history.data_ptr(), B, T, N, Cc, dx0.data_ptr(), g.data_ptr(), st), "step_gw_start_bwd")
+        launch_counter["kernels"] += 1
+        return None, g[:64].view(32, 2, 1, 1), g[64:]
+
+
+class GwSupports(torch.autograd.Function):
+    """(P1, P2) = (D^-1 (A + I), D'^-1 (A^T + I)) for the sampled graph A [B,N,N] (graphwavenet/model.py:121-130,160)."""
+
+    @staticmethod
+    def forward(ctx, adj):
+        adj = _f32(adj, "sampled_adj")
+        B, N, _ = adj.shape
+        st = _enter(adj)
+        deg = torch.empty(2, B, N, device=adj.device, dtype=torch.float32)
+        P1, P2 = torch.empty_like(adj), torch.empty_like(adj)
+        check(_L().step_gw_supports_fwd(adj.data_ptr(), B, N, deg.data_ptr(), P1.data_ptr(), P2.data_ptr(), st), "step_gw_supports_fwd")
+        launch_counter["kernels"] += 2
+        ctx.save_for_backward(P1, P2, deg)
+        return P1, P2
+
+    @staticmethod
+    def backward(ctx, dP1, dP2):
+        P1, P2, deg = ctx.saved_tensors
+        B, N, _ = P1.shape
+        dP1, dP2 = _f32(dP1, "dP1"), _f32(dP2, "dP2")
+        st = _enter(P1)
+        dots = torch.empty(2, B, N, device=P1.device, dtype=torch.float32)
+        dadj = torch.empty_like(P1)
+        check(_L().step_gw_supports_bwd(dP1.data_ptr(), dP2.data_ptr(), P1.data_ptr(), P2.data_ptr(), deg.data_ptr(), B, N,
+                                        dots.data_ptr(), dadj.data_ptr(), st), "step_gw_supports_bwd")
+        launch_counter["kernels"] += 2
+        return dadj
+
+
+class GwAdaptive(torch.autograd.Function):
+    """P3 [N,N] = softmax(relu(E1 E2), dim=1) (graphwavenet/model.py:165)."""
+
+    @staticmethod
+    def forward(ctx, e1, e2):
+        e1, e2 = _f32(e1, "nodevec1"), _f32(e2, "nodevec2")
+        N, R = e1.shape
+        st = _enter(e1)
+        P3 = torch.empty(N, N, device=e1.device, dtype=torch.float32)
+        check(_L().step_gw_adp_fwd(e1.data_ptr(), e2.data_ptr(), N, R, P3.data_ptr(), st), "step_gw_adp_fwd")
+        launch_counter["kernels"] += 1
+        ctx.save_for_backward(e1, e2, P3)
+        return P3
+
+    @staticmethod
+    def backward(ctx, dP3):
+        e1, e2, P3 = ctx.saved_tensors
+        N, R = e1.shape
+        dP3 = _f32(dP3, "dP3")
+        st = _enter(e1)
+        scratch = torch.empty(N, N, device=e1.device, dtype=torch.float32)
+        de1, de2 = torch.empty_like(e1), torch.empty_like(e2)
+        check(_L().step_gw_adp_bwd(e1.data_ptr(), e2.data_ptr(), P3.data_ptr(), dP3.data_ptr(), N, R, scratch.data_ptr(),
+                                   de1.data_ptr(), de2.data_ptr(), st), "step_gw_adp_bwd")
+        launch_counter["kernels"] += 2
+        return de1, de2
+
+
+# --------------------------------------------------------------------------- #
 # bf16 tensor-core encoder (tcgen05 / TMEM / TMA bulk)
 # --------------------------------------------------------------------------- #
 def tc_pack_weight(w: Tensor) -> Tensor:
@@ -361,8 +650,10 @@ def tc_image_to_rows(img: Tensor, T: int, K: int) -> Tensor:
 
 
 def tc_linear(a_img: Tensor, w_img: Tensor, bias: Tensor, T: int, K: int, Nout: int, mode: int, res_img: Optional[Tensor] = None,
-              ln_w: Optional[Tensor] = None, ln_b: Optional[Tensor] = None, want_f32: bool = False):
-    """mode 0 -> fp32 [T,Nout]; mode 1 -> ReLU image; mode 2 -> residual+LayerNorm image (and fp32 rows if want_f32)."""
+              ln_w: Optional[Tensor] = None, ln_b: Optional[Tensor] = None, want_f32: bool = False, drop_p: float = 0.0,
+              seed: int = 0):
+    """mode 0 -> fp32 [T,Nout]; mode 1 -> ReLU image; mode 2 -> residual+LayerNorm image (and fp32 rows if want_f32).
+    drop_p > 0 (modes 1, 2): the epilogue's dropout site is live."""
     st = _enter(a_img)
     MT = (T + 127) // 128
     out_img = out_f32 = None
@@ -370,8 +661,13 @@ def tc_linear(a_img: Tensor, w_img: Tensor, bias: Tensor, T: int, K: int, Nout: 
         out_f32 = torch.empty(T, Nout, device=a_img.device, dtype=torch.float32)
     if mode in (1, 2):
         out_img = torch.empty(MT * Nout * 256, device=a_img.device, dtype=torch.uint8)
-    check(_L().step_tc_linear(a_img.data_ptr(), w_img.data_ptr(), _f32(bias, "bias").data_ptr(), T, K, Nout, mode, _p(res_img),
-                              _p(ln_w), _p(ln_b), _p(out_img), _p(out_f32), st), "step_tc_linear")
+    if drop_p > 0.0:
+        check(_L().step_tc_linear_drop(a_img.data_ptr(), w_img.data_ptr(), _f32(bias, "bias").data_ptr(), T, K, Nout, mode,
+                                       _p(res_img), _p(ln_w), _p(ln_b), _p(out_img), _p(out_f32), float(drop_p),
+                                       int(seed) & (2**64 - 1), st), "step_tc_linear_drop")
+    else:
+        check(_L().step_tc_linear(a_img.data_ptr(), w_img.data_ptr(), _f32(bias, "bias").data_ptr(), T, K, Nout, mode, _p(res_img),
+                                  _p(ln_w), _p(ln_b), _p(out_img), _p(out_f32), st), "step_tc_linear")
     launch_counter["kernels"] += 1
     return out_img, out_f32
 
@@ -503,6 +799,67 @@ class TrunkConv(torch.autograd.Function):
               "step_dgl_conv_bwd")
         launch_counter["kernels"] += 5
         return (None, *grads, None, None, None, None)
+
+
+class TrunkFc(torch.autograd.Function):
+    """feat [N,100] = BatchNorm1d(relu(y2n @ W^T + b)) over the N nodes (discrete_graph_learning.py:134-135): the three
+    GEMMs of forward/backward run on tcgen05 with split-bf16 operands (csrc/trunk_fc.cu).  Returns (feat, stats [3,100]).
+    ``shard`` = None, or (k_begin, k_end, world, all_reduce_sum): this rank owns the [k_begin, k_end) slice of the K axis
+    (z and its gradient are summed over ranks; the weight gradient of the slice comes out already averaged)."""
+
+    @staticmethod
+    def forward(ctx, y2n, w, b, gamma, beta, eps, training, eval_stats, shard):
+        y2n, w, b, gamma, beta = _f32(y2n, "y2n"), _f32(w, "fc.weight"), _f32(b, "fc.bias"), _f32(gamma, "bn3.weight"), _f32(beta, "bn3.bias")
+        N, K = y2n.shape
+        if w.shape != (100, K):
+            raise _lib.StepB200Error(f"TrunkFc: fc.weight must be [100, {K}], got {tuple(w.shape)}")
+        k0, k1 = (0, K) if shard is None else (int(shard[0]), int(shard[1]))
+        st = _enter(y2n)
+        dev = y2n.device
+        splits = _L().step_dgl_fc_splits(N, k0, k1)
+        partial = torch.empty(splits, N, 100, device=dev, dtype=torch.float32)
+        z = torch.empty(N, 100, device=dev, dtype=torch.float32)
+        check(_L().step_dgl_fc_fwd(y2n.data_ptr(), w.data_ptr(), N, K, k0, k1, partial.data_ptr(), z.data_ptr(), st), "step_dgl_fc_fwd")
+        if shard is not None and shard[2] > 1:
+            shard[3](z)                                   # sum of the ranks' K slices
+        stats = torch.empty(3, 100, device=dev, dtype=torch.float32)
+        if not training:
+            stats[:2].copy_(_f32(eval_stats, "eval_stats")[:2])
+        feat = torch.empty(N, 100, device=dev, dtype=torch.float32)
+        check(_L().step_dgl_fc_bn_fwd(z.data_ptr(), b.data_ptr(), gamma.data_ptr(), beta.data_ptr(), N, float(eps),
+                                      1 if training else 0, stats.data_ptr(), feat.data_ptr(), st), "step_dgl_fc_bn_fwd")
+        launch_counter["kernels"] += 3
+        ctx.save_for_backward(y2n, w, gamma, z, stats)
+        ctx.training, ctx.shard = bool(training), shard
+        ctx.mark_non_differentiable(stats)
+        return feat, stats
+
+    @staticmethod
+    def backward(ctx, dfeat, _dstats):
+        if not ctx.training:
+            raise _lib.StepB200Error("TrunkFc: backward is only defined in training mode (batch statistics)")
+        y2n, w, gamma, z, stats = ctx.saved_tensors
+        N, K = y2n.shape
+        shard = ctx.shard
+        k0, k1 = (0, K) if shard is None else (int(shard[0]), int(shard[1]))
+        dfeat = _f32(dfeat, "dfeat")
+        st = _enter(y2n)
+        dev = y2n.device
+        g = torch.empty(N, 100, device=dev, dtype=torch.float32)
+        dgamma, dbeta, dbias = (torch.empty(100, device=dev, dtype=torch.float32) for _ in range(3))
+        check(_L().step_dgl_fc_bn_bwd(dfeat.data_ptr(), z.data_ptr(), gamma.data_ptr(), stats.data_ptr(), N, g.data_ptr(),
+                                      dgamma.data_ptr(), dbeta.data_ptr(), dbias.data_ptr(), st), "step_dgl_fc_bn_bwd")
+        scale = 1.0
+        if shard is not None and shard[2] > 1:
+            shard[3](g)                                   # every rank's loss contributes to this rank's slice
+            scale = 1.0 / shard[2]
+        full = (k0 == 0 and k1 == K)
+        dx = torch.empty_like(y2n) if full else torch.zeros_like(y2n)
+        dw = torch.empty_like(w) if full else torch.zeros_like(w)
+        check(_L().step_dgl_fc_bwd(g.data_ptr(), y2n.data_ptr(), w.data_ptr(), N, K, k0, k1, scale, dx.data_ptr(), dw.data_ptr(), st),
+              "step_dgl_fc_bwd")
+        launch_counter["kernels"] += 3
+        return dx, dw, dbias, dgamma, dbeta, None, None, None, None
 
 
 # --------------------------------------------------------------------------- #

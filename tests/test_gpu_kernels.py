@@ -376,3 +376,242 @@ def test_fused_step_loss_matches_oracle(null_val):
     assert rel_err(p2.grad.cpu(), 2.0 * pred.grad) < 1e-5
     mask = torch.ones(N, N, dtype=torch.bool); mask[0, 0] = False
     assert rel_err(t2.grad.cpu()[mask], 2.0 * th.grad[mask]) < 1e-4
+
+
+# --------------------------------------------------------------------------- trunk fc (split-bf16 tcgen05 GEMMs)
+@pytest.mark.parametrize("N,K", [(207, 16 * 2003), (13, 16 * 64), (307, 16 * 1001), (883, 16 * 700), (600, 16 * 301)])
+def test_trunk_fc_fwd_bwd(N, K):
+    """feat = BN3(relu(y2n W^T + b)) and all five gradients vs the oracle's formula in float64
+    (discrete_graph_learning.py:134-135).  Shapes cover: K % 32 == 16 (half-filled last stage), one / several
+    row groups and row tiles, several node passes of the weight-gradient kernel, K ranges shorter than the grid."""
+    from step_b200 import ops
+    g = torch.Generator().manual_seed(N * 7 + K)
+    y2n = torch.randn(N, K, generator=g)
+    w = (torch.rand(100, K, generator=g) * 2 - 1) / math.sqrt(K)
+    b, gamma, beta = torch.randn(100, generator=g) * 0.1, torch.rand(100, generator=g) + 0.5, torch.randn(100, generator=g) * 0.1
+    dfeat = torch.randn(N, 100, generator=g)
+    leaves = [t.double().requires_grad_(True) for t in (y2n, w, b, gamma, beta)]
+    z = leaves[0] @ leaves[1].t() + leaves[2]
+    ref = O._bn_train(torch.relu(z), leaves[3], leaves[4], [0])
+    ref.backward(dfeat.double())
+    mine = [t.to(DEV).requires_grad_(True) for t in (y2n, w, b, gamma, beta)]
+    feat, stats = ops.TrunkFc.apply(*mine, 1e-5, True, None, None)
+    feat.backward(dfeat.to(DEV))
+    assert rel_err(feat.detach().cpu(), ref.detach()) < 2e-5
+    r = torch.relu(z.detach())
+    assert (stats[0].cpu().double() - r.mean(0)).abs().max().item() < 1e-5
+    assert (stats[1].cpu().double() - r.var(0, unbiased=False)).abs().max().item() < 1e-5
+    for name, m, l in zip(("dy2n", "dW", "dbias", "dgamma", "dbeta"), mine, leaves):
+        assert rel_err(m.grad.cpu(), l.grad) < 5e-5, name
+    # eval mode: running statistics, forward only
+    rm, rv = torch.randn(100, generator=g) * 0.1, torch.rand(100, generator=g) + 0.5
+    with torch.no_grad():
+        fe, _ = ops.TrunkFc.apply(*[t.detach() for t in mine], 1e-5, False, torch.stack([rm, rv]).to(DEV), None)
+    ref_e = (torch.relu(z.detach()) - rm.double()) / torch.sqrt(rv.double() + 1e-5) * gamma.double() + beta.double()
+    assert rel_err(fe.cpu(), ref_e) < 2e-5
+
+
+def test_trunk_fc_k_range_slices_add_up():
+    """The [k_begin, k_end) slices a sharded trunk would use: partial z of two slices sums to the full product and the
+    backward writes only its slice (the rest stays untouched)."""
+    from step_b200 import ops
+    L = ops._L()
+    N, K = 50, 16 * 600
+    g = torch.Generator().manual_seed(5)
+    x, w = torch.randn(N, K, generator=g).to(DEV), (torch.randn(100, K, generator=g) * 0.01).to(DEV)
+    st = ops._enter(x)
+    cut = 64 * 70
+    zs = []
+    for k0, k1 in ((0, K), (0, cut), (cut, K)):
+        part = torch.empty(L.step_dgl_fc_splits(N, k0, k1), N, 100, device=DEV)
+        z = torch.empty(N, 100, device=DEV)
+        ops.check(L.step_dgl_fc_fwd(x.data_ptr(), w.data_ptr(), N, K, k0, k1, part.data_ptr(), z.data_ptr(), st), "fc_fwd")
+        zs.append(z)
+    ref = x.double() @ w.double().t()
+    assert rel_err(zs[0].cpu(), ref.cpu()) < 2e-5
+    assert rel_err((zs[1] + zs[2]).cpu(), ref.cpu()) < 2e-5
+    gg = torch.randn(N, 100, generator=g).to(DEV)
+    dx, dw = torch.full((N, K), 7.0, device=DEV), torch.full((100, K), 7.0, device=DEV)
+    ops.check(L.step_dgl_fc_bwd(gg.data_ptr(), x.data_ptr(), w.data_ptr(), N, K, cut, K, 0.5, dx.data_ptr(), dw.data_ptr(), st), "fc_bwd")
+    assert bool((dx[:, :cut] == 7.0).all()) and bool((dw[:, :cut] == 7.0).all())
+    assert rel_err(dx[:, cut:].cpu(), (gg.double() @ w.double())[:, cut:].cpu()) < 5e-5
+    assert rel_err(dw[:, cut:].cpu(), 0.5 * (gg.double().t() @ x.double())[:, cut:].cpu()) < 5e-5
+
+
+# --------------------------------------------------------------------------- general split-bf16 GEMM and what is built on it
+@pytest.mark.parametrize("M,N,K,tA,tB", [(300, 200, 96, 0, 0), (6624, 12, 512, 0, 0), (129, 257, 40, 0, 1), (100, 207, 100, 0, 0),
+                                         (512, 96, 6624, 1, 1), (12, 512, 1000, 1, 1), (207, 100, 100, 0, 1), (64, 10, 7, 1, 0),
+                                         (5, 3, 1, 0, 0)])
+def test_gemm_f32_layouts(M, N, K, tA, tB):
+    """C = opA opB^T for the four operand layouts, odd sizes (scalar tail loads), split-K; fp32-class accuracy."""
+    from step_b200 import ops
+    g = torch.Generator().manual_seed(M * 31 + N * 7 + K)
+    A = torch.randn((K, M) if tA else (M, K), generator=g)
+    Bm = torch.randn((K, N) if tB else (N, K), generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = (A.t() if tA else A).double() @ (Bm if tB else Bm.t()).double()
+    out = ops.gemm(A.to(DEV), Bm.to(DEV), transA=bool(tA), transB=bool(tB), alpha=0.5, bias=bias.to(DEV)).cpu()
+    assert rel_err(out, 0.5 * ref + bias.double()) < 3e-5
+    if K >= 64:
+        out2 = ops.gemm(A.to(DEV), Bm.to(DEV), transA=bool(tA), transB=bool(tB), ksplit=min(8, K // 32)).cpu()
+        assert rel_err(out2, ref) < 3e-5
+        acc = torch.ones(M, N, device=DEV)
+        ops.gemm(A.to(DEV), Bm.to(DEV), transA=bool(tA), transB=bool(tB), out=acc, accumulate=True)
+        assert rel_err(acc.cpu(), ref + 1.0) < 3e-5
+
+
+def test_gemm_epilogues_and_linear_autograd():
+    from step_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x, w, b = torch.randn(333, 96, generator=g), torch.randn(200, 96, generator=g) * 0.2, torch.randn(200, generator=g)
+    aux = torch.randn(333, 200, generator=g)
+    z = x.double() @ w.double().t() + b.double()
+    assert rel_err(ops.gemm(x.to(DEV), w.to(DEV), bias=b.to(DEV), epilogue=ops.GE_RELU).cpu(), torch.relu(z)) < 3e-5
+    assert rel_err(ops.gemm(x.to(DEV), w.to(DEV), bias=b.to(DEV), epilogue=ops.GE_MASK, aux=aux.to(DEV)).cpu(), z * (aux > 0)) < 3e-5
+    hs = torch.empty(333, 200, device=DEV)
+    o = ops.gemm(x.to(DEV), w.to(DEV), bias=b.to(DEV), epilogue=ops.GE_RELU_ADD_RELU, aux=aux.to(DEV), aux_out=hs).cpu()
+    assert rel_err(o, torch.relu(torch.relu(z) + aux.double())) < 3e-5 and rel_err(hs.cpu(), torch.relu(z)) < 3e-5
+    # autograd Function vs torch
+    for relu in (False, True):
+        leaves = [t.double().requires_grad_(True) for t in (x, w, b)]
+        ref = leaves[0] @ leaves[1].t() + leaves[2]
+        ref = torch.relu(ref) if relu else ref
+        dy = torch.randn(333, 200, generator=g)
+        ref.backward(dy.double())
+        mine = [t.to(DEV).requires_grad_(True) for t in (x, w, b)]
+        y = ops.Linear.apply(*mine, relu)
+        y.backward(dy.to(DEV))
+        assert rel_err(y.detach().cpu(), ref.detach()) < 3e-5
+        for m, l in zip(mine, leaves):
+            assert rel_err(m.grad.cpu(), l.grad) < 5e-5
+
+
+@pytest.mark.parametrize("B,N", [(3, 23), (2, 207), (1, 883)])
+def test_gwnet_prologue_and_epilogue_match_torch(B, N):
+    """G1 / G3 (graphwavenet/model.py:144-166,215-224): start conv, random-walk supports, adaptive adjacency, fc_his + end
+    convs - forward and every gradient against the oracle's formulas in float64."""
+    from step_b200 import ops
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(B * 100 + N)
+    hist = torch.randn(B, 12, N, 3, generator=g)
+    ws, bs = torch.randn(32, 2, 1, 1, generator=g), torch.randn(32, generator=g)
+    adj = (torch.rand(B, N, N, generator=g) < 0.4).float()
+    adj.diagonal(dim1=1, dim2=2).zero_()
+    e1, e2 = torch.randn(N, 10, generator=g), torch.randn(10, N, generator=g)
+    dd = lambda t: t.double().requires_grad_(True)
+    # --- start conv
+    Ws, Bs = dd(ws), dd(bs)
+    xin = F.pad(hist.double().transpose(1, 3), (1, 0))[:, :2]                     # [B,2,N,13]
+    ref_x0 = F.conv2d(xin, Ws, Bs).permute(0, 3, 2, 1)                            # [B,13,N,32]
+    dx0 = torch.randn(B, 13, N, 32, generator=g)
+    ref_x0.backward(dx0.double())
+    mw, mb = ws.to(DEV).requires_grad_(True), bs.to(DEV).requires_grad_(True)
+    x0 = ops.GwStart.apply(hist.to(DEV), mw, mb)
+    x0.backward(dx0.to(DEV))
+    assert rel_err(x0.detach().cpu(), ref_x0.detach()) < 1e-6
+    assert rel_err(mw.grad.cpu(), Ws.grad) < 2e-5 and rel_err(mb.grad.cpu(), Bs.grad) < 2e-5
+    # --- supports (A carries gradient: straight-through estimator)
+    Ad = dd(adj)
+    r1, r2 = O.random_walk(Ad), O.random_walk(Ad.transpose(-1, -2))
+    d1, d2 = torch.randn(B, N, N, generator=g), torch.randn(B, N, N, generator=g)
+    (r1 * d1.double()).sum().backward(retain_graph=True)
+    (r2 * d2.double()).sum().backward()
+    ma = adj.to(DEV).requires_grad_(True)
+    P1, P2 = ops.GwSupports.apply(ma)
+    ((P1 * d1.to(DEV)).sum() + (P2 * d2.to(DEV)).sum()).backward()
+    assert rel_err(P1.detach().cpu(), r1.detach()) < 1e-6 and rel_err(P2.detach().cpu(), r2.detach()) < 1e-6
+    assert rel_err(ma.grad.cpu(), Ad.grad) < 2e-5
+    # --- adaptive adjacency
+    E1, E2 = dd(e1), dd(e2)
+    r3 = torch.softmax(torch.relu(E1 @ E2), dim=1)
+    d3 = torch.randn(N, N, generator=g)
+    (r3 * d3.double()).sum().backward()
+    m1, m2 = e1.to(DEV).requires_grad_(True), e2.to(DEV).requires_grad_(True)
+    P3 = ops.GwAdaptive.apply(m1, m2)
+    (P3 * d3.to(DEV)).sum().backward()
+    assert rel_err(P3.detach().cpu(), r3.detach()) < 1e-5
+    assert rel_err(m1.grad.cpu(), E1.grad) < 5e-5 and rel_err(m2.grad.cpu(), E2.grad) < 5e-5
+    # --- epilogue
+    M = B * N
+    h, skip = torch.randn(M, 96, generator=g), torch.randn(M, 256, generator=g)
+    shapes = [(512, 96), (512,), (256, 512), (256,), (512, 256), (512,), (12, 512), (12,)]
+    ps = [torch.randn(*s, generator=g) / math.sqrt(s[-1] if len(s) > 1 else 16.0) for s in shapes]
+    L = [dd(t) for t in ps]
+    sk = dd(skip)
+    hs = torch.relu(torch.relu(h.double() @ L[0].t() + L[1]) @ L[2].t() + L[3])
+    ref = torch.relu(torch.relu(sk + hs) @ L[4].t() + L[5]) @ L[6].t() + L[7]
+    dout = torch.randn(M, 12, generator=g)
+    ref.backward(dout.double())
+    mp = [t.to(DEV).requires_grad_(True) for t in ps]
+    ms = skip.to(DEV).requires_grad_(True)
+    out = ops.GwEpilogue.apply(h.to(DEV), ms, *mp)
+    out.backward(dout.to(DEV))
+    assert rel_err(out.detach().cpu(), ref.detach()) < 3e-5
+    assert rel_err(ms.grad.cpu(), sk.grad) < 5e-5
+    for i, (m, l) in enumerate(zip(mp, L)):
+        assert rel_err(m.grad.cpu(), l.grad) < 1e-4, i
+
+
+# --------------------------------------------------------------------------- stage-1 training blocks
+@pytest.mark.parametrize("S,P,drop", [(3, 42, 0.0), (2, 168, 0.0), (2, 336, 0.0), (3, 50, 0.25)])
+def test_attention_backward(S, P, drop):
+    """dQ/dK/dV of the fp32 attention vs torch autograd; with dropout the mask is recovered from the forward kernel itself
+    (out with v = identity-like probes is not available at head dim 24, so the check is linearity: the gradient of
+    <out, w> w.r.t. v for a dropout-live forward equals the finite-difference directional derivative)."""
+    from step_b200 import ops
+    g = torch.Generator().manual_seed(S * 7 + P)
+    qkv = torch.randn(S * P, 288, generator=g)
+    dout = torch.randn(S * P, 96, generator=g)
+    mine = qkv.to(DEV).requires_grad_(True)
+    out = ops.Attention.apply(mine, S, P, drop, 99)
+    out.backward(dout.to(DEV))
+    if drop == 0.0:
+        ref_in = qkv.double().requires_grad_(True)
+        q, k, v = ref_in.view(S, P, 288).split(96, -1)
+        sh = lambda t: t.reshape(S, P, 4, 24).transpose(1, 2)
+        att = torch.softmax(sh(q) @ sh(k).transpose(-1, -2) / math.sqrt(24), -1)
+        ref = (att @ sh(v)).transpose(1, 2).reshape(S * P, 96)
+        ref.backward(dout.double())
+        assert rel_err(out.detach().cpu(), ref.detach()) < 1e-5
+        assert rel_err(mine.grad.cpu(), ref_in.grad) < 5e-5
+    else:
+        # out is linear in v (for fixed q, k and mask): <dout, out(v + e)> - <dout, out(v)> == <dv, e> exactly (up to fp32)
+        e = torch.zeros_like(qkv)
+        e[:, 192:] = torch.randn(S * P, 96, generator=g)
+        out2 = ops.attention((qkv + e).to(DEV), S, P, drop, 99)
+        lhs = ((out2 - out.detach()).double() * dout.to(DEV).double()).sum().item()
+        rhs = (mine.grad.cpu().double() * e.double()).sum().item()
+        assert abs(lhs - rhs) < 1e-3 * max(1.0, abs(rhs))
+        # and in (q, k): central finite difference along a random direction
+        d = torch.zeros_like(qkv)
+        d[:, :192] = torch.randn(S * P, 192, generator=g)
+        h = 1e-2
+        f = lambda t: (ops.attention(t.to(DEV), S, P, drop, 99).double() * dout.to(DEV).double()).sum().item()
+        fd = (f(qkv + h * d) - f(qkv - h * d)) / (2 * h)
+        an = (mine.grad.cpu().double() * d.double()).sum().item()
+        assert abs(fd - an) < 2e-2 * max(1.0, abs(an))
+
+
+def test_add_layernorm_and_dropout_autograd():
+    from step_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    M = 1000
+    x, r, w, b = torch.randn(M, 96, generator=g), torch.randn(M, 96, generator=g), torch.rand(96, generator=g) + 0.5, torch.randn(96, generator=g)
+    dy = torch.randn(M, 96, generator=g)
+    L = [t.double().requires_grad_(True) for t in (x, r, w, b)]
+    ref = O._layer_norm(L[0] + L[1], L[2], L[3])
+    ref.backward(dy.double())
+    mine = [t.to(DEV).requires_grad_(True) for t in (x, r, w, b)]
+    y = ops.AddLayerNorm.apply(*mine)
+    y.backward(dy.to(DEV))
+    assert rel_err(y.detach().cpu(), ref.detach()) < 1e-5
+    for m, l in zip(mine, L):
+        assert rel_err(m.grad.cpu(), l.grad) < 5e-5
+    # dropout: keep fraction, scale, and backward == the same mask
+    xx = torch.ones(4096, 96, device=DEV, requires_grad=True)
+    yy = ops.dropout(xx, 0.1, 1234, 5)
+    keep = (yy != 0).float().mean().item()
+    assert abs(keep - 0.9) < 5e-3 and abs(yy.max().item() - 1 / 0.9) < 1e-6
+    yy.backward(torch.ones_like(yy))
+    assert torch.equal(xx.grad, yy.detach())
+    assert not torch.equal(ops.dropout(xx, 0.1, 1235, 5), yy)

@@ -115,7 +115,7 @@ def test_metrics_match_reference_golden():
 
 def test_tsformer_pretrain_config_and_runner_contract():
     """Stage-1 config layout (reference step/TSFormer_<NAME>.py) and the TSFormerRunner glue: constructor arguments the
-    reference passes, 72 checkpoint keys, masked-MAE objective, forward-only status stated loudly."""
+    reference passes, 72 checkpoint keys, masked-MAE objective, no CPU path."""
     import importlib
     from step.step_runner import TSFormerRunner
     from step.step_runner.metrics import masked_mae
@@ -127,9 +127,9 @@ def test_tsformer_pretrain_config_and_runner_contract():
         assert CFG.MODEL.FORWARD_FEATURES == [0] and CFG.DATASET_INPUT_LEN == int(tokens) * 12
     runner = TSFormerRunner(CFG, device="cpu")
     assert len(runner.model.state_dict()) == 72 and runner.model.mode == "pre-train"
-    with pytest.raises(NotImplementedError):
-        runner.train_iters(1, 0, (torch.zeros(1, 12, 3, 3), torch.zeros(1, 4032, 3, 3)))
     from step_b200.lib import StepB200Error
+    with pytest.raises(StepB200Error):                     # stage-1 training exists on the GPU only: CPU tensors fail loudly
+        runner.train_iters(1, 0, (torch.zeros(1, 12, 3, 3), torch.zeros(1, 4032, 3, 3)))
     with pytest.raises(StepB200Error):                     # CPU tensors never run silently
         runner.loss_iters(1, 0, (torch.zeros(1, 12, 3, 3), torch.zeros(1, 4032, 3, 3)))
 
