@@ -388,6 +388,26 @@ int step_gwnet_stack_bwd(const float *dskip, const float *x0, const float *P1, c
                          const float *bn_stats, float *stash, float *dx0, float *dP1, float *dP2, float *dP3,
                          void *stream);
 
+/* ------------------------------------------------------------------------ *
+ * Optimiser step + metric accumulation
+ *   clip_grad_norm_(max_norm) + torch.optim.Adam(lr, betas, eps, weight_decay) - step/STEP_METR-LA.py:88-107 - over all
+ *   parameter tensors in two launches; masked MAE / RMSE / MAPE accumulated on the device (base_tsf_runner.py:252-254
+ *   syncs the host three times per step for them).
+ * Tables (device memory, int64 unless noted): p_ptr / g_ptr = addresses of parameter i and of its gradient (0 = no
+ * gradient this step: the tensor is skipped), numel, state_off = offset of tensor i in the flat moment buffers m / v;
+ * chunk_tensor (int32) / chunk_off: one entry per block of step_opt_chunk_elems() elements.
+ * sumsq: 1 double scratch; norm_out (optional): the gradient norm before clipping.  step: 1-based Adam step count.
+ * ------------------------------------------------------------------------ */
+int step_opt_chunk_elems(void);
+int step_clip_adam_step(const long long *p_ptr, const long long *g_ptr, const long long *numel, const long long *state_off,
+                        const int *chunk_tensor, const long long *chunk_off, int n_chunks, float *m, float *v, double *sumsq,
+                        float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, long long step,
+                        float *norm_out, void *stream);
+/* Adds this batch's masked MAE / RMSE / MAPE (of pred*std+mean vs real*std+mean, null handling of basicts/metrics) to
+ * acc[0..2] and 1 to acc[3]; sums[5] is scratch that must be zero before the first call. */
+int step_metrics_accumulate(const float *pred, const float *real, long long n, float mean, float stdv, float null_val,
+                            int use_nan_mask, double *sums, double *acc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

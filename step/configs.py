@@ -9,7 +9,7 @@ from .easydict_lite import EasyDict
 from .step_arch import STEP
 from .step_loss import step_loss
 from .step_runner import STEPRunner, TSFormerRunner
-from .step_data import ForecastingDataset
+from .step_data import ForecastingDataset, PretrainingDataset
 
 _NODES = {"METR-LA": 207, "PEMS-BAY": 325, "PEMS03": 358, "PEMS04": 307, "PEMS07": 883, "PEMS08": 170}
 _SEQ = {"METR-LA": 288 * 7, "PEMS-BAY": 288 * 7, "PEMS07": 288 * 7, "PEMS03": 288 * 7 * 2, "PEMS04": 288 * 7 * 2, "PEMS08": 288 * 7 * 2}
@@ -66,29 +66,30 @@ def step_config(name: str, gpu_num: int = 1) -> EasyDict:
 
 # ---- stage 1: TSFormer pre-training configs (reference step/TSFormer_<NAME>.py) ------------------------------------
 _TS_BATCH = {"METR-LA": 8, "PEMS-BAY": 16, "PEMS03": 3, "PEMS04": 6, "PEMS07": 3, "PEMS08": 6}
+_TS_SEQ = dict(_SEQ, PEMS03=288 * 7)     # the reference pre-trains PEMS03 on one week although STEP_PEMS03 reads two
 _TS_LR = {"METR-LA": 0.0005, "PEMS-BAY": 0.001, "PEMS03": 0.001, "PEMS04": 0.001, "PEMS07": 0.001, "PEMS08": 0.001}
 
 
 def tsformer_config(name: str, gpu_num: int = 1) -> EasyDict:
-    """Masked-patch pre-training of TSFormer: history of _SEQ[name] steps, channel 0 only, 75 % of the 12-step patches
+    """Masked-patch pre-training of TSFormer: history of _TS_SEQ[name] steps, channel 0 only, 75 % of the 12-step patches
     masked, objective masked MAE (null value 0) between the reconstructed and the true masked patches."""
     from .step_arch import TSFormer
     from .step_runner.metrics import masked_mae
     CFG = EasyDict()
     CFG.DESCRIPTION = f"TSFormer({name}) configuration"
     CFG.RUNNER = TSFormerRunner
-    CFG.DATASET_CLS = ForecastingDataset
+    CFG.DATASET_CLS = PretrainingDataset
     CFG.DATASET_NAME = name
-    CFG.DATASET_INPUT_LEN = _SEQ[name]
+    CFG.DATASET_INPUT_LEN = _TS_SEQ[name]
     CFG.DATASET_OUTPUT_LEN = 12
-    CFG.DATASET_ARGS = {"seq_len": _SEQ[name]}
+    CFG.DATASET_ARGS = {}
     CFG.GPU_NUM = gpu_num
     CFG.ENV = EasyDict(SEED=0, CUDNN=EasyDict(ENABLED=True))
     CFG.MODEL = EasyDict()
     CFG.MODEL.NAME = "TSFormer"
     CFG.MODEL.ARCH = TSFormer
     CFG.MODEL.PARAM = {"patch_size": 12, "in_channel": 1, "embed_dim": 96, "num_heads": 4, "mlp_ratio": 4, "dropout": 0.1,
-                       "num_token": _SEQ[name] / 12, "mask_ratio": 0.75, "encoder_depth": 4, "decoder_depth": 1,
+                       "num_token": _TS_SEQ[name] / 12, "mask_ratio": 0.75, "encoder_depth": 4, "decoder_depth": 1,
                        "mode": "pre-train"}
     CFG.MODEL.FORWARD_FEATURES = [0]
     CFG.MODEL.TARGET_FEATURES = [0]

@@ -24,9 +24,9 @@ def step_loss(prediction, real_value, theta, priori_adj, gsl_coefficient, null_v
     if prediction.is_cuda and theta.dim() == 3 and theta.stride(0) == 0 and prediction.dtype == torch.float32:
         from step_b200 import ops
         return ops.FusedStepLoss.apply(prediction, real_value, theta[0], priori_adj, float(gsl_coefficient), float(null_val), 0.0, 1.0)
-    # theta may be an expanded (stride-0) view of the batch-invariant [N,N] probabilities
-    log_t = torch.log(theta).clamp_min(-100.0)
-    log_1mt = torch.log(1.0 - theta).clamp_min(-100.0)
-    loss_graph = -(priori_adj * log_t + (1.0 - priori_adj) * log_1mt).mean()
+    # any other call shape: nn.BCELoss semantics (log clamped at -100, finite gradients at saturated theta) through the
+    # library op, as the reference does (step_loss.py:10-13)
+    bce = torch.nn.functional.binary_cross_entropy(theta.contiguous().view(theta.shape[0], -1),
+                                                   priori_adj.contiguous().view(theta.shape[0], -1))
     loss_pred = masked_mae(preds=prediction, labels=real_value, null_val=null_val)
-    return loss_pred + loss_graph * gsl_coefficient
+    return loss_pred + bce * gsl_coefficient

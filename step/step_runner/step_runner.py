@@ -10,6 +10,8 @@ import math
 
 import torch
 
+from .scaler import load_scaler, rescale
+
 
 class STEPRunner:
     def __init__(self, cfg: dict, device=None):
@@ -20,7 +22,7 @@ class STEPRunner:
         self.target_features = cfg["MODEL"].get("TARGET_FEATURES", None)
         self.loss = cfg["TRAIN"]["LOSS"]
         self.null_val = cfg["TRAIN"].get("NULL_VAL", float("nan"))
-        self.scaler = cfg.get("SCALER", {"mean": 0.0, "std": 1.0})        # re_standard_transform arguments
+        self.scaler = load_scaler(cfg)      # re_standard_transform arguments from the dataset's scaler pickle
         self.cl_param = cfg["TRAIN"].get("CL", None)
         self.output_seq_len = cfg.get("DATASET_OUTPUT_LEN", 12)
         self.iter_per_epoch = cfg.get("ITER_PER_EPOCH", 1)
@@ -54,7 +56,7 @@ class STEPRunner:
 
     # ---- reference: base_tsf_runner.py:225-255 (without the epoch meters) ----
     def rescale(self, x: torch.Tensor) -> torch.Tensor:
-        return x * self.scaler["std"] + self.scaler["mean"]
+        return rescale(x, self.scaler)
 
     def curriculum_learning(self, epoch: int) -> int:
         if self.cl_param is None:
@@ -87,8 +89,7 @@ class STEPRunner:
             pairs = []
             for data in data_loader:
                 ret = self.forward(data=data, epoch=None, iter_num=None, train=False)
-                pairs.append((ret[0], ret[1]))
+                pairs.append((self.rescale(ret[0]), self.rescale(ret[1])))
         finally:
             self.model.train(was_training)
-        return metrics.evaluate(pairs, scaler_mean=self.scaler["mean"], scaler_std=self.scaler["std"], null_val=self.null_val,
-                                horizons=horizons)
+        return metrics.evaluate(pairs, null_val=self.null_val, horizons=horizons)

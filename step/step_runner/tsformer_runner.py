@@ -6,6 +6,8 @@ host -> running device -> channel selection -> ``model(history_data=..., future_
 kernels, ``TSFormer.pretrain_forward_autograd``); ``loss_iters`` evaluates it without a graph on the fused kernels."""
 import torch
 
+from .scaler import load_scaler, rescale
+
 
 class TSFormerRunner:
     def __init__(self, cfg: dict, device=None):
@@ -15,7 +17,7 @@ class TSFormerRunner:
         self.forward_features = cfg["MODEL"].get("FORWARD_FEATURES", None)
         self.loss = cfg["TRAIN"]["LOSS"]
         self.null_val = cfg["TRAIN"].get("NULL_VAL", float("nan"))
-        self.scaler = cfg.get("SCALER", {"mean": 0.0, "std": 1.0})
+        self.scaler = load_scaler(cfg)
         self.iter_per_epoch = cfg.get("ITER_PER_EPOCH", 1)
 
     def select_input_features(self, data: torch.Tensor) -> torch.Tensor:
@@ -31,12 +33,10 @@ class TSFormerRunner:
     def loss_iters(self, epoch: int, iter_index: int, data: tuple) -> torch.Tensor:
         """The pre-training objective on one batch (re-scaled like base_tsf_runner.py:238-250 does before the loss)."""
         rec, label = self.forward(data, epoch=epoch, iter_num=(epoch - 1) * self.iter_per_epoch + iter_index, train=False)
-        mean, std = self.scaler["mean"], self.scaler["std"]
-        return self.loss(rec * std + mean, label * std + mean, null_val=self.null_val)
+        return self.loss(rescale(rec, self.scaler), rescale(label, self.scaler), null_val=self.null_val)
 
     def train_iters(self, epoch: int, iter_index: int, data: tuple) -> torch.Tensor:
         """reference base_tsf_runner.py:225-255 for the 2-tuple model: forward, re-scale, ``cfg.TRAIN.LOSS``; the caller
         (easytorch's ``backward``) calls ``.backward()`` on the returned loss, clips and steps the optimiser."""
         rec, label = self.forward(data, epoch=epoch, iter_num=(epoch - 1) * self.iter_per_epoch + iter_index, train=True)
-        mean, std = self.scaler["mean"], self.scaler["std"]
-        return self.loss(rec * std + mean, label * std + mean, null_val=self.null_val)
+        return self.loss(rescale(rec, self.scaler), rescale(label, self.scaler), null_val=self.null_val)

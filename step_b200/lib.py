@@ -98,6 +98,10 @@ SIGNATURES = {
     "step_gw_supports_bwd": (C.c_int, [f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_int, f32p, f32p, vp]),
     "step_gw_adp_fwd": (C.c_int, [f32p, f32p, C.c_int, C.c_int, f32p, vp]),
     "step_gw_adp_bwd": (C.c_int, [f32p, f32p, f32p, f32p, C.c_int, C.c_int, f32p, f32p, f32p, vp]),
+    "step_opt_chunk_elems": (C.c_int, []),
+    "step_clip_adam_step": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, f32p, f32p, vp, C.c_float, C.c_float, C.c_float, C.c_float,
+                                      C.c_float, C.c_float, ll, f32p, vp]),
+    "step_metrics_accumulate": (C.c_int, [f32p, f32p, ll, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp, vp]),
     "step_gwnet_stash_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "step_gwnet_stack_fwd": (C.c_int, [f32p, f32p, f32p, f32p, C.POINTER(GwLayerParams), C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_float, ull, f32p, f32p, f32p, vp]),

@@ -5,7 +5,7 @@ import os
 import pytest
 import torch
 
-from conftest import GOLDEN, build_step_model
+from conftest import GOLDEN, ROOT, build_step_model
 from oracle import step_oracle as O
 
 
@@ -162,3 +162,73 @@ def test_step_forward_orchestration_with_stub_submodules(tmp_path):
     assert theta.shape == (B, N, N) and theta.stride(0) == 0 and torch.equal(theta[1], FakeDGL.theta)
     assert coeff == 1 / 3 and knn.shape == (B, N, N)
     assert model(history_data=history, long_history_data=long_history, future_data=None, batch_seen=0, epoch=None)[3] == 0
+
+
+def test_scaler_is_loaded_and_applied_before_masking(tmp_path):
+    """the runner must re-standardise prediction and label with the dataset's scaler pickle before the loss, so
+    that a missing reading (raw 0 = -mean/std in z-score units) is masked (reference base_tsf_runner.py:36,238-250)."""
+    import pickle
+    import numpy as np
+    from step.step_runner.scaler import load_scaler, rescale, scalar_stats
+    from step.step_runner.metrics import masked_mae
+    d = tmp_path / "datasets" / "X"
+    d.mkdir(parents=True)
+    cfg = {"TRAIN": {"DATA": {"DIR": str(d)}}, "DATASET_INPUT_LEN": 12, "DATASET_OUTPUT_LEN": 12}
+    assert load_scaler(cfg) == {"mean": 0.0, "std": 1.0}                       # synthetic data: identity
+    with open(d / "scaler_in12_out12.pkl", "wb") as f:
+        pickle.dump({"func": "re_standard_transform", "args": {"mean": 54.4, "std": 19.5}}, f)
+    sc = load_scaler(cfg)
+    assert sc == {"mean": 54.4, "std": 19.5} and scalar_stats(sc) == (54.4, 19.5)
+    label = torch.tensor([[-54.4 / 19.5, 1.0, 0.5]])                          # first entry: a missing reading
+    pred = torch.tensor([[3.0, 1.0, 1.0]])
+    got = float(masked_mae(rescale(pred, sc), rescale(label, sc), null_val=0.0))
+    assert abs(got - 0.25 * 19.5) < 1e-4                                       # mean |err| over the two valid entries only
+    wrong = float(masked_mae(pred, label, null_val=0.0))                       # z-score space: the missing entry is NOT masked
+    assert abs(wrong - (3.0 + 54.4 / 19.5 + 0.5) / 3) < 1e-5
+    arr = {"mean": np.array([1.0, 2.0], dtype=np.float32), "std": np.array([2.0, 3.0], dtype=np.float32)}
+    assert torch.equal(rescale(torch.ones(4, 2), arr), torch.tensor([[3.0, 5.0]] * 4))
+    assert load_scaler({"SCALER": {"mean": 1.0, "std": 2.0}}) == {"mean": 1.0, "std": 2.0}
+
+
+def test_config_files_and_datasets_cover_all_six_datasets(tmp_path):
+    import importlib
+    from step.step_data import PretrainingDataset, ForecastingDataset
+    for name in ("METR-LA", "PEMS-BAY", "PEMS03", "PEMS04", "PEMS07", "PEMS08"):
+        s2 = importlib.import_module(f"step.STEP_{name}").CFG
+        s1 = importlib.import_module(f"step.TSFormer_{name}").CFG
+        assert s2.DATASET_CLS is ForecastingDataset and s1.DATASET_CLS is PretrainingDataset
+        assert s2.MODEL.PARAM["dataset_name"] == name and s1.MODEL.PARAM["mode"] == "pre-train"
+    assert importlib.import_module("step.TSFormer_PEMS03").CFG.DATASET_INPUT_LEN == 288 * 7      # shipped as-is (SURVEY Appx C)
+    assert importlib.import_module("step.STEP_PEMS03").CFG.DATASET_ARGS["seq_len"] == 288 * 7 * 2
+    ds = PretrainingDataset(synthetic=True, num_nodes=5, seq_len=48, length=6)
+    future, history = ds[2]
+    assert future.shape == (12, 5, 3) and history.shape == (48, 5, 3) and len(ds) == 6
+    assert torch.equal(history, ds.data[2:50]) and torch.equal(future, ds.data[50:62])
+    with pytest.raises(FileNotFoundError):
+        PretrainingDataset(str(tmp_path / "nope.pkl"), str(tmp_path / "nope2.pkl"))
+
+
+def test_run_py_never_touches_a_real_dataset_directory(tmp_path):
+    """--synthetic writes into a scratch work directory and refuses to overwrite a data file it did not write."""
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("run_mod", os.path.join(ROOT, "step", "run.py"))
+    run = importlib.util.module_from_spec(spec); spec.loader.exec_module(run)
+    cwd = os.getcwd()
+    try:
+        work = tmp_path / "w"
+        args = argparse.Namespace(workdir=str(work), synthetic=True)
+        run.enter_synthetic_workdir(args, "PEMS08", 170, 4032, need_ckpt=False)
+        assert os.path.samefile(os.getcwd(), work) and os.path.isfile("datasets/PEMS08/data_in12_out12.pkl")
+        assert not run.have_real_data("PEMS08", 12)                              # no index file -> not "real data"
+        os.chdir(cwd)
+        run.enter_synthetic_workdir(args, "PEMS08", 170, 4032, need_ckpt=False)   # re-running over its own files is fine
+        os.chdir(cwd)
+        real = tmp_path / "real" / "datasets" / "PEMS08"
+        real.mkdir(parents=True)
+        (real / "data_in12_out12.pkl").write_bytes(b"user data")
+        with pytest.raises(SystemExit):
+            run.enter_synthetic_workdir(argparse.Namespace(workdir=str(tmp_path / "real"), synthetic=True), "PEMS08", 170, 4032, False)
+        assert (real / "data_in12_out12.pkl").read_bytes() == b"user data"
+    finally:
+        os.chdir(cwd)
