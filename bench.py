@@ -346,7 +346,7 @@ class Arm:
     def train_step(self, history, long_history, future):
         y_hat, theta, adj_knn, coeff = self.model(history_data=history, long_history_data=long_history, future_data=None,
                                                   batch_seen=0, epoch=1)
-        loss = self.step_loss(y_hat[..., [0]], future[..., [0]], theta, adj_knn, coeff, null_val=0.0)
+        loss = self.step_loss(y_hat[..., :1], future[..., :1], theta, adj_knn, coeff, null_val=0.0)
         self.reducer.zero()
         loss.backward()
         self.reducer.reduce()                     # NCCL all-reduce (big tensor in place + one packed buffer) when world > 1

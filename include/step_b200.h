@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define STEP_B200_ABI_VERSION 1
+#define STEP_B200_ABI_VERSION 2
 
 #define STEP_OK 0
 #define STEP_EINVAL (-1)
@@ -155,6 +155,10 @@ typedef struct step_ts_layer_images {
   const void *out_proj; /* [12][96][8]  */
   const void *lin1;     /* [12][384][8] */
   const void *lin2;     /* [48][96][8]  */
+  /* Optional (NULL = run the four token GEMMs as separate launches): the weights of the fused token-block kernel as
+   * twelve [12][96][8] slices (18432 B each) in program order: out_proj | lin1 rows 0-95, lin2 K-columns 0-95, ... (x4) |
+   * the NEXT layer's in_proj rows 0-95 (q), 96-191 (k), 192-287 (v); the last layer carries the first nine only. */
+  const void *fused;
 } step_ts_layer_images;
 
 /* fp32 W [Nout][K] -> bf16 weight image [K/8][Nout][8] (Nout*K*2 bytes). */
@@ -167,6 +171,10 @@ int step_tc_image_to_rows(const void *img, long long T, int K, float *x, void *s
  *   mode 2 (Nout == 96): LayerNorm(residual image + .) -> out_img and/or out_f32 [T][96]. */
 int step_tc_linear(const void *a_img, const void *w_img, const float *bias, long long T, int K, int Nout, int mode,
                    const void *res_img, const float *ln_w, const float *ln_b, void *out_img, float *out_f32, void *stream);
+/* Patch + positional embedding (x sqrt(96), positional dropout) straight into the X tile image [B*N*P, 96] - the first
+ * kernel of step_ts_encoder_fwd_bf16, exposed for the per-site dropout tests. */
+int step_tc_embed_fwd(const float *series, long long sB, long long sT, long long sN, int B, int N, int P, const float *patch_w,
+                      const float *patch_b, const float *pos, void *x_img, float drop_p, unsigned long long seed, void *stream);
 /* Same as step_tc_linear for modes 1 and 2 with the dropout site of that epilogue live (inverted dropout on the ReLU
  * output / on the GEMM result before the residual add; transformer_layers.py:10-11 -> nn.TransformerEncoderLayer's
  * dropout, dropout1, dropout2), drawn from the counter-based generator keyed by `seed`. */
@@ -396,17 +404,24 @@ int step_gwnet_stack_bwd(const float *dskip, const float *x0, const float *P1, c
  * Tables (device memory, int64 unless noted): p_ptr / g_ptr = addresses of parameter i and of its gradient (0 = no
  * gradient this step: the tensor is skipped), numel, state_off = offset of tensor i in the flat moment buffers m / v;
  * chunk_tensor (int32) / chunk_off: one entry per block of step_opt_chunk_elems() elements.
- * sumsq: 1 double scratch; norm_out (optional): the gradient norm before clipping.  step: 1-based Adam step count.
+ * steps_in / steps_out (int32 per tensor, two distinct buffers the caller swaps every call): Adam steps taken so far -
+ * torch keeps `step` per parameter, a tensor without gradient does not advance.
+ * sumsq: 1 double scratch; norm_out (optional): the gradient norm before clipping.
  * ------------------------------------------------------------------------ */
 int step_opt_chunk_elems(void);
 int step_clip_adam_step(const long long *p_ptr, const long long *g_ptr, const long long *numel, const long long *state_off,
-                        const int *chunk_tensor, const long long *chunk_off, int n_chunks, float *m, float *v, double *sumsq,
-                        float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, long long step,
-                        float *norm_out, void *stream);
+                        const int *chunk_tensor, const long long *chunk_off, int n_chunks, const int *steps_in, int *steps_out,
+                        float *m, float *v, double *sumsq, float max_norm, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, float *norm_out, void *stream);
 /* Adds this batch's masked MAE / RMSE / MAPE (of pred*std+mean vs real*std+mean, null handling of basicts/metrics) to
  * acc[0..2] and 1 to acc[3]; sums[5] is scratch that must be zero before the first call. */
 int step_metrics_accumulate(const float *pred, const float *real, long long n, float mean, float stdv, float null_val,
                             int use_nan_mask, double *sums, double *acc, void *stream);
+
+/* Test hook: the dropout site of the gcn output (graphwavenet/model.py:47) applied to a stand-alone [rows, 32] buffer with
+ * exactly the mask the layer kernels draw for elements [0, rows*32) of layer `layer`. */
+int step_gwnet_dropout_probe(const float *x, long long rows, float drop_p, unsigned long long seed, int layer, float *y,
+                             void *stream);
 
 #ifdef __cplusplus
 }

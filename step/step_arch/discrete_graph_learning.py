@@ -102,7 +102,7 @@ class DiscreteGraphLearning(nn.Module):
         """long_term_history [B, P*L, N, C] -> (bernoulli_unnorm [B,N*N,2], hidden [B,N,P,d], adj_knn, sampled_adj)."""
         batch_size, _, num_nodes, _ = long_term_history.shape
         feat = self._global_feature(long_term_history.device)
-        hidden_states = tsformer(long_term_history[..., [0]])
+        hidden_states = tsformer(long_term_history[..., 0:1])        # a strided view: the encoder reads it in place
         half = self.embedding_dim
         # the two halves of fc_out (reference :148-151 after the one-hot gathers), split-bf16 tcgen05 GEMMs
         w_send, w_recv = self.fc_out.weight[:, :half].contiguous(), self.fc_out.weight[:, half:].contiguous()

@@ -252,20 +252,21 @@ __global__ void __launch_bounds__(256) gw_adp_bwd_kernel(const float *__restrict
   }
 }
 
-// dE2[k,w] = sum_v E1[v,k] dR[v,w]
+// dE2[k,w] += sum_{v in slab} E1[v,k] dR[v,w]   (grid.y slabs of rows; dE2 zero-initialised by the host)
 __global__ void gw_adp_bwd_e2_kernel(const float *__restrict__ E1, const float *__restrict__ dR, int N, float *__restrict__ dE2) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= N) return;
+  const int per = (N + gridDim.y - 1) / gridDim.y, v0 = blockIdx.y * per, v1 = min(N, v0 + per);
   float acc[ADP_R];
 #pragma unroll
   for (int k = 0; k < ADP_R; ++k) acc[k] = 0.f;
-  for (int v = 0; v < N; ++v) {
+  for (int v = v0; v < v1; ++v) {
     const float d = dR[(size_t)v * N + w];
 #pragma unroll
     for (int k = 0; k < ADP_R; ++k) acc[k] = fmaf(E1[(size_t)v * ADP_R + k], d, acc[k]);
   }
 #pragma unroll
-  for (int k = 0; k < ADP_R; ++k) dE2[(size_t)k * N + w] = acc[k];
+  for (int k = 0; k < ADP_R; ++k) atomicAdd(dE2 + (size_t)k * N + w, acc[k]);
 }
 
 }  // namespace stepk
@@ -322,6 +323,7 @@ extern "C" int step_gw_adp_bwd(const float *E1, const float *E2, const float *P3
   cudaStream_t st = (cudaStream_t)stream;
   gw_adp_bwd_kernel<<<N, 256, 0, st>>>(E1, E2, P3, dP3, N, scratch, dE1);
   STEP_LAUNCH_CHECK("gw_adp_bwd_kernel");
-  gw_adp_bwd_e2_kernel<<<(N + 127) / 128, 128, 0, st>>>(E1, scratch, N, dE2);
+  cudaMemsetAsync(dE2, 0, (size_t)ADP_R * N * sizeof(float), st);
+  gw_adp_bwd_e2_kernel<<<dim3((N + 127) / 128, 32), 128, 0, st>>>(E1, scratch, N, dE2);
   return check_launch("gw_adp_bwd_e2_kernel");
 }

@@ -383,6 +383,18 @@ __device__ __forceinline__ float4 dropout4(float4 h, uint64_t elem0, int c4, uin
                      (r.z >= thr) ? h.z * scale : 0.f, (r.w >= thr) ? h.w * scale : 0.f);
 }
 
+// The dropout site of the gcn output (graphwavenet/model.py:47) on a stand-alone [rows, 32] buffer: exactly the mask the
+// layer kernels draw for the element range [0, rows*32) of layer `layer` (test hook for the distribution checks).
+__global__ void gw_dropout_probe_kernel(const float *__restrict__ x, long long rows, uint32_t thr, float scale, uint64_t key,
+                                        float *__restrict__ y) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float h[GC];
+  load_row(x + r * GC, h);
+  dropout_row(h, (uint64_t)(r * GC), thr, scale, key);
+  store_row(y + r * GC, h);
+}
+
 // ---------------------------------------------------------------------------
 // forward layer kernel: grid (T_out, B)
 // ---------------------------------------------------------------------------
@@ -1381,4 +1393,12 @@ extern "C" int step_gwnet_stack_bwd(const float *dskip, const float *x0, const f
     }
   }
   return STEP_OK;
+}
+
+extern "C" int step_gwnet_dropout_probe(const float *x, long long rows, float drop_p, unsigned long long seed, int layer, float *y,
+                                        void *stream) {
+  STEP_REQUIRE(x && y && rows > 0 && drop_p > 0.f && drop_p < 1.f && layer >= 0, "gwnet_dropout_probe: bad argument");
+  gw_dropout_probe_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      x, rows, drop_threshold(drop_p), 1.f / (1.f - drop_p), rng_key(seed, 0x100u + (unsigned)layer), y);
+  return check_launch("gw_dropout_probe_kernel");
 }

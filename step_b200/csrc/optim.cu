@@ -16,6 +16,8 @@ constexpr int OPT_CHUNK = 16384;      // elements per block
 struct AdamTables {
   const long long *p_ptr, *g_ptr;     // per tensor: device addresses (g_ptr 0 = no gradient this step: skipped, as torch does)
   const long long *numel, *state_off; // per tensor
+  const int *steps_in;                // per tensor: Adam steps taken so far (torch keeps `step` per parameter: a tensor
+  int *steps_out;                     //   without gradient is skipped and does not advance)
   const int *chunk_tensor;            // per chunk
   const long long *chunk_off;         // per chunk: element offset inside the tensor
 };
@@ -47,14 +49,18 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(AdamTables t, double *_
 // clip_coef = min(1, max_norm / (||g|| + 1e-6)); g' = clip_coef g + wd p; m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2;
 // p -= (lr / bc1) m / (sqrt(v) / sqrt(bc2) + eps)        (torch.optim.Adam, amsgrad off, maximize off)
 __global__ void __launch_bounds__(256) adam_update_kernel(AdamTables t, const double *__restrict__ sumsq, float max_norm,
-                                                          float lr, float b1, float b2, float eps, float wd, float bc1,
-                                                          float bc2_sqrt, float *__restrict__ m, float *__restrict__ v,
+                                                          float lr, float b1, float b2, float eps, float wd,
+                                                          float *__restrict__ m, float *__restrict__ v,
                                                           float *__restrict__ norm_out) {
   const int ti = t.chunk_tensor[blockIdx.x];
   const float *g = reinterpret_cast<const float *>(t.g_ptr[ti]);
   const float total = (float)sqrt(*sumsq);
   if (blockIdx.x == 0 && threadIdx.x == 0 && norm_out) *norm_out = total;
+  const int step_prev = t.steps_in[ti];
+  if (t.chunk_off[blockIdx.x] == 0 && threadIdx.x == 0) t.steps_out[ti] = step_prev + (g != nullptr ? 1 : 0);
   if (g == nullptr) return;
+  const float tstep = (float)(step_prev + 1);
+  const float bc1 = 1.f - powf(b1, tstep), bc2_sqrt = sqrtf(1.f - powf(b2, tstep));
   float coef = 1.f;
   if (max_norm > 0.f) { coef = max_norm / (total + 1e-6f); coef = coef > 1.f ? 1.f : coef; }
   float *p = reinterpret_cast<float *>(t.p_ptr[ti]);
@@ -115,17 +121,16 @@ extern "C" int step_opt_chunk_elems(void) { return OPT_CHUNK; }
 
 extern "C" int step_clip_adam_step(const long long *p_ptr, const long long *g_ptr, const long long *numel,
                                    const long long *state_off, const int *chunk_tensor, const long long *chunk_off, int n_chunks,
-                                   float *m, float *v, double *sumsq, float max_norm, float lr, float beta1, float beta2, float eps,
-                                   float weight_decay, long long step, float *norm_out, void *stream) {
-  STEP_REQUIRE(p_ptr && g_ptr && numel && state_off && chunk_tensor && chunk_off && m && v && sumsq && n_chunks > 0 && step > 0,
-               "clip_adam_step: bad argument");
+                                   const int *steps_in, int *steps_out, float *m, float *v, double *sumsq, float max_norm, float lr,
+                                   float beta1, float beta2, float eps, float weight_decay, float *norm_out, void *stream) {
+  STEP_REQUIRE(p_ptr && g_ptr && numel && state_off && chunk_tensor && chunk_off && steps_in && steps_out && steps_in != steps_out &&
+                   m && v && sumsq && n_chunks > 0, "clip_adam_step: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  AdamTables t{p_ptr, g_ptr, numel, state_off, chunk_tensor, chunk_off};
+  AdamTables t{p_ptr, g_ptr, numel, state_off, steps_in, steps_out, chunk_tensor, chunk_off};
   cudaMemsetAsync(sumsq, 0, sizeof(double), st);
   grad_sumsq_kernel<<<n_chunks, 256, 0, st>>>(t, sumsq);
   STEP_LAUNCH_CHECK("grad_sumsq_kernel");
-  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
-  adam_update_kernel<<<n_chunks, 256, 0, st>>>(t, sumsq, max_norm, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), m, v, norm_out);
+  adam_update_kernel<<<n_chunks, 256, 0, st>>>(t, sumsq, max_norm, lr, beta1, beta2, eps, weight_decay, m, v, norm_out);
   return check_launch("adam_update_kernel");
 }
 

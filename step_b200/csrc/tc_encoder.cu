@@ -862,6 +862,300 @@ __global__ void gram_normalize_kernel(const float *__restrict__ g, int N, float 
   sim[(size_t)b * N * N + e] = gb[e] / (ni * nj);
 }
 
+// ===========================================================================
+// Fused token block of one encoder layer (everything between two attentions is row-local):
+//   Y  = LN1(X + drop(O Wo^T + bo))                         (out-projection, nn.TransformerEncoderLayer norm1)
+//   H  = drop(relu(Y W1^T + b1)),  X' = LN2(Y + drop(H W2^T + b2))      (feed-forward, norm2)
+//   Q,K,V of the NEXT layer = X' Wqkv'^T + b'  (written straight into the attention operand images), or, for the last
+//   layer, encoder_norm(X') as fp32 hidden states + the Gram operand image.
+// One CTA owns a tile of 128 tokens at a time; Y, H (one 96-column slab at a time) and X' never leave shared memory, so a
+// layer moves O + X in and X' + QKV out (1.3 GB at METR-LA) instead of the 3.9 GB of the four separate token GEMMs.
+// All weights are streamed from L2 as twelve 18 KB K-major slices [12 chunks][96 rows][8] in program order
+// (Wo | W1_0 W2_0 ... W1_3 W2_3 | Wq Wk Wv) through a 3-slot TMA ring; accumulators: two 96-column TMEM slots.
+// Warp roles: 0 TMA producer, 1 MMA issuer (+ TMEM alloc), 2-5 epilogue (thread = token row).  The per-tile dependency
+// chain MMA -> epilogue -> MMA is serial inside a CTA; two CTAs are co-resident per SM (110 KB smem, 256 TMEM columns
+// each) and fill each other's bubbles.
+// ===========================================================================
+constexpr int TLK_THREADS = 192;
+constexpr uint32_t TLK_SLICE = 12 * 96 * 16;           // 18432 B: one [96 x 96] weight slice
+constexpr int TLK_RING = 3;
+
+struct TcLayerArgs {
+  const uint8_t *O, *X;            // attention output / layer input (residual) tile images [MT][12][128][8]
+  const uint8_t *W;                // 12 (9 for the last layer) slices in program order
+  const float *bo, *b1, *b2, *bqkv;
+  const float *ln1w, *ln1b, *ln2w, *ln2b, *fnw, *fnb;
+  uint8_t *Xout;                   // next layer's input image (nullptr for the last layer)
+  uint8_t *q_img, *k_img, *v_img;  // next layer's attention operands
+  float *hidden;                   // last layer: fp32 [T][96]
+  uint8_t *seq_img;                // last layer: Gram operand image (may be null)
+  int seq_nodes, seq_rows;
+  int MT, P, Pk, RT, last;
+  long long T;
+  float qscale;
+  uint32_t thr16; float dscale; uint64_t key_o, key_h, key_f;
+};
+
+__global__ void __launch_bounds__(TLK_THREADS, 2) tc_layer_kernel(TcLayerArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *sRing = smem;                                   // TLK_RING x 18432
+  uint8_t *sOH = sRing + TLK_RING * TLK_SLICE;             // O tile, later the H slab (same 24 KB)
+  uint8_t *sY = sOH + SLICE_BYTES;                         // Y, later X'
+  float *sPar = reinterpret_cast<float *>(sY + SLICE_BYTES);   // bo[96] b1[384] b2[96] bqkv[288] ln1w ln1b ln2w ln2b fnw fnb
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sPar + 96 + 384 + 96 + 288 + 6 * 96);
+  uint64_t *ring_full = bars, *ring_empty = bars + 3, *o_full = bars + 6, *oh_free = bars + 7, *acc_full = bars + 8,
+           *acc_empty = bars + 10, *y_ready = bars + 12, *h_ready = bars + 13, *h_free = bars + 14, *x_ready = bars + 15;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *sBo = sPar, *sB1 = sPar + 96, *sB2 = sB1 + 384, *sBq = sB2 + 96, *sLn = sBq + 288;
+  for (int i = threadIdx.x; i < 96; i += blockDim.x) {
+    sBo[i] = a.bo[i]; sB2[i] = a.b2[i];
+    sLn[i] = a.ln1w[i]; sLn[96 + i] = a.ln1b[i]; sLn[192 + i] = a.ln2w[i]; sLn[288 + i] = a.ln2b[i];
+    sLn[384 + i] = a.fnw ? a.fnw[i] : 1.f; sLn[480 + i] = a.fnb ? a.fnb[i] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 384; i += blockDim.x) sB1[i] = a.b1[i];
+  if (!a.last)
+    for (int i = threadIdx.x; i < 288; i += blockDim.x) sBq[i] = a.bqkv[i];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TLK_RING; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+    mbar_init(o_full, 1); mbar_init(oh_free, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    mbar_init(y_ready, 4); mbar_init(h_ready, 4); mbar_init(h_free, 1); mbar_init(x_ready, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int NS = a.last ? 9 : 12;                          // weight slices per tile
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      uint32_t n = 0, it = 0;
+      for (int mt = blockIdx.x; mt < a.MT; mt += gridDim.x, ++it) {
+        mbar_wait(oh_free, (it & 1) ^ 1);                  // the previous tile's last FFN2 has read the H slab
+        mbar_expect_tx(o_full, SLICE_BYTES);
+        tma_bulk_g2s(sOH, a.O + (size_t)mt * SLICE_BYTES, SLICE_BYTES, o_full);
+        for (int s = 0; s < NS; ++s, ++n) {
+          const uint32_t slot = n % TLK_RING;
+          mbar_wait(&ring_empty[slot], ((n / TLK_RING) & 1) ^ 1);
+          mbar_expect_tx(&ring_full[slot], TLK_SLICE);
+          tma_bulk_g2s(sRing + slot * TLK_SLICE, a.W + (size_t)s * TLK_SLICE, TLK_SLICE, &ring_full[slot]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (one thread) ------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, 96, 0, 0);
+      const uint32_t oh = smem_u32(sOH), yy = smem_u32(sY), ring = smem_u32(sRing);
+      uint32_t n = 0, it = 0, u0 = 0, u1 = 0, hcnt = 0;   // ring slices, tiles, uses of acc slot 0 / 1, H slabs
+      // one [128 x 96] x [96 x 96]^T product: 6 k-steps of 16
+      auto gemm96 = [&](uint32_t a_addr, uint32_t acc_col, bool accumulate) {
+        const uint32_t slot = n % TLK_RING;
+        mbar_wait(&ring_full[slot], (n / TLK_RING) & 1);
+        tc_fence_after();
+        const uint32_t w = ring + slot * TLK_SLICE;
+#pragma unroll
+        for (int kk = 0; kk < 6; ++kk)
+          umma_bf16(tmem + acc_col, umma_desc(a_addr + kk * 2 * 2048, 2048, 128), umma_desc(w + kk * 2 * 1536, 1536, 128), idesc,
+                    (accumulate || kk != 0) ? 1u : 0u);
+        umma_commit(&ring_empty[slot]);
+        ++n;
+      };
+      for (int mt = blockIdx.x; mt < a.MT; mt += gridDim.x, ++it) {
+        // out-projection -> acc 0
+        mbar_wait(o_full, it & 1);
+        mbar_wait(&acc_empty[0], (u0 & 1) ^ 1);
+        tc_fence_after();
+        gemm96(oh, 0, false);
+        umma_commit(&acc_full[0]); ++u0;
+        // feed-forward: FFN1 slab j -> acc 1, FFN2 K-slab j accumulates into acc 0
+        mbar_wait(y_ready, it & 1);
+        tc_fence_after();
+        for (int j = 0; j < 4; ++j, ++hcnt) {
+          mbar_wait(&acc_empty[1], (u1 & 1) ^ 1);
+          tc_fence_after();
+          gemm96(yy, 128, false);
+          umma_commit(&acc_full[1]); ++u1;
+          mbar_wait(h_ready, hcnt & 1);
+          if (j == 0) mbar_wait(&acc_empty[0], (u0 & 1) ^ 1);
+          tc_fence_after();
+          gemm96(oh, 0, j != 0);
+          umma_commit(h_free);
+        }
+        umma_commit(&acc_full[0]); ++u0;
+        umma_commit(oh_free);
+        // QKV of the next layer from X' (in the Y buffer): Q -> acc 1, K -> acc 0, V -> acc 1
+        if (!a.last) {
+          mbar_wait(x_ready, it & 1);
+          tc_fence_after();
+          for (int q = 0; q < 3; ++q) {
+            const int s = (q == 1) ? 0 : 1;
+            uint32_t &u = s ? u1 : u0;
+            mbar_wait(&acc_empty[s], (u & 1) ^ 1);
+            tc_fence_after();
+            gemm96(yy, s * 128, false);
+            umma_commit(&acc_full[s]); ++u;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue warps: thread = token row ------------------------------
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t it = 0, u0 = 0, u1 = 0, hcnt = 0;
+    auto load_acc = [&](int s, uint32_t &u, float (&v)[96]) {
+      mbar_wait(&acc_full[s], u & 1);
+      ++u;
+      tc_fence_after();
+      const uint32_t taddr = tmem + lane_base + s * 128;
+      float t0[32];
+      tmem_ld32(taddr, t0);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[c] = t0[c];
+      tmem_ld32(taddr + 32, t0);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[32 + c] = t0[c];
+      tmem_ld32(taddr + 64, t0);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[64 + c] = t0[c];
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[s]);
+    };
+    for (int mt = blockIdx.x; mt < a.MT; mt += gridDim.x, ++it) {
+      const long long token = (long long)mt * 128 + row;
+      const bool valid = token < a.T;
+      float v[96];
+      // ---- E1: Y = LN1(X + drop(acc + bo)) -> sY ----
+      load_acc(0, u0, v);
+      {
+        const uint4 *res = reinterpret_cast<const uint4 *>(a.X) + ((size_t)mt * 12) * 128 + row;
+#pragma unroll
+        for (int cc = 0; cc < 12; ++cc) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[cc * 8 + j] += sBo[cc * 8 + j];
+          if (a.thr16) drop8(&v[cc * 8], (uint64_t)token * 12 + cc, a.thr16, a.dscale, a.key_o);
+          float r8[8];
+          unpack8_bf16(res[cc * 128], r8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[cc * 8 + j] += r8[j];
+        }
+        layer_norm96(v, sLn, sLn + 96);
+        uint4 *o = reinterpret_cast<uint4 *>(sY) + row;
+#pragma unroll
+        for (int cc = 0; cc < 12; ++cc) o[cc * 128] = pack8_bf16(&v[cc * 8]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(y_ready);
+      }
+      // ---- E2: H slab j = drop(relu(acc + b1[96j..])) -> sOH ----
+      for (int j = 0; j < 4; ++j, ++hcnt) {
+        load_acc(1, u1, v);
+        mbar_wait(h_free, (hcnt & 1) ^ 1);                  // FFN2 of the previous slab has consumed the buffer
+        uint4 *o = reinterpret_cast<uint4 *>(sOH) + row;
+#pragma unroll
+        for (int cc = 0; cc < 12; ++cc) {
+          float x[8];
+#pragma unroll
+          for (int jx = 0; jx < 8; ++jx) x[jx] = fmaxf(v[cc * 8 + jx] + sB1[j * 96 + cc * 8 + jx], 0.f);
+          if (a.thr16) drop8(x, ((uint64_t)token * 384 + j * 96) / 8 + cc, a.thr16, a.dscale, a.key_h);
+          o[cc * 128] = pack8_bf16(x);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(h_ready);
+      }
+      // ---- E3: X' = LN2(Y + drop(acc + b2)) ----
+      load_acc(0, u0, v);
+      {
+        const uint4 *yres = reinterpret_cast<const uint4 *>(sY) + row;
+#pragma unroll
+        for (int cc = 0; cc < 12; ++cc) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[cc * 8 + j] += sB2[cc * 8 + j];
+          if (a.thr16) drop8(&v[cc * 8], (uint64_t)token * 12 + cc, a.thr16, a.dscale, a.key_f);
+          float r8[8];
+          unpack8_bf16(yres[cc * 128], r8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[cc * 8 + j] += r8[j];
+        }
+        layer_norm96(v, sLn + 192, sLn + 288);
+        if (a.last) {
+          if (a.fnw != nullptr) layer_norm96(v, sLn + 384, sLn + 480);
+          if (valid) {
+            float *o = a.hidden + token * 96;
+#pragma unroll
+            for (int c = 0; c < 96; c += 4) *reinterpret_cast<float4 *>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            if (a.seq_img != nullptr) {
+              const long long sq = token / a.P;
+              const int pp = (int)(token - sq * a.P);
+              const long long bb = sq / a.seq_nodes;
+              const int nn = (int)(sq - bb * a.seq_nodes);
+              uint4 *o2 = reinterpret_cast<uint4 *>(a.seq_img) + ((size_t)bb * a.P * 12 + (size_t)pp * 12) * a.seq_rows + nn;
+#pragma unroll
+              for (int cc = 0; cc < 12; ++cc) o2[(size_t)cc * a.seq_rows] = pack8_bf16(&v[cc * 8]);
+            }
+          }
+        } else {
+          uint4 *o = reinterpret_cast<uint4 *>(sY) + row;
+          uint4 *og = reinterpret_cast<uint4 *>(a.Xout) + ((size_t)mt * 12) * 128 + row;
+#pragma unroll
+          for (int cc = 0; cc < 12; ++cc) {
+            const uint4 pk = pack8_bf16(&v[cc * 8]);
+            o[cc * 128] = pk;
+            og[cc * 128] = pk;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(x_ready);
+        }
+      }
+      // ---- E4: Q, K, V of the next layer ----
+      if (!a.last) {
+        const long long s = valid ? token / a.P : 0;
+        const int p = valid ? (int)(token - s * a.P) : 0;
+        for (int qq = 0; qq < 3; ++qq) {
+          if (qq == 1) load_acc(0, u0, v);
+          else load_acc(1, u1, v);
+#pragma unroll
+          for (int c = 0; c < 96; ++c) v[c] += sBq[qq * 96 + c];
+          if (!valid) continue;
+          if (qq == 0) {
+            const int rt = p >> 7, r = p & 127;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              uint4 *o = reinterpret_cast<uint4 *>(a.q_img) + (((size_t)s * 4 + h) * a.RT + rt) * 3 * 128 + r;
+#pragma unroll
+              for (int cc = 0; cc < 3; ++cc) {
+                float x[8];
+#pragma unroll
+                for (int jx = 0; jx < 8; ++jx) x[jx] = v[h * HD + cc * 8 + jx] * a.qscale;
+                o[cc * 128] = pack8_bf16(x);
+              }
+            }
+          } else {
+            uint8_t *base = (qq == 1) ? a.k_img : a.v_img;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              uint4 *o = reinterpret_cast<uint4 *>(base) + ((size_t)s * 4 + h) * 3 * a.Pk + p;
+#pragma unroll
+              for (int cc = 0; cc < 3; ++cc) o[(size_t)cc * a.Pk] = pack8_bf16(&v[h * HD + cc * 8]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
 // ---------------------------------------------------------------------------
 static size_t tcl_smem_bytes(int K, int Nout) {
   return (size_t)K * Nout * 2 + TCL_STAGES * SLICE_BYTES + 32 * 8 + (384 + 4 * 96) * 4 + 16;
@@ -899,6 +1193,19 @@ static int tc_linear_launch(const TcLinearArgs &a, cudaStream_t st) {
   }
 #undef TCL_LAUNCH
   return check_launch("tc_linear_kernel");
+}
+
+static size_t tlk_smem_bytes() { return TLK_RING * (size_t)TLK_SLICE + 2 * (size_t)SLICE_BYTES + (96 + 384 + 96 + 288 + 6 * 96) * 4 + 17 * 8 + 16; }
+
+static int tc_layer_launch(const TcLayerArgs &a, cudaStream_t st) {
+  int dev = 0, sms = 148, rc;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t smem = tlk_smem_bytes();
+  if ((rc = allow_smem(tc_layer_kernel, smem))) return rc;
+  const int grid = a.MT < 2 * sms ? a.MT : 2 * sms;
+  tc_layer_kernel<<<grid, TLK_THREADS, smem, st>>>(a);
+  return check_launch("tc_layer_kernel");
 }
 
 }  // namespace stepk
@@ -939,6 +1246,18 @@ extern "C" int step_tc_linear(const void *a_img, const void *w_img, const float 
   a.out_img = (uint8_t *)out_img; a.out_f32 = out_f32;
   a.dscale = 1.f;
   return tc_linear_launch(a, (cudaStream_t)stream);
+}
+
+extern "C" int step_tc_embed_fwd(const float *series, long long sB, long long sT, long long sN, int B, int N, int P,
+                                 const float *patch_w, const float *patch_b, const float *pos, void *x_img, float drop_p,
+                                 unsigned long long seed, void *stream) {
+  STEP_REQUIRE(series && patch_w && patch_b && pos && x_img && B > 0 && N > 0 && P > 0, "tc_embed: bad argument");
+  STEP_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "tc_embed: drop_p must be in [0, 1)");
+  uint32_t thr16 = 0; float dscale = 1.f;
+  if (drop_p > 0.f) { thr16 = (uint32_t)(drop_p * 65536.0f); dscale = 1.f / (1.f - drop_p); }
+  tc_embed_kernel<<<dim3((P + 31) / 32, (N + 15) / 16, B), 256, 0, (cudaStream_t)stream>>>(
+      series, sB, sT, sN, N, P, patch_w, patch_b, pos, reinterpret_cast<uint4 *>(x_img), thr16, dscale, rng_key(seed, 1));
+  return check_launch("tc_embed_kernel");
 }
 
 extern "C" int step_tc_linear_drop(const void *a_img, const void *w_img, const float *bias, long long T, int K, int Nout, int mode,
@@ -1085,6 +1404,39 @@ extern "C" int step_ts_encoder_fwd_bf16(const float *series, long long sB, long 
   STEP_LAUNCH_CHECK("tc_embed_kernel");
   uint8_t *cur = X, *nxt = X2;
   int rc;
+  bool fused = true;                      // one token-block kernel per layer (needs the per-layer slice buffers)
+  for (int l = 0; l < n_layers; ++l) fused = fused && (I[l].fused != nullptr);
+  if (fused) {
+    // QKV of layer 0 from the embedded tokens, then per layer: attention + ONE fused token-block kernel that also emits
+    // the next layer's Q/K/V (2 launches per layer)
+    TcLinearArgs a{};
+    a.A = cur; a.W = (const uint8_t *)I[0].in_proj; a.bias = L[0].in_proj_b; a.MT = (int)MT; a.K = 96; a.Nout = 288;
+    a.mode = TCM_QKV; a.T = T; a.q_img = Q; a.k_img = Kimg; a.v_img = Vimg; a.P = P; a.Pk = Pk; a.RT = RT;
+    a.qscale = 0.20412414523193154f * 1.4426950408889634f; a.dscale = 1.f;
+    if ((rc = tc_linear_launch(a, st))) return rc;
+    for (int l = 0; l < n_layers; ++l) {
+      const uint32_t site = 16u * (l + 1);
+      const bool last = (l == n_layers - 1);
+      if ((rc = tc_attn_launch(Q, Kimg, Vimg, O, (int)S, P, drop_p, seed, site + 1, st))) return rc;
+      TcLayerArgs t{};
+      t.O = O; t.X = cur; t.W = (const uint8_t *)I[l].fused;
+      t.bo = L[l].out_proj_b; t.b1 = L[l].lin1_b; t.b2 = L[l].lin2_b; t.bqkv = last ? nullptr : L[l + 1].in_proj_b;
+      t.ln1w = L[l].norm1_w; t.ln1b = L[l].norm1_b; t.ln2w = L[l].norm2_w; t.ln2b = L[l].norm2_b;
+      t.MT = (int)MT; t.P = P; t.Pk = Pk; t.RT = RT; t.T = T; t.last = last ? 1 : 0;
+      t.qscale = 0.20412414523193154f * 1.4426950408889634f;
+      t.thr16 = thr16; t.dscale = dscale;
+      t.key_o = rng_key(seed, site + 2); t.key_h = rng_key(seed, site + 3); t.key_f = rng_key(seed, site + 4);
+      if (last) {
+        t.fnw = fnw; t.fnb = fnb; t.hidden = hidden; t.seq_img = (uint8_t *)seq_img; t.seq_nodes = N;
+        t.seq_rows = (N + 127) / 128 * 128;
+      } else {
+        t.Xout = nxt; t.q_img = Q; t.k_img = Kimg; t.v_img = Vimg;
+      }
+      if ((rc = tc_layer_launch(t, st))) return rc;
+      uint8_t *tmp = cur; cur = nxt; nxt = tmp;
+    }
+    return STEP_OK;
+  }
   for (int l = 0; l < n_layers; ++l) {
     const uint32_t site = 16u * (l + 1);
     TcLinearArgs a{};

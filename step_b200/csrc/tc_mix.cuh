@@ -248,7 +248,9 @@ __global__ void __launch_bounds__(DP_THREADS, 1) tc_dP_kernel(TcDpArgs a) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t dp_smem[];
   const int mt = blockIdx.x, sb = blockIdx.y, s = sb / a.B, b = sb - s * a.B;
-  const int N = a.N, Nb = (N + 15) / 16 * 16;
+  // column tile of up to 256 target nodes (MMA N <= 256, 256 TMEM columns): grid.z tiles cover N > 256 (PEMS04/BAY/03/07)
+  const int N = a.N, col0 = blockIdx.z * 256;
+  const int Nb = min(256, (N - col0 + 15) / 16 * 16);
   const uint32_t a_img = 8 * 128 * 16, b_img = 8u * Nb * 16;      // 8 chunks (2 pairs x 32 channels) per time step
   const uint32_t stage_bytes = 2 * a_img + 2 * b_img;
   uint64_t *bars = reinterpret_cast<uint64_t *>(dp_smem + 2 * stage_bytes);
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) tc_dP_kernel(TcDpArgs a) {
       }
       // B: rows w; chunk = pair*4 + cg
       for (int u = wt; u < 8 * Nb; u += 256) {
-        const int chunk = u / Nb, w = u - chunk * Nb, pair = chunk >> 2, cg = chunk & 3;
+        const int chunk = u / Nb, wl = u - chunk * Nb, w = col0 + wl, pair = chunk >> 2, cg = chunk & 3;
         float hi[8], lo[8];
         if (w < N) {
           const float *src = (pair ? a.DQ[s] : a.DH) + toff + (size_t)w * 32 + cg * 8;
@@ -366,8 +368,9 @@ __global__ void __launch_bounds__(DP_THREADS, 1) tc_dP_kernel(TcDpArgs a) {
       for (int r = warp - 2; r < 128; r += 8) {
         const int v = mt * 128 + r;
         if (v >= N) break;
-        float *dst = dstb + (size_t)v * N;
-        for (int c = lane; c < N; c += 32) {
+        float *dst = dstb + (size_t)v * N + col0;
+        const int ncols = min(Nb, N - col0);
+        for (int c = lane; c < ncols; c += 32) {
           const float x = tile[r * ldt + c];
           if (shared) atomicAdd(dst + c, x);
           else dst[c] += x;
@@ -380,14 +383,14 @@ __global__ void __launch_bounds__(DP_THREADS, 1) tc_dP_kernel(TcDpArgs a) {
   if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
-inline bool tc_dP_supported(int N) { return (N + 15) / 16 * 16 <= 256; }
+inline bool tc_dP_supported(int N) { return N > 0; }
 
 inline int tc_dP_launch(const TcDpArgs &a, cudaStream_t st) {
   int rc = allow_smem(tc_dP_kernel, 227 * 1024);
   if (rc) return rc;
-  const int Nb = (a.N + 15) / 16 * 16;
+  const int Nb = a.N >= 256 ? 256 : (a.N + 15) / 16 * 16;
   const size_t smem = 2 * (size_t)(2 * 8 * 128 * 16 + 2 * 8 * Nb * 16) + 8 * 8 + 16;
-  tc_dP_kernel<<<dim3((a.N + 127) / 128, 3 * a.B), DP_THREADS, smem, st>>>(a);
+  tc_dP_kernel<<<dim3((a.N + 127) / 128, 3 * a.B, (a.N + 255) / 256), DP_THREADS, smem, st>>>(a);
   return check_launch("tc_dP_kernel");
 }
 

@@ -24,7 +24,7 @@ class TsLayerWeights(C.Structure):
 
 
 class TsLayerImages(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("in_proj", "out_proj", "lin1", "lin2")]
+    _fields_ = [(n, C.c_void_p) for n in ("in_proj", "out_proj", "lin1", "lin2", "fused")]
 
 
 class GwLayerParams(C.Structure):
@@ -62,6 +62,8 @@ SIGNATURES = {
     "step_tc_rows_to_image": (C.c_int, [f32p, ll, C.c_int, vp, vp]),
     "step_tc_image_to_rows": (C.c_int, [vp, ll, C.c_int, f32p, vp]),
     "step_tc_linear": (C.c_int, [vp, vp, f32p, ll, C.c_int, C.c_int, C.c_int, vp, f32p, f32p, vp, f32p, vp]),
+    "step_tc_embed_fwd": (C.c_int, [f32p, ll, ll, ll, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, vp, C.c_float, ull, vp]),
+    "step_gwnet_dropout_probe": (C.c_int, [f32p, ll, C.c_float, ull, C.c_int, f32p, vp]),
     "step_tc_linear_drop": (C.c_int, [vp, vp, f32p, ll, C.c_int, C.c_int, C.c_int, vp, f32p, f32p, vp, f32p, C.c_float, ull, vp]),
     "step_tc_attn_image_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "step_tc_qkv": (C.c_int, [vp, vp, f32p, C.c_int, C.c_int, vp, vp, vp, vp]),
@@ -99,8 +101,8 @@ SIGNATURES = {
     "step_gw_adp_fwd": (C.c_int, [f32p, f32p, C.c_int, C.c_int, f32p, vp]),
     "step_gw_adp_bwd": (C.c_int, [f32p, f32p, f32p, f32p, C.c_int, C.c_int, f32p, f32p, f32p, vp]),
     "step_opt_chunk_elems": (C.c_int, []),
-    "step_clip_adam_step": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, f32p, f32p, vp, C.c_float, C.c_float, C.c_float, C.c_float,
-                                      C.c_float, C.c_float, ll, f32p, vp]),
+    "step_clip_adam_step": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, f32p, f32p, vp, C.c_float, C.c_float, C.c_float,
+                                      C.c_float, C.c_float, C.c_float, f32p, vp]),
     "step_metrics_accumulate": (C.c_int, [f32p, f32p, ll, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp, vp]),
     "step_gwnet_stash_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "step_gwnet_stack_fwd": (C.c_int, [f32p, f32p, f32p, f32p, C.POINTER(GwLayerParams), C.c_int, C.c_int, C.c_int, C.c_int,
@@ -110,7 +112,7 @@ SIGNATURES = {
                                        f32p, f32p, f32p, f32p, vp]),
 }
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 _lib = None
 _lock = threading.Lock()
 

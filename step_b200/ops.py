@@ -532,7 +532,8 @@ class GwEpilogue(torch.autograd.Function):
         dh1 = gemm(dz2, w2, transB=True, epilogue=GE_MASK, aux=h1)
         dw1 = gemm(dh1, h, transA=True, transB=True, ksplit=_ksplit(w1.shape[0], w1.shape[1], M))
         db1 = colsum(dh1)
-        return None, dx2, dw1, db1, dw2, db2, dwe1, dbe1, dwe2, dbe2
+        dh = gemm(dh1, w1, transB=True) if ctx.needs_input_grad[0] else None     # STEP: frozen TSFormer, no consumer
+        return dh, dx2, dw1, db1, dw2, db2, dwe1, dbe1, dwe2, dbe2
 
 
 class GwStart(torch.autograd.Function):
@@ -622,6 +623,12 @@ class GwAdaptive(torch.autograd.Function):
 # --------------------------------------------------------------------------- #
 # bf16 tensor-core encoder (tcgen05 / TMEM / TMA bulk)
 # --------------------------------------------------------------------------- #
+import os as _os
+
+# one fused token-block kernel per layer (default) or the four separate token GEMMs (STEP_B200_TS_FUSED=0: A/B, tests)
+TS_FUSED_LAYER = _os.environ.get("STEP_B200_TS_FUSED", "1") != "0"
+
+
 def tc_pack_weight(w: Tensor) -> Tensor:
     """fp32 [Nout, K] -> bf16 weight image (uint8 tensor of Nout*K*2 bytes)."""
     w = _f32(w, "w")
@@ -688,10 +695,25 @@ def tc_qkv_attention(x_img: Tensor, w_img: Tensor, bias: Tensor, S: int, P: int,
     return o
 
 
-def ts_pack_layer_images(layers: Sequence[Dict[str, Tensor]]):
-    """Pack the four weight matrices of every encoder layer into bf16 UMMA images (done once: the TSFormer is frozen)."""
-    return [{"in_proj": tc_pack_weight(lw["in_proj_w"]), "out_proj": tc_pack_weight(lw["out_proj_w"]),
-             "lin1": tc_pack_weight(lw["lin1_w"]), "lin2": tc_pack_weight(lw["lin2_w"])} for lw in layers]
+def ts_pack_layer_images(layers: Sequence[Dict[str, Tensor]], fused: bool = True):
+    """Pack the four weight matrices of every encoder layer into bf16 UMMA images (done once: the TSFormer is frozen).
+    ``fused``: also the slice buffer of the fused token-block kernel (twelve [96 x 96] slices in program order: out_proj,
+    4 x (lin1 rows, lin2 K-columns), then the NEXT layer's q / k / v projections)."""
+    out = []
+    for i, lw in enumerate(layers):
+        im = {"in_proj": tc_pack_weight(lw["in_proj_w"]), "out_proj": tc_pack_weight(lw["out_proj_w"]),
+              "lin1": tc_pack_weight(lw["lin1_w"]), "lin2": tc_pack_weight(lw["lin2_w"]), "fused": None}
+        if fused:
+            parts = [im["out_proj"]]
+            for j in range(4):
+                parts.append(tc_pack_weight(lw["lin1_w"][96 * j:96 * (j + 1)].contiguous()))
+                parts.append(tc_pack_weight(lw["lin2_w"][:, 96 * j:96 * (j + 1)].contiguous()))
+            if i + 1 < len(layers):
+                nxt = layers[i + 1]["in_proj_w"]
+                parts += [tc_pack_weight(nxt[96 * j:96 * (j + 1)].contiguous()) for j in range(3)]
+            im["fused"] = torch.cat(parts)
+        out.append(im)
+    return out
 
 
 def ts_encoder_forward_bf16(series: Tensor, patch_w: Tensor, patch_b: Tensor, pos: Tensor, layers: Sequence[Dict[str, Tensor]],
@@ -716,6 +738,7 @@ def ts_encoder_forward_bf16(series: Tensor, patch_w: Tensor, patch_b: Tensor, po
     for i, im in enumerate(images):
         for name in ("in_proj", "out_proj", "lin1", "lin2"):
             setattr(iarr[i], name, im[name].data_ptr())
+        iarr[i].fused = None if (im.get("fused") is None or not TS_FUSED_LAYER) else im["fused"].data_ptr()
     pw, pb, ps = _f32(patch_w.reshape(96, 12), "patch_w"), _f32(patch_b, "patch_b"), _f32(pos, "pos")
     nw, nb = _f32(norm_w, "norm_w"), _f32(norm_b, "norm_b")
     sB, sT, sN = series.stride()
@@ -723,7 +746,7 @@ def ts_encoder_forward_bf16(series: Tensor, patch_w: Tensor, patch_b: Tensor, po
                                         iarr, len(layers), nw.data_ptr(), nb.data_ptr(), hidden.data_ptr(), _p(seq_img),
                                         ws.data_ptr(), ws_bytes, float(drop_p), int(seed) & (2**64 - 1), st),
           "step_ts_encoder_fwd_bf16")
-    launch_counter["kernels"] += 1 + len(layers) * 5
+    launch_counter["kernels"] += 2 + len(layers) * 2 if TS_FUSED_LAYER else 1 + len(layers) * 5
     return (hidden, seq_img) if want_seq_image else hidden
 
 

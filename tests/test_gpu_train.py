@@ -45,7 +45,7 @@ def test_fused_clip_adam_matches_torch(max_norm, wd):
     assert ref2.param_groups[0]["lr"] == 5e-3 and len(ref2.state) == len(shapes)
     again = FusedClipAdam([torch.nn.Parameter(p.detach().clone()) for p in my_p], lr=1.0)
     again.load_state_dict(ref_opt.state_dict())
-    assert again.step_count == 4 and again.lr == 5e-3
+    assert again.step_count == 4 and again.lr == 5e-3 and again._steps[0].tolist() == [4, 4, 3, 4, 4, 4]
     o = again.state_off[3]
     assert torch.allclose(again.exp_avg[o:o + 256 * 512].view(256, 512), ref_opt.state[ref_p[3]]["exp_avg"], atol=1e-7)
 
@@ -109,10 +109,9 @@ def test_checkpoint_round_trip_and_training_steps(tmp_path):
     model2, opt2 = make()
     info = load_checkpoint(path, model2, opt2)
     assert info == {"epoch": 1, "best_metrics": {"val_MAE": 3.5}} and opt2.step_count == 3
-    for a, b in zip(model.discrete_graph_learning.bn1.buffers(), model2.discrete_graph_learning.bn1.buffers()):
-        pass
     resumed = [step(model2, opt2) for _ in range(2)]
-    assert resumed == cont
+    # same state, same inputs; split-K fp32 atomics make the weight gradients agree to ~1e-6 relative, not bitwise
+    assert all(abs(a - b) < 1e-4 * max(1.0, abs(a)) for a, b in zip(resumed, cont))
 
 
 def test_device_window_loader_on_gpu_feeds_the_runner():
