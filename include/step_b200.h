@@ -208,6 +208,12 @@ int step_tc_hidden_to_seq_image(const float *hidden, int B, int N, int P, void *
  * diagonal).  gram_scratch, sim: [B,N,N] fp32. */
 int step_tc_cosine_gram(const void *seq_img, int B, int N, int P, float *gram_scratch, float *sim, void *stream);
 
+/* Node-sharded mode: raw Gram rows of the 128-row tiles tile_first, tile_first + tile_step, ... only (a rank's share; the
+ * other rows of `gram` [B,N,N] are left untouched - a zero-initialised buffer summed over ranks is the full matrix), and
+ * the normalisation sim = G / ((sqrt(G_ii)+1e-7)(sqrt(G_jj)+1e-7)) as a separate step after the exchange. */
+int step_tc_gram_rows(const void *seq_img, int B, int N, int P, int tile_first, int tile_step, float *gram, void *stream);
+int step_gram_normalize(const float *gram, int B, int N, float *sim, void *stream);
+
 /* ------------------------------------------------------------------------ *
  * kNN prior graph: cosine-similarity Gram matrix + global top-k select
  *   step/step_arch/similarity.py:6-16,

@@ -56,6 +56,7 @@ class DiscreteGraphLearning(nn.Module):
         self.dropout = nn.Dropout(0.5)                            # unused (as in the reference)
         self.gumbel_uniform = None     # optional [B, N*N, 2] U(0,1) draws to inject (tests / reproduction)
         self.theta = None              # softmax(bernoulli_unnorm)[..., 0] of the last forward, [N, N]
+        self.before_trainable = None   # optional callable run after the frozen encoder, before the first trainable parameter is read
         self._calls = 0
         self._feats_dev = None
 
@@ -101,8 +102,12 @@ class DiscreteGraphLearning(nn.Module):
     def forward(self, long_term_history, tsformer):
         """long_term_history [B, P*L, N, C] -> (bernoulli_unnorm [B,N*N,2], hidden [B,N,P,d], adj_knn, sampled_adj)."""
         batch_size, _, num_nodes, _ = long_term_history.shape
-        feat = self._global_feature(long_term_history.device)
+        # the frozen encoder first: it touches no trainable parameter, so a gradient all-reduce of the previous step that is
+        # still in flight (parallel.GradReducer.reduce(async_op=True)) overlaps with it and is joined right after
         hidden_states = tsformer(long_term_history[..., 0:1])        # a strided view: the encoder reads it in place
+        if self.before_trainable is not None:
+            self.before_trainable()
+        feat = self._global_feature(long_term_history.device)
         half = self.embedding_dim
         # the two halves of fc_out (reference :148-151 after the one-hot gathers), split-bf16 tcgen05 GEMMs
         w_send, w_recv = self.fc_out.weight[:, :half].contiguous(), self.fc_out.weight[:, half:].contiguous()
@@ -118,7 +123,13 @@ class DiscreteGraphLearning(nn.Module):
         if seq_img is not None:
             # bf16 mode: the encoder also emitted its output as the K-major operand image of the Gram GEMM (tcgen05)
             with torch.no_grad():
-                sim = ops.tc_cosine_gram(seq_img, batch_size, num_nodes, hidden_states.shape[2])
+                shard = getattr(tsformer, "node_shard", None)
+                if shard is not None and shard[1] > 1 and getattr(tsformer, "gathered_patches", None):
+                    from step_b200 import parallel
+                    sim = ops.tc_cosine_gram_sharded(seq_img, batch_size, num_nodes, tsformer.gathered_patches, shard[0], shard[1],
+                                                     parallel.all_reduce_sum)
+                else:
+                    sim = ops.tc_cosine_gram(seq_img, batch_size, num_nodes, hidden_states.shape[2])
                 adj_knn = ops.topk_mask(sim, self.k * self.num_nodes)
         else:
             adj_knn = ops.knn_prior(hidden_states, self.k * self.num_nodes)

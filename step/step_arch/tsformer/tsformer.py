@@ -153,6 +153,7 @@ class TSFormer(nn.Module):
         # node-sharded mode (STEP_PEMS07 on several GPUs): (rank, world) -> this rank encodes only its node range and
         # the hidden states are assembled with one NCCL all-gather (step_b200.parallel.all_gather_nodes)
         self.node_shard = None
+        self.gathered_patches = None  # node-parallel bf16 path: P of the sequence image (hidden then holds the last patch only)
         self._calls = 0
         self.initialize_weights()
 
@@ -196,11 +197,20 @@ class TSFormer(nn.Module):
             hidden = ops.ts_encoder_forward(series, emb.weight, emb.bias, self.positional_encoding.position_embedding, layers,
                                             self.encoder_norm.weight, self.encoder_norm.bias, drop_p=drop, seed=seed,
                                             chunk_seqs=self.chunk_seqs)
-        if self.node_shard is not None:
+        if self.node_shard is not None and self.node_shard[1] > 1:
             from step_b200 import parallel
             rank, world = self.node_shard
-            hidden = parallel.all_gather_nodes(hidden, num_nodes, rank, world)
-            self.seq_image = ops.tc_hidden_to_seq_image(hidden) if self.precision == "bf16" and hidden.shape[2] * 12 % 8 == 0 else None
+            if self.precision == "bf16" and self.seq_image is not None:
+                # node-parallel, bf16 path: ONE all-gather of the bf16 Gram operand image (half the bytes of the fp32 states)
+                # plus the last-patch states the forecaster consumes ([B,N,1,96], 0.3 % of the states).  STEP only reads
+                # hidden[:, :, -1, :] (reference step.py:58), which this [B,N,1,96] tensor serves.
+                B, P = hidden.shape[0], hidden.shape[2]
+                self.seq_image = parallel.all_gather_seq_image(self.seq_image, B, P * 12, num_nodes, rank, world)
+                hidden = parallel.gather_node_rows(hidden[:, :, -1:, :], num_nodes, rank, world)
+                self.gathered_patches = P
+            else:
+                hidden = parallel.all_gather_nodes(hidden, num_nodes, rank, world)
+                self.seq_image = ops.tc_hidden_to_seq_image(hidden) if self.precision == "bf16" and hidden.shape[2] * 12 % 8 == 0 else None
         return hidden, None, None
 
     @torch.no_grad()

@@ -767,11 +767,12 @@ struct TcGramArgs {
   const uint8_t *img;
   float *gram;              // [B][N][N] raw dot products
   int N, R, KC;             // nodes, padded rows per chunk, chunks per sample (multiple of TG_KC)
+  int tile_first, tile_step; // row tiles handled by this launch: tile_first + i * tile_step (a rank's share when sharded)
 };
 
 __global__ void __launch_bounds__(192, 1) tc_gram_kernel(TcGramArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int b = blockIdx.z, mt = blockIdx.y, nblk = blockIdx.x;
+  const int b = blockIdx.z, mt = a.tile_first + blockIdx.y * a.tile_step, nblk = blockIdx.x;
   const int col0 = nblk * 256;
   const int Rb = min(256, a.R - col0);                         // B rows staged per chunk
   const int Ncols = min(256, ((a.N - col0) + 15) / 16 * 16);   // MMA N
@@ -1343,22 +1344,40 @@ extern "C" int step_tc_hidden_to_seq_image(const float *hidden, int B, int N, in
   return check_launch("tc_hidden_to_seq_image_kernel");
 }
 
-extern "C" int step_tc_cosine_gram(const void *seq_img, int B, int N, int P, float *gram_scratch, float *sim, void *stream) {
-  STEP_REQUIRE(seq_img && gram_scratch && sim && B > 0 && N > 0 && P > 0, "tc_cosine_gram: bad argument");
+static int tc_gram_raw_launch(const void *seq_img, int B, int N, int P, int tile_first, int tile_step, float *gram, cudaStream_t st) {
   if ((P * 12) % TG_KC != 0) return fail(STEP_EUNSUPPORTED, "tc_cosine_gram: P*12 = %lld must be a multiple of 8", (long long)P * 12);
-  cudaStream_t st = (cudaStream_t)stream;
   TcGramArgs a{};
-  a.img = (const uint8_t *)seq_img; a.gram = gram_scratch; a.N = N; a.R = (N + 127) / 128 * 128; a.KC = P * 12;
+  a.img = (const uint8_t *)seq_img; a.gram = gram; a.N = N; a.R = (N + 127) / 128 * 128; a.KC = P * 12;
+  a.tile_first = tile_first; a.tile_step = tile_step;
+  const int tiles = a.R / 128;
+  const int mine = tile_first < tiles ? (tiles - tile_first + tile_step - 1) / tile_step : 0;
+  if (mine == 0) return STEP_OK;
   const int nblk = (N + 255) / 256;
   const int Rb = a.R < 256 ? a.R : 256;
   const size_t smem = TG_STAGES * (size_t)(TG_KC * 2048 + TG_KC * Rb * 16) + 16 * 8 + 16;
   int rc = allow_smem(tc_gram_kernel, 227 * 1024);
   if (rc) return rc;
-  tc_gram_kernel<<<dim3(nblk, a.R / 128, B), 192, smem, st>>>(a);
-  STEP_LAUNCH_CHECK("tc_gram_kernel");
+  tc_gram_kernel<<<dim3(nblk, mine, B), 192, smem, st>>>(a);
+  return check_launch("tc_gram_kernel");
+}
+
+extern "C" int step_tc_gram_rows(const void *seq_img, int B, int N, int P, int tile_first, int tile_step, float *gram, void *stream) {
+  STEP_REQUIRE(seq_img && gram && B > 0 && N > 0 && P > 0 && tile_first >= 0 && tile_step >= 1, "tc_gram_rows: bad argument");
+  return tc_gram_raw_launch(seq_img, B, N, P, tile_first, tile_step, gram, (cudaStream_t)stream);
+}
+
+extern "C" int step_gram_normalize(const float *gram, int B, int N, float *sim, void *stream) {
+  STEP_REQUIRE(gram && sim && B > 0 && N > 0, "gram_normalize: bad argument");
   const long long per = (long long)N * N;
-  gram_normalize_kernel<<<dim3((unsigned)((per + 255) / 256), B), 256, 0, st>>>(gram_scratch, N, sim);
+  gram_normalize_kernel<<<dim3((unsigned)((per + 255) / 256), B), 256, 0, (cudaStream_t)stream>>>(gram, N, sim);
   return check_launch("gram_normalize_kernel");
+}
+
+extern "C" int step_tc_cosine_gram(const void *seq_img, int B, int N, int P, float *gram_scratch, float *sim, void *stream) {
+  STEP_REQUIRE(seq_img && gram_scratch && sim && B > 0 && N > 0 && P > 0, "tc_cosine_gram: bad argument");
+  int rc = tc_gram_raw_launch(seq_img, B, N, P, 0, 1, gram_scratch, (cudaStream_t)stream);
+  if (rc) return rc;
+  return step_gram_normalize(gram_scratch, B, N, sim, stream);
 }
 
 // packed weight images of one encoder layer

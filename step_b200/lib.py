@@ -75,6 +75,8 @@ SIGNATURES = {
     "step_tc_seq_image_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "step_tc_hidden_to_seq_image": (C.c_int, [f32p, C.c_int, C.c_int, C.c_int, vp, vp]),
     "step_tc_cosine_gram": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, f32p, f32p, vp]),
+    "step_tc_gram_rows": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, vp]),
+    "step_gram_normalize": (C.c_int, [f32p, C.c_int, C.c_int, f32p, vp]),
     "step_cosine_gram_f32": (C.c_int, [f32p, C.c_int, C.c_int, ll, f32p, f32p, vp]),
     "step_topk_mask_f32": (C.c_int, [f32p, C.c_int, C.c_int, C.c_int, f32p, vp]),
     "step_edge_logits_fwd": (C.c_int, [f32p, f32p, f32p, f32p, C.c_int, C.c_int, f32p, f32p, vp]),

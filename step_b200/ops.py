@@ -625,8 +625,12 @@ class GwAdaptive(torch.autograd.Function):
 # --------------------------------------------------------------------------- #
 import os as _os
 
-# one fused token-block kernel per layer (default) or the four separate token GEMMs (STEP_B200_TS_FUSED=0: A/B, tests)
-TS_FUSED_LAYER = _os.environ.get("STEP_B200_TS_FUSED", "1") != "0"
+# STEP_B200_TS_FUSED=1: one fused token-block kernel per layer (out-proj + LN1 + FFN + LN2 + next QKV, tc_layer_kernel)
+# instead of the four separate token GEMMs.  It is bit-identical and moves 2.7x fewer HBM bytes, but measured 0.84 ms vs
+# 0.74 ms per layer at METR-LA (profiles/r02_fused_layer.md): its per-tile chain of 21 dependent MMA -> epilogue hops is
+# latency-bound with the two co-resident CTAs the 512 TMEM columns allow, so the separate, deeply pipelined kernels stay
+# the default.
+TS_FUSED_LAYER = _os.environ.get("STEP_B200_TS_FUSED", "0") == "1"
 
 
 def tc_pack_weight(w: Tensor) -> Tensor:
@@ -759,6 +763,20 @@ def tc_hidden_to_seq_image(hidden: Tensor) -> Tensor:
     check(_L().step_tc_hidden_to_seq_image(hidden.data_ptr(), B, N, P, img.data_ptr(), st), "step_tc_hidden_to_seq_image")
     launch_counter["kernels"] += 1
     return img
+
+
+def tc_cosine_gram_sharded(seq_img: Tensor, B: int, N: int, P: int, rank: int, world: int, all_reduce_sum) -> Tensor:
+    """Node-parallel mode: every rank holds the full bf16 sequence image, computes the raw Gram rows of its share of the
+    128-row tiles (tile t belongs to rank t mod world), one small all-reduce (B*N*N fp32) assembles the matrix, then the
+    cosine normalisation runs replicated."""
+    st = _enter(seq_img)
+    gram = torch.zeros(B, N, N, device=seq_img.device, dtype=torch.float32)
+    check(_L().step_tc_gram_rows(seq_img.data_ptr(), B, N, P, rank, world, gram.data_ptr(), st), "step_tc_gram_rows")
+    all_reduce_sum(gram)
+    sim = torch.empty_like(gram)
+    check(_L().step_gram_normalize(gram.data_ptr(), B, N, sim.data_ptr(), st), "step_gram_normalize")
+    launch_counter["kernels"] += 2
+    return sim
 
 
 def tc_cosine_gram(seq_img: Tensor, B: int, N: int, P: int) -> Tensor:

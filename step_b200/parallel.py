@@ -85,12 +85,18 @@ class GradReducer:
         self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
         self.big_numel = big_numel
         self._flat = None
+        self._comm_stream = None
+        self._pending = False
 
     def zero(self) -> None:
         for p in self.params:
             p.grad = None
 
-    def reduce(self) -> None:
+    def reduce(self, async_op: bool = False) -> None:
+        """Average the gradients over the ranks.  ``async_op=True``: the collectives are enqueued on a side stream and
+        ``wait()`` joins them later - the frozen TSFormer encoder of the NEXT step (40 % of the step, no trainable
+        parameter) runs meanwhile, so the 160 MB all-reduce leaves the critical path; ``wait()`` must be called before the
+        gradients / the parameters they update are used (STEP: ``discrete_graph_learning.before_trainable``)."""
         if self.world <= 1:
             return
         big, small = [], []
@@ -102,6 +108,20 @@ class GradReducer:
                 g = g.contiguous()
                 p.grad = g
             (big if g.numel() >= self.big_numel else small).append(g)
+        dev = (big + small)[0].device if (big or small) else None
+        if async_op and dev is not None and dev.type == "cuda":
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(dev)
+            self._comm_stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(self._comm_stream):
+                self._reduce_now(big, small)
+                for g in big + small:
+                    g.record_stream(self._comm_stream)
+            self._pending = True
+        else:
+            self._reduce_now(big, small)
+
+    def _reduce_now(self, big, small) -> None:
         works = [dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True) for g in big]
         if small:
             n = sum(g.numel() for g in small)
@@ -119,6 +139,12 @@ class GradReducer:
             w.wait()
         if big:
             torch._foreach_div_(big, float(self.world))
+
+    def wait(self) -> None:
+        """Join an asynchronous ``reduce``: the current stream waits for the side stream's collectives."""
+        if self._pending:
+            torch.cuda.current_stream(self._comm_stream.device).wait_stream(self._comm_stream)
+            self._pending = False
 
 
 def node_shard_bounds(num_nodes: int, rank: int, world: int) -> tuple:
@@ -146,3 +172,54 @@ def all_gather_nodes(local: torch.Tensor, num_nodes: int, rank: int, world: int,
         n0, n1 = node_shard_bounds(num_nodes, r, world)
         full[:, n0:n1] = gathered[r, :, : n1 - n0]
     return full
+
+
+def gather_node_rows(local: torch.Tensor, num_nodes: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """All-gather along the node axis (dim 1) for any trailing shape: local [B, n1-n0, ...] -> [B, N, ...].
+    Shards may differ by one node and travel padded to the largest."""
+    if world == 1:
+        return local
+    B, nloc = local.shape[:2]
+    tail = tuple(local.shape[2:])
+    nmax = (num_nodes + world - 1) // world
+    send = local.contiguous()
+    if nloc < nmax:
+        send = torch.zeros((B, nmax) + tail, device=local.device, dtype=local.dtype)
+        send[:, :nloc] = local
+    gathered = torch.empty((world, B, nmax) + tail, device=local.device, dtype=local.dtype)
+    dist.all_gather_into_tensor(gathered.view((world * B, nmax) + tail), send, group=group)
+    full = torch.empty((B, num_nodes) + tail, device=local.device, dtype=local.dtype)
+    for r in range(world):
+        n0, n1 = node_shard_bounds(num_nodes, r, world)
+        full[:, n0:n1] = gathered[r, :, : n1 - n0]
+    return full
+
+
+def all_gather_seq_image(img_local: torch.Tensor, B: int, KC: int, num_nodes: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """Node-parallel mode, bf16 path: the encoder's Gram operand image of the LOCAL nodes ([B][KC][R_loc][8] bf16, as a flat
+    uint8 tensor, R_loc = nodes rounded up to 128) is all-gathered over NVLink - 2 bytes per hidden value instead of the 4 of
+    the fp32 states (114 vs 228 MB at PEMS07) - and re-assembled as the image of all N nodes ([B][KC][R_full][8])."""
+    n0, n1 = node_shard_bounds(num_nodes, rank, world)
+    nloc = n1 - n0
+    r_loc = (nloc + 127) // 128 * 128
+    r_full = (num_nodes + 127) // 128 * 128
+    loc = img_local.view(B, KC, r_loc, 16)
+    if world == 1:
+        return img_local
+    nmax = (num_nodes + world - 1) // world
+    send = loc[:, :, :nmax] if r_loc >= nmax else torch.cat(
+        [loc, torch.zeros(B, KC, nmax - r_loc, 16, device=loc.device, dtype=loc.dtype)], dim=2)
+    send = send.contiguous()
+    gathered = torch.empty(world, B, KC, nmax, 16, device=loc.device, dtype=loc.dtype)
+    dist.all_gather_into_tensor(gathered.view(world * B, KC, nmax, 16), send, group=group)
+    full = torch.zeros(B, KC, r_full, 16, device=loc.device, dtype=loc.dtype)
+    for r in range(world):
+        m0, m1 = node_shard_bounds(num_nodes, r, world)
+        full[:, :, m0:m1] = gathered[r, :, :, : m1 - m0]
+    return full.view(-1)
+
+
+def all_reduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t

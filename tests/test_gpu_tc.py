@@ -161,8 +161,8 @@ def test_tc_attention_dropout_statistics():
 
 @pytest.mark.parametrize("B,N,P,drop", [(2, 9, 168, 0.0), (1, 11, 336, 0.0), (3, 5, 24, 0.0), (2, 13, 168, 0.1)])
 def test_fused_token_block_kernel_matches_separate_kernels(B, N, P, drop):
-    """One fused kernel per layer (out-proj + LN1 + FFN + LN2 + next layer's QKV, intermediates in shared memory) vs the four
-    separate token GEMM launches: same MMA order, same dropout counters -> the hidden states and the Gram operand image are
+    """The optional fused kernel per layer (STEP_B200_TS_FUSED=1: out-proj + LN1 + FFN + LN2 + next layer's QKV,
+    intermediates in shared memory) vs the default four separate token GEMM launches: same MMA order, same dropout counters -> the hidden states and the Gram operand image are
     bit-identical, with and without dropout."""
     from step_b200 import ops
     sd = O.synthetic_tsformer_params(2)
@@ -184,4 +184,5 @@ def test_fused_token_block_kernel_matches_separate_kernels(B, N, P, drop):
         ops.TS_FUSED_LAYER = prev
     assert torch.isfinite(outs[True][0]).all()
     assert torch.equal(outs[True][0], outs[False][0])
-    assert torch.equal(outs[True][1], outs[False][1])
+    # the image's padding rows (nodes .. 128-row boundary) are never written: compare what the Gram GEMM reads from it
+    assert torch.equal(ops.tc_cosine_gram(outs[True][1], B, N, P), ops.tc_cosine_gram(outs[False][1], B, N, P))

@@ -143,3 +143,48 @@ def test_all_gather_nodes_world2_uneven():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True, (0, 4)), (1, True, (4, 7))]
+
+
+def _image_worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from step_b200 import parallel
+    parallel.init_from_env("gloo")
+    B, N, KC = 2, 300, 5                            # 300 nodes over 2 ranks: 150 + 150 -> local images padded to 256 rows
+    r_full = (N + 127) // 128 * 128
+    g = torch.Generator().manual_seed(3)
+    full = torch.randint(0, 255, (B, KC, r_full, 16), dtype=torch.uint8, generator=g)
+    full[:, :, N:] = 0
+    n0, n1 = parallel.node_shard_bounds(N, rank, world)
+    r_loc = (n1 - n0 + 127) // 128 * 128
+    local = torch.zeros(B, KC, r_loc, 16, dtype=torch.uint8)
+    local[:, :, : n1 - n0] = full[:, :, n0:n1]
+    got = parallel.all_gather_seq_image(local.view(-1), B, KC, N, rank, world)
+    ok_img = bool(torch.equal(got.view(B, KC, r_full, 16), full))
+    # node rows with an arbitrary trailing shape (the last-patch hidden states [B, n, 1, 96]) and an uneven split
+    N2 = 7
+    rows = torch.arange(B * N2 * 1 * 4, dtype=torch.float32).view(B, N2, 1, 4)
+    m0, m1 = parallel.node_shard_bounds(N2, rank, world)
+    ok_rows = bool(torch.equal(parallel.gather_node_rows(rows[:, m0:m1], N2, rank, world), rows))
+    # the Gram exchange: every rank fills its tiles' rows of a zero matrix, the sum over ranks is the full matrix
+    gram = torch.zeros(3, 3)
+    gram[rank] = float(rank + 1)
+    parallel.all_reduce_sum(gram)
+    ok_sum = bool(torch.equal(gram, torch.tensor([[1.0] * 3, [2.0] * 3, [0.0] * 3])))
+    out.put((rank, ok_img, ok_rows, ok_sum))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_node_parallel_exchanges_world2():
+    """Node-parallel mode host logic: bf16 sequence-image all-gather + re-assembly, last-patch row gather, Gram row exchange."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_image_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(out.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True, True, True), (1, True, True, True)]

@@ -55,3 +55,25 @@ for M in (69, 414, 883, 6624):
         check(f"dwe1 = de1^T x2 (ksplit {ks})", lambda: ops.gemm(G(de1r), G(x2r), transA=True, transB=True, ksplit=ks), de1r.t() @ x2r)
         check(f"dwe2 = dout^T e1 (ksplit {ks})", lambda: ops.gemm(doutd, G(e1r), transA=True, transB=True, ksplit=ks), D(dout).t() @ e1r)
     check("colsum(dout)", lambda: ops.colsum(doutd), D(dout).sum(0))
+
+print("==== GwEpilogue autograd Function, all gradients ====")
+for M in (69, 414, 883):
+    for rep in range(2):
+        g = torch.Generator().manual_seed(M + 1000)
+        h, skip = torch.randn(M, 96, generator=g), torch.randn(M, 256, generator=g)
+        shapes = [(512, 96), (512,), (256, 512), (256,), (512, 256), (512,), (12, 512), (12,)]
+        ps = [torch.randn(*s, generator=g) / math.sqrt(s[-1] if len(s) > 1 else 16.0) for s in shapes]
+        dout = torch.randn(M, 12, generator=g)
+        L = [t.double().requires_grad_(True) for t in ps]
+        sk = skip.double().requires_grad_(True)
+        hs = torch.relu(torch.relu(h.double() @ L[0].t() + L[1]) @ L[2].t() + L[3])
+        ref = torch.relu(torch.relu(sk + hs) @ L[4].t() + L[5]) @ L[6].t() + L[7]
+        ref.backward(dout.double())
+        mp = [t.to(DEV).requires_grad_(True) for t in ps]
+        ms = skip.to(DEV).requires_grad_(True)
+        out = ops.GwEpilogue.apply(h.to(DEV), ms, *mp)
+        out.backward(dout.to(DEV))
+        names = ["w1", "b1", "w2", "b2", "we1", "be1", "we2", "be2"]
+        line = f"M={M} rep={rep} out {rel(out.detach(), ref.detach()):.1e} dskip {rel(ms.grad, sk.grad):.1e} " + \
+            " ".join(f"{n} {rel(m.grad, l.grad):.1e}" for n, m, l in zip(names, mp, L))
+        print(line, flush=True)
