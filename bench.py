@@ -442,6 +442,33 @@ def run_e2e(arm, steps, dev, world):
     return timed(e2e_step, steps, dev, world), losses
 
 
+def run_device_loader_leg(arm, steps, dev):
+    """the series stays resident on the GPU and every batch is gathered on the device from the window
+    index (step.step_data.DeviceWindowLoader) - only the B sample indices cross PCIe, against 162 MB of overlapping host
+    windows per METR-LA batch in the `e2e` leg.  Same step, loss read back every step."""
+    from step.step_data import DeviceWindowLoader, ForecastingDataset
+    ds = ForecastingDataset(synthetic=True, num_nodes=arm.nodes, seq_len=arm.patches * 12, length=arm.B * 8, seed=5)
+    loader = DeviceWindowLoader(ds, dev, batch_size=arm.B, shuffle=True, drop_last=True, seed=1)
+    batches = iter(())
+    losses = []
+
+    def step(i):
+        nonlocal batches
+        try:
+            future, history, long_history = next(batches)
+        except StopIteration:
+            batches = iter(loader)
+            future, history, long_history = next(batches)
+        losses.append(arm.train_step(history, long_history, future).item())
+    for i in range(3):
+        step(i)
+    ms = timed(step, steps, dev, 1)
+    return {"value": arm.B * steps / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / steps,
+            "h2d_bytes_per_step": arm.B * 8, "d2h_bytes_per_step": 4,
+            "what": "series resident in HBM (%.0f MB), windows gathered on the device per batch, loss read back every step"
+                    % (ds.data.numel() * 4 / 1e6)}
+
+
 def rooflines(arm, args, pk):
     """Kernels / kernel groups timed alone with CUDA events on the launching stream (after warm-up); algorithmic
     bytes / FLOPs per DESIGN.md section 4 (SURVEY section 8(d) and Appx B figures x the units one launch processes)."""
@@ -603,8 +630,18 @@ def rooflines(arm, args, pk):
     return roofline, other
 
 
+def _claim_stdout():
+    """Libraries print to stdout (NCCL's version banner does, whatever NCCL_DEBUG_FILE says): keep the real stdout for the
+    ONE JSON line and point file descriptor 1 at stderr for everything else."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     args = parse()
+    out_stream = _claim_stdout()
     ds = args.workload
     nodes, cfg_batch, patches = WORKLOADS[ds]
     if args.batch is None:
@@ -629,7 +666,7 @@ def main():
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
                           "data": "synthetic", "config": {"workload": "STEP_%s N=%d P=%d 12->12, CPU sample batch %d" % (ds, nodes, patches, b)},
                           "cpu_baseline": info,
-                          "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), file=out_stream, flush=True)
         return
 
     if not torch.cuda.is_available():
@@ -664,7 +701,7 @@ def main():
     if args.only_resident:
         if rank == 0:
             sampler.stop()
-            print(json.dumps({"only_resident": True, "ms_per_step": ms_res / args.steps, "gpu_launches": launches}))
+            print(json.dumps({"only_resident": True, "ms_per_step": ms_res / args.steps, "gpu_launches": launches}), file=out_stream, flush=True)
         return
 
     ms_e2e, losses = run_e2e(arm, args.steps, dev, world)
@@ -672,6 +709,7 @@ def main():
 
     pk = peaks()
     roofline, roofline_other = rooflines(arm, args, pk) if rank == 0 else (None, None)
+    device_loader = run_device_loader_leg(arm, args.steps, dev) if world == 1 else None
 
     # ---- the other BASELINE configs, short runs (same timing rules; every rank takes part when they are multi-GPU) ----
     secondary = []
@@ -734,6 +772,8 @@ def main():
         "roofline": roofline, "roofline_other": roofline_other,
         "loss": losses[-1] if losses else None,
     }
+    if device_loader is not None:
+        out["e2e_device_loader"] = device_loader
     if secondary:
         out["secondary"] = secondary
     if not args.no_eager_baseline and world == 1:
@@ -743,7 +783,7 @@ def main():
         info["value"] = v
         info["unit"] = "samples/s"
         out["cpu_baseline"] = info
-    print(json.dumps(out))
+    print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -27,6 +27,8 @@ def parse_args():
     parser.add_argument("--steps", type=int, default=20)
     parser.add_argument("--synthetic", action="store_true", help="force synthetic data / random TSFormer weights (in --workdir)")
     parser.add_argument("--workdir", default=None, help="where synthetic data and checkpoints are written (default: a temp dir)")
+    parser.add_argument("--device-loader", action="store_true",
+                        help="stage 2: keep the series resident on the GPU and gather every batch there (DeviceWindowLoader)")
     parser.add_argument("--save", default=None, help="write an easytorch-format checkpoint here after the last step")
     parser.add_argument("--resume", default=None, help="resume model + optimiser state from this checkpoint")
     return parser.parse_args()
@@ -98,7 +100,11 @@ def main():
         ds = PretrainingDataset(mode="train", synthetic=True, num_nodes=nodes, seq_len=seq, length=batch * 4)
     else:
         ds = ForecastingDataset(mode="train", seq_len=seq, synthetic=True, num_nodes=nodes, length=batch * 4)
-    loader = torch.utils.data.DataLoader(ds, batch_size=batch, shuffle=True, drop_last=True, pin_memory=True)
+    if args.device_loader and not stage1:
+        from step.step_data import DeviceWindowLoader
+        loader = DeviceWindowLoader(ds, runner.device, batch_size=batch, shuffle=True, drop_last=True, seed=CFG.ENV.SEED)
+    else:
+        loader = torch.utils.data.DataLoader(ds, batch_size=batch, shuffle=True, drop_last=True, pin_memory=True)
     opt = FusedClipAdam([p for p in runner.model.parameters() if p.requires_grad],
                         max_norm=CFG.TRAIN.CLIP_GRAD_PARAM["max_norm"], **CFG.TRAIN.OPTIM.PARAM)
     epoch = 1

@@ -53,8 +53,7 @@ class DeviceWindowLoader:
         long_history = self.data[rows.clamp_(min=0)]
         if self.long_channels is not None:
             long_history = long_history.index_select(-1, self.long_channels)
-        if bool(short.any()):
-            long_history = long_history.masked_fill(short.view(-1, 1, 1, 1), 0.0)
+        long_history = long_history.masked_fill(short.view(-1, 1, 1, 1), 0.0)       # no host sync: applied unconditionally
         return future, history, long_history
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:

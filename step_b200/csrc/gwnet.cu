@@ -625,6 +625,312 @@ __global__ void __launch_bounds__(GW_THREADS, 2) gw_layer_fwd_kernel(GwFwdArgs a
 }
 
 // ---------------------------------------------------------------------------
+// ONE launch per Graph WaveNet layer (forward): the whole layer body of graphwavenet/model.py:169-213 for a
+// (sample, pair of time steps) column block - gated dilated conv, the three supports' two diffusion hops and the 1x1
+// mixing (Horner form, see the header), dropout, residual, BatchNorm partial sums - with the neighbour aggregation on
+// tcgen05 INSIDE the kernel: nothing but the layer input, the stash rows the backward needs and the layer output touch HBM.
+//   workers (8 warps, thread = node):  u = tanh(.) * sigmoid(.)  -> shared memory;  a_s = W_s2 u -> stash + bf16 hi/lo B image
+//   MMA lane:                          m_s = P_s^T a_s   (A = P_s^T images streamed by the TMA lane, K slices of 32 nodes)
+//   workers:                           q_s = W_s1 u + m_s (TMEM -> registers) -> stash + B image (overwrites a_s)
+//   MMA lane:                          H  += P_s^T q_s   (second accumulator, accumulated over the three supports)
+//   workers:                           h = H + W_0 u + b -> dropout -> + BN(residual) -> z, BN partial sums
+// Numerically identical operations to the split path (gw_layer_fwd_kernel<1,2,3> + 2 x tc_mix_kernel: same split-bf16 MMAs
+// in the same K order, same CUDA-core channel mixes); N <= 256 (two 128-row tiles).  grid = (ceil(T_out / 2), B), 1 CTA/SM.
+// ---------------------------------------------------------------------------
+constexpr int GWF_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 workers
+constexpr int GWF_NT = 2;             // time steps per CTA
+
+struct GwFusedArgs {
+  const float *zin; float *zout;
+  int Tin, Tout, dil, N, has_in_bn, collect_stats;
+  const float *in_scale, *in_shift;
+  step_gw_layer_params w;
+  float *f, *g, *q[3], *a[3];
+  const uint8_t *img[3];
+  long long img_bstride[3];
+  MixGeom geom;
+  double *sums;
+  uint32_t drop_thr; float drop_scale; uint64_t key;
+};
+
+static size_t gwf_smem_bytes(const MixGeom &g) {
+  return 2 * (size_t)(2 * 4 * 128 * g.MT * 16) + 2 * (size_t)GWF_NT * 4 * g.Kpad * 16 + (size_t)GWF_NT * g.N * GC * 4 + 7 * 1024 * 4 +
+         2 * 8 * 64 * 4 + 16 * 8 + 16;
+}
+
+__global__ void __launch_bounds__(GWF_THREADS, 1) gw_fused_fwd_kernel(GwFusedArgs a) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t gwf_smem[];
+  const MixGeom g = a.geom;
+  const int N = a.N, b = blockIdx.y, t0 = blockIdx.x * GWF_NT, nt = min(GWF_NT, a.Tout - t0);
+  const uint32_t rows = 128u * g.MT;
+  const uint32_t half_bytes = 4 * rows * 16, stage_bytes = 2 * half_bytes;
+  const uint32_t bimg = (uint32_t)GWF_NT * 4 * g.Kpad * 16;
+  uint8_t *sA = gwf_smem;
+  uint8_t *sBh = sA + 2 * stage_bytes, *sBl = sBh + bimg;
+  float *sU = reinterpret_cast<float *>(sBl + bimg);                 // [nt][N][32]
+  float *sW = sU + (size_t)GWF_NT * N * GC;                           // 7 x 1024
+  float *sRed = sW + 7 * 1024;                                        // [2][8 warps][64]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sRed + 2 * 8 * 64);
+  uint64_t *full = bars, *empty = bars + 2, *b_ready = bars + 4, *acc1_full = bars + 5, *hopb_done = bars + 6;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 7);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t col = (size_t)N * GC;
+  const int nslices = g.Kpad / 32;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(b_ready, 8); mbar_init(acc1_full, 1); mbar_init(hopb_done, 1);
+    fence_barrier_init();
+  }
+  // B-image rows of the padding nodes [N, Kpad) stay zero for the whole kernel
+  for (uint32_t i = threadIdx.x; i < 2 * bimg / 16; i += blockDim.x) reinterpret_cast<uint4 *>(sBh)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA lane: P_s^T image slices, 6 passes (3 supports x 2 hops) ------------------------------
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int s = 0; s < 3; ++s) {
+        const uint8_t *img_hi = a.img[s] + (size_t)b * a.img_bstride[s], *img_lo = img_hi + g.img_bytes;
+        for (int hop = 0; hop < 2; ++hop) {
+          for (int i = 0; i < nslices; ++i, ++n) {
+            const uint32_t st = n & 1;
+            mbar_wait(&empty[st], ((n >> 1) & 1) ^ 1);
+            mbar_expect_tx(&full[st], stage_bytes);
+            for (int c = 0; c < 4; ++c) {
+              const size_t off = ((size_t)(i * 4 + c) * g.Mpad) * 16;
+              tma_bulk_g2s(sA + st * stage_bytes + c * rows * 16, img_hi + off, rows * 16, &full[st]);
+              tma_bulk_g2s(sA + st * stage_bytes + half_bytes + c * rows * 16, img_lo + off, rows * 16, &full[st]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA lane ------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, nt * 32, 0, 1);
+      const uint32_t bh = smem_u32(sBh), bl = smem_u32(sBl);
+      const uint32_t b_sbo = (uint32_t)g.Kpad * 16, a_lbo = rows * 16;
+      uint32_t n = 0, ph = 0;
+      for (int s = 0; s < 3; ++s) {
+        for (int hop = 0; hop < 2; ++hop, ++ph) {
+          mbar_wait(b_ready, ph & 1);
+          tc_fence_after();
+          for (int i = 0; i < nslices; ++i, ++n) {
+            const uint32_t st = n & 1;
+            mbar_wait(&full[st], (n >> 1) & 1);
+            tc_fence_after();
+            const uint32_t ah = smem_u32(sA + st * stage_bytes), al = ah + half_bytes;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint32_t koff = (uint32_t)(i * 2 + kk) * 256;
+              const uint64_t dbh = umma_desc(bh + koff, 128, b_sbo), dbl = umma_desc(bl + koff, 128, b_sbo);
+              for (int m = 0; m < g.MT; ++m) {
+                const uint64_t dah = umma_desc(ah + kk * 2 * a_lbo + m * 2048, a_lbo, 128);
+                const uint64_t dal = umma_desc(al + kk * 2 * a_lbo + m * 2048, a_lbo, 128);
+                const uint32_t d = tmem + (hop ? 128 : 0) + m * 64;
+                const uint32_t acc = hop ? ((s | i | kk) != 0 ? 1u : 0u) : ((i | kk) != 0 ? 1u : 0u);
+                umma_bf16(d, dah, dbh, idesc, acc);
+                umma_bf16(d, dah, dbl, idesc, 1u);
+                umma_bf16(d, dal, dbh, idesc, 1u);
+              }
+            }
+            umma_commit(&empty[st]);
+          }
+          umma_commit(hop ? hopb_done : acc1_full);
+        }
+      }
+    }
+  } else {
+    // ------------------------------ workers: thread = node ------------------------------
+    const int q = warp & 3, m = (warp - 2) >> 2;
+    const int node = m * 128 + q * 32 + lane;
+    const bool valid = node < N;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int wt = threadIdx.x - 64;
+    auto worker_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    // store one [32]-channel row of (time step t) as four 16-byte hi/lo units of the B image
+    auto put_b_row = [&](int t, const float (&r)[GC]) {
+#pragma unroll
+      for (int cg = 0; cg < 4; ++cg) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float h = __bfloat162float(__float2bfloat16_rn(r[cg * 8 + j]));
+          hi[j] = h;
+          lo[j] = r[cg * 8 + j] - h;
+        }
+        const uint32_t u = (uint32_t)(t * 4 + cg) * g.Kpad + node;
+        reinterpret_cast<uint4 *>(sBh)[u] = pack8_bf16(hi);
+        reinterpret_cast<uint4 *>(sBl)[u] = pack8_bf16(lo);
+      }
+    };
+
+    // ---- P1: gated dilated conv (filter / gate taps staged in sW) ----
+    for (int i = wt; i < 1024; i += 256) {
+      sW[i] = a.w.filter_w[2 * i]; sW[1024 + i] = a.w.filter_w[2 * i + 1];
+      sW[2048 + i] = a.w.gate_w[2 * i]; sW[3072 + i] = a.w.gate_w[2 * i + 1];
+    }
+    worker_sync();
+    if (valid) {
+#pragma unroll
+      for (int t = 0; t < GWF_NT; ++t) {
+        if (t >= nt) continue;
+        const float *z0 = a.zin + ((size_t)b * a.Tin + t0 + t) * col + (size_t)node * GC;
+        const float *z1 = a.zin + ((size_t)b * a.Tin + t0 + t + a.dil) * col + (size_t)node * GC;
+        const size_t ro = ((size_t)b * a.Tout + t0 + t) * col + (size_t)node * GC;
+        float r0[GC], r1[GC];
+        load_row(z0, r0);
+        load_row(z1, r1);
+        if (a.has_in_bn) {
+#pragma unroll
+          for (int c = 0; c < GC; ++c) {
+            const float sc = a.in_scale[c], sh = a.in_shift[c];
+            r0[c] = fmaf(r0[c], sc, sh);
+            r1[c] = fmaf(r1[c], sc, sh);
+          }
+        }
+        float *fo = a.f + ro, *go = a.g + ro, *uo = sU + ((size_t)t * N + node) * GC;
+#pragma unroll 1
+        for (int cg = 0; cg < GC; cg += 4) {
+          float fv[4], gv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int co = cg + j;
+            const float4 *wf0 = reinterpret_cast<const float4 *>(sW + co * GC);
+            const float4 *wf1 = reinterpret_cast<const float4 *>(sW + 1024 + co * GC);
+            const float4 *wg0 = reinterpret_cast<const float4 *>(sW + 2048 + co * GC);
+            const float4 *wg1 = reinterpret_cast<const float4 *>(sW + 3072 + co * GC);
+            float f0 = a.w.filter_b[co], f1 = 0.f, f2 = 0.f, f3 = 0.f, g0 = a.w.gate_b[co], g1 = 0.f, g2 = 0.f, g3 = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+              const float4 A0 = wf0[c4], A1 = wf1[c4], G0 = wg0[c4], G1 = wg1[c4];
+              ffma2(f0, f1, A0.x, A0.y, r0[4 * c4], r0[4 * c4 + 1]); ffma2(f2, f3, A0.z, A0.w, r0[4 * c4 + 2], r0[4 * c4 + 3]);
+              ffma2(f0, f1, A1.x, A1.y, r1[4 * c4], r1[4 * c4 + 1]); ffma2(f2, f3, A1.z, A1.w, r1[4 * c4 + 2], r1[4 * c4 + 3]);
+              ffma2(g0, g1, G0.x, G0.y, r0[4 * c4], r0[4 * c4 + 1]); ffma2(g2, g3, G0.z, G0.w, r0[4 * c4 + 2], r0[4 * c4 + 3]);
+              ffma2(g0, g1, G1.x, G1.y, r1[4 * c4], r1[4 * c4 + 1]); ffma2(g2, g3, G1.z, G1.w, r1[4 * c4 + 2], r1[4 * c4 + 3]);
+            }
+            const float af = (f0 + f1) + (f2 + f3), ag = (g0 + g1) + (g2 + g3);
+            fv[j] = tanhf(af);
+            gv[j] = 1.0f / (1.0f + expf(-ag));
+          }
+          *reinterpret_cast<float4 *>(fo + cg) = make_float4(fv[0], fv[1], fv[2], fv[3]);
+          *reinterpret_cast<float4 *>(go + cg) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+          *reinterpret_cast<float4 *>(uo + cg) = make_float4(fv[0] * gv[0], fv[1] * gv[1], fv[2] * gv[2], fv[3] * gv[3]);
+        }
+      }
+    }
+    worker_sync();
+    // the 7 transposed [32x32] blocks of the gcn 1x1 conv: sW[k][ci][co] = mlp_w[co][k*32 + ci]
+    for (int i = wt; i < 7 * 1024; i += 256) {
+      const int k = i >> 10, co = (i >> 5) & 31, ci = i & 31;
+      sW[k * 1024 + ci * 32 + co] = a.w.mlp_w[(size_t)co * 224 + k * 32 + ci];
+    }
+    worker_sync();
+
+    // ---- P2: per support: a_s -> hop A -> q_s -> hop B ----
+    for (int s = 0; s < 3; ++s) {
+      float arow[GWF_NT][GC];
+      if (valid) {
+#pragma unroll
+        for (int t = 0; t < GWF_NT; ++t) {
+          if (t >= nt) continue;
+          float u[GC];
+          load_row(sU + ((size_t)t * N + node) * GC, u);
+#pragma unroll
+          for (int c = 0; c < GC; ++c) arow[t][c] = 0.f;
+          matvec_t_reg(sW + (2 + 2 * s) * 1024, u, arow[t]);
+          store_row(a.a[s] + ((size_t)b * a.Tout + t0 + t) * col + (size_t)node * GC, arow[t]);
+        }
+      }
+      if (s > 0) mbar_wait(hopb_done, (s - 1) & 1);          // hop B of the previous support has read the B image
+      if (valid) {
+#pragma unroll
+        for (int t = 0; t < GWF_NT; ++t)
+          if (t < nt) put_b_row(t, arow[t]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_ready);
+      // q_s = W_s1 u + m_s
+      mbar_wait(acc1_full, s & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < GWF_NT; ++t) {
+        if (t >= nt) continue;
+        float qrow[GC];
+        if (m < g.MT) tmem_ld32(tmem + lane_base + m * 64 + t * 32, qrow);
+        if (valid) {
+          float u[GC];
+          load_row(sU + ((size_t)t * N + node) * GC, u);
+          matvec_t_reg(sW + (1 + 2 * s) * 1024, u, qrow);
+          store_row(a.q[s] + ((size_t)b * a.Tout + t0 + t) * col + (size_t)node * GC, qrow);
+          put_b_row(t, qrow);                                 // hop A has completed (acc1_full): the image is free
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_ready);
+    }
+
+    // ---- P3: h = H + W_0 u + b; dropout; residual; z; BatchNorm partial sums ----
+    mbar_wait(hopb_done, 0);                                  // third completion of the barrier (phases 0, 1, 0)
+    tc_fence_after();
+    float csum[GC], csq[GC];
+#pragma unroll
+    for (int c = 0; c < GC; ++c) { csum[c] = 0.f; csq[c] = 0.f; }
+#pragma unroll
+    for (int t = 0; t < GWF_NT; ++t) {
+      if (t >= nt) continue;
+      float h[GC];
+      if (m < g.MT) tmem_ld32(tmem + lane_base + 128 + m * 64 + t * 32, h);
+      if (valid) {
+        const size_t ro = ((size_t)b * a.Tout + t0 + t) * col + (size_t)node * GC;
+        float u[GC], r[GC];
+        load_row(sU + ((size_t)t * N + node) * GC, u);
+        load_row(a.zin + ((size_t)b * a.Tin + t0 + t + a.dil) * col + (size_t)node * GC, r);
+#pragma unroll
+        for (int c = 0; c < GC; ++c) h[c] += a.w.mlp_b[c];
+        matvec_t_reg(sW, u, h);
+        if (a.drop_thr) dropout_row(h, (uint64_t)ro, a.drop_thr, a.drop_scale, a.key);
+#pragma unroll
+        for (int c = 0; c < GC; ++c) {
+          const float rv = a.has_in_bn ? fmaf(r[c], a.in_scale[c], a.in_shift[c]) : r[c];
+          h[c] += rv;
+          csum[c] += h[c];
+          csq[c] = fmaf(h[c], h[c], csq[c]);
+        }
+        store_row(a.zout + ro, h);
+      }
+    }
+    tc_fence_before();
+    if (a.collect_stats) {
+      const float s1 = warp_colsum32(csum), s2 = warp_colsum32(csq);     // lane c: channel c over the warp's 32 nodes
+      sRed[(warp - 2) * 64 + lane] = s1;
+      sRed[(warp - 2) * 64 + 32 + lane] = s2;
+      worker_sync();
+      if (wt < 64) {
+        float tsum = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) tsum += sRed[w8 * 64 + wt];
+        atomicAdd(a.sums + wt, (double)tsum);                            // [0,32): sums, [32,64): sums of squares
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// ---------------------------------------------------------------------------
 // skip convolutions of ALL layers, hoisted out of the layer kernels (only the last time step of each layer's
 // u = f*g reaches the output because skip[..., -T:] truncation ends at T = 1; model.py:189-197):
 //   skip[b,n,:] = sum_l ( Wk_l u_l[b, Tout_l - 1, n, :] + bk_l )
@@ -1155,6 +1461,14 @@ static bool gw_use_tc(int N) {
   return mix_smem_bytes(mix_geom(N)) <= 227 * 1024;
 }
 
+// One fused launch per layer (gw_fused_fwd_kernel) when the graph fits two 128-row tiles and the shared-memory plan;
+// STEP_B200_GW_FUSED=0 selects the five-launch split path (A/B comparison, tests)
+static bool gw_use_fused(const MixGeom &g) {
+  const char *e = getenv("STEP_B200_GW_FUSED");
+  if (e != nullptr && strcmp(e, "0") == 0) return false;
+  return g.MT <= 2 && gwf_smem_bytes(g) <= 227 * 1024;
+}
+
 static size_t fwd_smem_bytes(int N) { return ((size_t)N * GC + 7 * 1024) * sizeof(float); }
 static size_t bwd_smem_bytes(int N) { return ((size_t)N * GC + 7 * 1024 + 7 * 64 * 32) * sizeof(float); }
 static size_t bwd_in_smem_bytes(int N) { return ((size_t)N * GC + 4 * 1024 + 3 * 64 * 32 + 128) * sizeof(float); }
@@ -1228,6 +1542,21 @@ extern "C" int step_gwnet_stack_fwd(const float *x0, const float *P1, const floa
         a.Min[s] = stash + p.off_M3[s];
         a.Oin[s] = stash + p.off_O3[s];
       }
+      if (gw_use_fused(geom)) {
+        // one launch per layer: neighbour aggregation (tcgen05) and gated conv / channel mixing fused in shared memory
+        GwFusedArgs fa{};
+        fa.zin = a.zin; fa.zout = a.zout; fa.Tin = a.Tin; fa.Tout = a.Tout; fa.dil = a.dil; fa.N = N;
+        fa.has_in_bn = a.has_in_bn; fa.collect_stats = a.collect_stats; fa.in_scale = a.in_scale; fa.in_shift = a.in_shift;
+        fa.w = a.w; fa.f = a.f; fa.g = a.g; fa.geom = geom; fa.sums = a.sums;
+        fa.drop_thr = a.drop_thr; fa.drop_scale = a.drop_scale; fa.key = a.key;
+        for (int s = 0; s < 3; ++s) {
+          fa.q[s] = a.q[s]; fa.a[s] = stash + p.off_a[i][s];
+          fa.img[s] = m.img[s]; fa.img_bstride[s] = m.img_bstride[s];
+        }
+        if ((rc = allow_smem(gw_fused_fwd_kernel, 227 * 1024))) return rc;
+        gw_fused_fwd_kernel<<<dim3((a.Tout + GWF_NT - 1) / GWF_NT, B), GWF_THREADS, gwf_smem_bytes(geom), st>>>(fa);
+        STEP_LAUNCH_CHECK("gw_fused_fwd_kernel");
+      } else {
       gw_layer_fwd_kernel<1><<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
       STEP_LAUNCH_CHECK("gw_layer_fwd_kernel[conv]");
       for (int s = 0; s < 3; ++s) { m.Y[s] = stash + p.off_a[i][s]; m.out[s] = stash + p.off_M3[s]; }
@@ -1238,6 +1567,7 @@ extern "C" int step_gwnet_stack_fwd(const float *x0, const float *P1, const floa
       if ((rc = tc_mix_launch(m, st))) return rc;
       gw_layer_fwd_kernel<3><<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);
       STEP_LAUNCH_CHECK("gw_layer_fwd_kernel[out]");
+      }
     }
     if (a.has_gcn && training) {
       bn_finalize_kernel<<<1, 32, 0, st>>>(a.sums, (double)B * a.Tout * N, Lp[i].bn_w, Lp[i].bn_b, bn_stats + (size_t)i * 128);
