@@ -503,10 +503,11 @@ def rooflines(arm, args, pk):
         v = torch.empty(L.step_tc_attn_image_bytes(S_seq, P, 1), device=dev, dtype=torch.uint8)
         o = torch.empty(((tokens + 127) // 128) * 96 * 256, device=dev, dtype=torch.uint8)
         st = ops._enter(x_img)
+        bound = torch.empty(L.step_tc_attn_image_bytes(S_seq, P, 2) // 4, device=dev, dtype=torch.float32)
         ops.check(L.step_tc_qkv(x_img.data_ptr(), w_in.data_ptr(), b_in.data_ptr(), S_seq, P, q.data_ptr(), k.data_ptr(),
-                                v.data_ptr(), st), "step_tc_qkv")
-        att_ms = time_ms(lambda: ops.check(L.step_tc_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), S_seq,
-                                                              P, drop, 1, st), "step_tc_attention"), dev)
+                                v.data_ptr(), bound.data_ptr(), st), "step_tc_qkv")
+        att_ms = time_ms(lambda: ops.check(L.step_tc_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
+                                                              bound.data_ptr(), S_seq, P, drop, 1, st), "step_tc_attention"), dev)
         att_flops = 4.0 * S_seq * 4 * P * P * 24            # useful (unpadded) QK^T + PV flops of one layer
         att_tflops = att_flops / (att_ms * 1e-3) / 1e12
         w1 = ops.tc_pack_weight(torch.randn(384, 96, device=dev) * 0.1)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define STEP_B200_ABI_VERSION 2
+#define STEP_B200_ABI_VERSION 3
 
 #define STEP_OK 0
 #define STEP_EINVAL (-1)
@@ -181,16 +181,22 @@ int step_tc_embed_fwd(const float *series, long long sB, long long sT, long long
 int step_tc_linear_drop(const void *a_img, const void *w_img, const float *bias, long long T, int K, int Nout, int mode,
                         const void *res_img, const float *ln_w, const float *ln_b, void *out_img, float *out_f32,
                         float drop_p, unsigned long long seed, void *stream);
-/* Bytes of the per-(sequence, head) attention operand images: which = 0 -> Q, 1 -> K (== V). */
+/* Bytes of the per-(sequence, head) attention operand images: which = 0 -> Q, 1 -> K (== V), 2 -> the row-maximum bound
+ * workspace (S*4 floats max_j |k_j| followed by S*4*P floats |q_i|). */
 size_t step_tc_attn_image_bytes(int S, int P, int which);
 /* QKV projection of an X image [S*P, 96] straight into the attention operand images (Q pre-scaled by
- * log2(e)/sqrt(24)). */
+ * log2(e)/sqrt(24); the last row tile of odd heads is placed at tile rows 64.. when it holds <= 64 queries).
+ * `bound` (may be NULL): workspace of step_tc_attn_image_bytes(S, P, 2) bytes that receives the operand norms. */
 int step_tc_qkv(const void *x_img, const void *w_img, const float *bias, int S, int P, void *q_img, void *k_img, void *v_img,
-                void *stream);
-/* softmax(Q K^T) V per (sequence, head) on tcgen05 -> O tile image [S*P, 96].  P <= 352
- * (P > 176 runs the key-split variant: two 176-key blocks per row tile merged in shared memory). */
-int step_tc_attention(const void *q_img, const void *k_img, const void *v_img, void *o_img, int S, int P, float drop_p,
-                      unsigned long long seed, void *stream);
+                float *bound, void *stream);
+/* softmax(Q K^T) V per (sequence, head) on tcgen05 -> O tile image [S*P, 96]
+ * (transformer_layers.py:13-20 -> nn.MultiheadAttention inside nn.TransformerEncoderLayer).  P <= 352
+ * (P > 176 runs the key-split variant: two 176-key blocks per row tile merged in shared memory).
+ * `bound` (may be NULL): the workspace step_tc_qkv filled; rows whose Cauchy-Schwarz bound |q_i| max_j |k_j| is <= 40
+ * (log2 domain) are exponentiated in one pass against that bound, all others (and every row when NULL) take the exact
+ * two-pass row maximum.  Both are the same softmax up to bf16 rounding of the probabilities. */
+int step_tc_attention(const void *q_img, const void *k_img, const void *v_img, void *o_img, const float *bound, int S, int P,
+                      float drop_p, unsigned long long seed, void *stream);
 size_t step_ts_encoder_bf16_workspace_bytes(int B, int N, int P);
 /* Whole encoder in bf16: series -> hidden [B,N,P,96] fp32 (same contract as step_ts_encoder_fwd). */
 int step_ts_encoder_fwd_bf16(const float *series, long long sB, long long sT, long long sN, int B, int N, int P,

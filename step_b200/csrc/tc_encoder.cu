@@ -47,6 +47,63 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// ---- attention-probability dropout: two keep decisions per 32-bit random word -------------------------------------
+// Each half of the word is compared AS A bf16 NUMBER with a threshold (one HSET2.BF16 for two elements, result 0xFFFF /
+// 0x0000 per half, applied to the packed bf16 probabilities with one AND).  As numbers the 65536 patterns order as
+// -inf = 0xFF80 < ... < 0x8001 < -0 = +0 < 0x0001 < ... < +inf, and the 254 NaN patterns fail every comparison, so
+// "dropped" = NaNs + the (D - 254) most negative patterns for D = p * 65536 dropped patterns out of 65536: the keep
+// probability is exactly 1 - D / 65536 for p >= 254 / 65536 (smaller p are served as 254 / 65536).
+__host__ __device__ inline uint32_t drop_thr_bf16x2(uint32_t thr16) {
+  const uint32_t need = thr16 > 254u ? thr16 - 254u : 0u;
+  uint32_t t;
+  if (need <= 32640u) t = 0xFF80u - need;
+  else { t = need - 32641u; if (t > 0x7F80u) t = 0x7F80u; }
+  return t | (t << 16);
+}
+__device__ __forceinline__ uint32_t keep_mask_bf16x2(uint32_t r, uint32_t thr2) {
+  uint32_t m;
+  asm("set.ge.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(r), "r"(thr2));
+  return m;
+}
+// Placement of a (head, row tile) in the 128 TMEM lanes: a last tile of <= 64 queries sits at lanes 64.. for odd heads, so
+// that the partial tiles of consecutive heads are exponentiated by warps of different SM sub-partitions.
+__host__ __device__ __forceinline__ int q_tail_offset(int P, int rt, int h) {
+  return ((P - rt * 128) <= 64 && (h & 1)) ? 64 : 0;
+}
+// One block of NC score columns of a row: p = 2^(s - m) (0 for columns >= `valid`), row sums, dropout, bf16 K-major image.
+// `dst` points at this row's 16-byte slot of the block's first 8-column chunk; chunks at or beyond `chunks` are not stored.
+template <int NC, bool DROP, bool PRED>
+__device__ __forceinline__ void softmax_cols(float (&t)[NC], float negm, int valid, int chunks, float &l0, float &l1, float &l2,
+                                             float &l3, uint32_t st, uint32_t cadd, uint32_t thr2, uint4 *dst) {
+#pragma unroll
+  for (int c = 0; c < NC; c += 4) {
+    tc::fadd2(t[c], t[c + 1], negm, negm);
+    tc::fadd2(t[c + 2], t[c + 3], negm, negm);
+    t[c] = fast_exp2(t[c]); t[c + 1] = fast_exp2(t[c + 1]); t[c + 2] = fast_exp2(t[c + 2]); t[c + 3] = fast_exp2(t[c + 3]);
+    if (PRED) {
+      if (c >= valid) t[c] = 0.f;
+      if (c + 1 >= valid) t[c + 1] = 0.f;
+      if (c + 2 >= valid) t[c + 2] = 0.f;
+      if (c + 3 >= valid) t[c + 3] = 0.f;
+    }
+    tc::fadd2(l0, l1, t[c], t[c + 1]);
+    tc::fadd2(l2, l3, t[c + 2], t[c + 3]);
+  }
+#pragma unroll
+  for (int cc = 0; cc < NC / 8; ++cc) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      w[j] = tc::pack_bf16(t[cc * 8 + 2 * j], t[cc * 8 + 2 * j + 1]);
+      if (DROP) {
+        st = st * 2891336453u + cadd;             // full-period LCG mod 2^32 (odd addend, one IMAD); both halves decide
+        w[j] &= keep_mask_bf16x2(st, thr2);
+      }
+    }
+    if (!PRED || cc < chunks) dst[(size_t)cc * 128] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 // ===========================================================================
 // weight packing: fp32 W [Nout][K] -> bf16 image [K/8][Nout][8]
 // ===========================================================================
@@ -181,6 +238,8 @@ struct TcLinearArgs {
   uint8_t *seq_img;        // TCM_RESLN: per-sample K-major image [B][P*12 chunks][seq_rows][8] of the output (Gram operand)
   int seq_nodes, seq_rows; // nodes per sample, padded rows per chunk
   uint8_t *q_img, *k_img, *v_img;  // TCM_QKV
+  float *bound;            // TCM_QKV: [nseq*4] max_j |k_j| (zeroed by the host), then [nseq*4][P] |q_i|; may be null
+  long long nseq;
   int P, Pk, RT;
   float qscale;
   uint32_t thr16; float dscale; uint64_t key;
@@ -383,17 +442,21 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_linear_kernel(TcLinearArgs 
             const long long s = token / a.P;
             const int p = (int)(token - s * a.P);
             if (nb == 0) {
-              const int rt = p >> 7, r = p & 127;
+              const int rt = p >> 7;
 #pragma unroll
               for (int h = 0; h < 4; ++h) {
+                const int r = (p & 127) + q_tail_offset(a.P, rt, h);
                 uint4 *o = reinterpret_cast<uint4 *>(a.q_img) + (((size_t)s * 4 + h) * a.RT + rt) * 3 * 128 + r;
+                float n2 = 0.f;
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc) {
                   float x[8];
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) x[j] = v[h * HD + cc * 8 + j] * a.qscale;
+                  for (int j = 0; j < 8; ++j) { x[j] = v[h * HD + cc * 8 + j] * a.qscale; n2 = fmaf(x[j], x[j], n2); }
                   o[cc * 128] = pack8_bf16(x);
                 }
+                // |q_i| for the attention kernel's row-maximum bound (the 1 % margin there covers the bf16 rounding)
+                if (a.bound != nullptr) a.bound[(size_t)a.nseq * 4 + ((size_t)s * 4 + h) * a.P + p] = sqrtf(n2);
               }
             } else {
               uint8_t *base = (nb == 1) ? a.k_img : a.v_img;
@@ -402,6 +465,27 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_linear_kernel(TcLinearArgs 
                 uint4 *o = reinterpret_cast<uint4 *>(base) + ((size_t)s * 4 + h) * 3 * a.Pk + p;
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc) o[(size_t)cc * a.Pk] = pack8_bf16(&v[h * HD + cc * 8]);
+              }
+            }
+          }
+          if (nb == 1 && a.bound != nullptr) {
+            // max_j |k_j| per (sequence, head): non-negative floats order like their bit patterns -> integer atomicMax.
+            // A warp holds 32 consecutive tokens; when they share one sequence a shuffle reduction leaves 4 atomics.
+            const long long s = valid ? token / a.P : -1;
+            const long long s0 = __shfl_sync(0xffffffffu, s, 0);
+            const bool same = __all_sync(0xffffffffu, s == s0);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              float n2 = 0.f;
+#pragma unroll
+              for (int c = 0; c < HD; ++c) n2 = fmaf(v[h * HD + c], v[h * HD + c], n2);
+              float kn = valid ? sqrtf(n2) : 0.f;
+              uint32_t *dst = reinterpret_cast<uint32_t *>(a.bound);
+              if (same) {
+                kn = warp_max(kn);
+                if (lane == 0 && s0 >= 0) atomicMax(dst + s0 * 4 + h, __float_as_uint(kn));
+              } else if (valid) {
+                atomicMax(dst + s * 4 + h, __float_as_uint(kn));
               }
             }
           }
@@ -426,6 +510,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_linear_kernel(TcLinearArgs 
 struct TcAttnArgs {
   const uint8_t *q_img, *k_img, *v_img;
   uint8_t *o_img;
+  const float *bound;      // [S*4] max_j |k_j| (as uint bits) then [S*4][P] |q_i| of the bf16 operands; null -> exact row maxima
   int S, P, Pk, RT;
   uint32_t thr16; float dscale; uint64_t key;
 };
@@ -444,6 +529,7 @@ constexpr int TCA_KSPLIT = 176, TCA_KVBUF_SPLIT = 2, TCA_XROW = 27;   // key-spl
 // style through a small shared-memory exchange (O = (O0 2^(m0-m) + O1 2^(m1-m)) / (l0 2^(m0-m) + l1 2^(m1-m))).
 template <int PF, bool DROP, bool SPLIT>
 __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
+  static_assert(PF == 0 || PF == 168 || PF == 336, "compile-time sequence lengths: 168 (alternating groups) or 336 (key split)");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int P = PF > 0 ? PF : a.P, Pk = PF > 0 ? (PF + 15) / 16 * 16 : a.Pk, RT = PF > 0 ? (PF + 127) / 128 : a.RT;
   constexpr int KVBUFS = SPLIT ? TCA_KVBUF_SPLIT : TCA_KVBUF;
@@ -583,12 +669,31 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
     // columns this group exponentiates: all Pk (alternating iterations) or its key block (SPLIT, every iteration)
     const int Pl = SPLIT ? (g == 0 ? TCA_KSPLIT : P - TCA_KSPLIT) : P;
     const int Pkl = SPLIT ? (g == 0 ? TCA_KSPLIT : Pk - TCA_KSPLIT) : Pk;
+    const uint32_t thr2 = DROP ? drop_thr_bf16x2(a.thr16) : 0u;
+    const uint32_t salt_lo = (uint32_t)a.key ^ ((uint32_t)(a.key >> 32) * 0x9E3779B9u);
+    const uint32_t cadd = (salt_lo * 0x85EBCA6Bu) | 1u;
+    const uint32_t *kmax = reinterpret_cast<const uint32_t *>(a.bound);
+    const float *qnorm = a.bound != nullptr ? a.bound + (size_t)a.S * 4 : nullptr;
     for (int i = SPLIT ? 0 : g; i < NIT; i += SPLIT ? 1 : 2) {
       const int u = SPLIT ? i : i >> 1;
       const int seq = blockIdx.x + (i / per_seq) * gridDim.x, w = i % per_seq, h = w / RT, rt = w % RT;
       const int rows_valid = min(128, P - rt * 128);
-      const bool warp_active = q * 32 < rows_valid;
-      const bool row_valid = row < rows_valid;
+      const int roff = q_tail_offset(P, rt, h);
+      const int lrow = row - roff;                       // query index inside the row tile
+      const bool warp_active = q * 32 + 32 > roff && q * 32 < roff + rows_valid;
+      const bool row_valid = lrow >= 0 && lrow < rows_valid;
+      // Upper bound of the row maximum without reading the scores (Cauchy-Schwarz on the bf16 operands, written by the
+      // QKV epilogue): s_ij <= |q_i| max_j |k_j|.  Softmax is shift invariant, so any m >= max works as long as
+      // 2^(s - m) stays representable: with m_b <= 40 every s - m_b lies in [-80, 0].  Rows with a larger bound (never
+      // seen with LayerNorm'd inputs, but weights are data) take the exact two-pass route, warp-uniformly.
+      float mb = 0.f;
+      bool bounded = false;
+      if (qnorm != nullptr && warp_active) {
+        const float qn = row_valid ? __ldg(qnorm + ((size_t)seq * 4 + h) * P + rt * 128 + lrow) : 0.f;
+        const float km = __uint_as_float(__ldg(kmax + (size_t)seq * 4 + h));
+        mb = fmaf(qn * km, 1.01f, 1e-3f);
+        bounded = !__any_sync(0xffffffffu, !(mb <= 40.f));
+      }
       mbar_wait(&s_full[g], u & 1);
       tc_fence_after();
       // V rows of the padded keys must be finite zeros (P is 0 there, but 0 * NaN = NaN)
@@ -601,102 +706,96 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       }
       float m = -INFINITY, l = 0.f;
       if (warp_active) {
-        // Full 32-column blocks run unpredicated with four independent max / sum chains; only the tail block
-        // (columns [c_tail, P), then zero fill up to Pk) carries per-element predicates.
+        // Full 32-column blocks run unpredicated; only the tail block (columns [c_tail, P), then zero fill up to Pk)
+        // carries per-element predicates.
         const int c_tail = (Pl / 32) * 32;
         const bool tail32 = c_tail + 32 <= Pkl;          // else the tail is one 16-column load (Pk is a multiple of 16)
-        // ---- pass 1: row maximum ----
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-        if (PF == 168 && !SPLIT) {
-          // reduction-only pass: 64-column loads and a combined 32 + 16 tail -> 3 TMEM round trips instead of 6
-#pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 64) {
-            float t[64];
-            tmem_ld64(TM_S + lane_base + c0, t);
+        if (bounded) {
+          m = mb;
+        } else {
+          // ---- pass 1 (exact route only): row maximum ----
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+          for (int c0 = 0; c0 < c_tail; c0 += 32) {
+            float t[32];
+            tmem_ld32(TM_S + lane_base + c0, t);
 #pragma unroll
-            for (int c = 0; c < 64; c += 4) {
+            for (int c = 0; c < 32; c += 4) {
               m0 = fmaxf(m0, t[c]); m1 = fmaxf(m1, t[c + 1]); m2 = fmaxf(m2, t[c + 2]); m3 = fmaxf(m3, t[c + 3]);
             }
           }
-          float t[32], tq[16];
-          tmem_ld32_16(TM_S + lane_base + 128, TM_S + lane_base + 160, t, tq);
+          if (c_tail < Pl) {
+            float t[32];
+            if (tail32) {
+              tmem_ld32(TM_S + lane_base + c_tail, t);
+            } else {
+              float t16[16];
+              tmem_ld16(TM_S + lane_base + c_tail, t16);
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            m0 = fmaxf(m0, t[c]); m1 = fmaxf(m1, t[c + 1]); m2 = fmaxf(m2, t[c + 2]); m3 = fmaxf(m3, t[c + 3]);
-          }
+              for (int c = 0; c < 16; ++c) t[c] = t16[c];
 #pragma unroll
-          for (int c = 0; c < 8; c += 4) {
-            m0 = fmaxf(m0, tq[c]); m1 = fmaxf(m1, tq[c + 1]); m2 = fmaxf(m2, tq[c + 2]); m3 = fmaxf(m3, tq[c + 3]);
-          }
-        } else {
-        for (int c0 = 0; c0 < c_tail; c0 += 32) {
-          float t[32];
-          tmem_ld32(TM_S + lane_base + c0, t);
+              for (int c = 16; c < 32; ++c) t[c] = -INFINITY;
+            }
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            m0 = fmaxf(m0, t[c]); m1 = fmaxf(m1, t[c + 1]); m2 = fmaxf(m2, t[c + 2]); m3 = fmaxf(m3, t[c + 3]);
+            for (int c = 0; c < 32; ++c) if (c_tail + c < Pl) m0 = fmaxf(m0, t[c]);
           }
+          m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         }
-        if (c_tail < Pl) {
-          float t[32];
-          if (tail32) {
-            tmem_ld32(TM_S + lane_base + c_tail, t);
-          } else {
-            float t16[16];
-            tmem_ld16(TM_S + lane_base + c_tail, t16);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) t[c] = t16[c];
-#pragma unroll
-            for (int c = 16; c < 32; ++c) t[c] = -INFINITY;
-          }
-#pragma unroll
-          for (int c = 0; c < 32; ++c) if (c_tail + c < Pl) m0 = fmaxf(m0, t[c]);
-        }
-        }
-        m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        // ---- pass 2: p = 2^(s - m), row sum, (dropout), bf16 image ----
-        const uint64_t drop_base = (((uint64_t)seq * 4 + h) * P + (rt * 128 + row)) * (uint64_t)(Pk / 8) +
-                                   (SPLIT ? g * (TCA_KSPLIT / 8) : 0);
+        // ---- p = 2^(s - m), row sum, (dropout), bf16 image: one pass over the scores ----
+        const float negm = -m;
+        const uint64_t rowid = ((uint64_t)seq * 4 + h) * P + (uint64_t)(rt * 128 + lrow);
+        const uint32_t salt = salt_lo ^ ((uint32_t)(rowid >> 28) * 0x85EBCA6Bu);
+        const uint32_t ctr = (uint32_t)rowid * 16u + (SPLIT ? (uint32_t)g * 6u : 0u);   // + 32-column block index
         uint4 *prow = reinterpret_cast<uint4 *>(myP) + row;
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-        for (int c0 = 0; c0 < c_tail; c0 += 32) {
-          float t[32];
-          tmem_ld32(TM_S + lane_base + c0, t);
+        if (PF > 0) {
+          // compile-time sequence length (168 / 336): five full blocks per group, the load of block k+1 in flight
+          // while block k is exponentiated (two register buffers)
+          constexpr int NBLK = 5;
+          float ta[32], tb[32];
+          tmem_ld32_issue(TM_S + lane_base, ta);
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            t[c] = fast_exp2(t[c] - m); t[c + 1] = fast_exp2(t[c + 1] - m);
-            t[c + 2] = fast_exp2(t[c + 2] - m); t[c + 3] = fast_exp2(t[c + 3] - m);
-            l0 += t[c]; l1 += t[c + 1]; l2 += t[c + 2]; l3 += t[c + 3];
+          for (int k = 0; k < NBLK; ++k) {
+            if ((k & 1) == 0) {
+              tmem_wait_ld32(ta);
+              if (k + 1 < NBLK) tmem_ld32_issue(TM_S + lane_base + (k + 1) * 32, tb);
+              softmax_cols<32, DROP, false>(ta, negm, 32, 4, l0, l1, l2, l3, DROP ? hash32((ctr + k) ^ salt) : 0u, cadd, thr2,
+                                            prow + (size_t)(k * 4) * 128);
+            } else {
+              tmem_wait_ld32(tb);
+              if (k + 1 < NBLK) tmem_ld32_issue(TM_S + lane_base + (k + 1) * 32, ta);
+              softmax_cols<32, DROP, false>(tb, negm, 32, 4, l0, l1, l2, l3, DROP ? hash32((ctr + k) ^ salt) : 0u, cadd, thr2,
+                                            prow + (size_t)(k * 4) * 128);
+            }
           }
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            if (DROP) drop8(&t[cc * 8], drop_base + (c0 >> 3) + cc, a.thr16, 1.0f, a.key);
-            prow[(size_t)((c0 >> 3) + cc) * 128] = pack8_bf16(&t[cc * 8]);
-          }
-        }
-        if (c_tail < Pkl) {
-          float t[32];
-          if (tail32) {
-            tmem_ld32(TM_S + lane_base + c_tail, t);
-          } else {
+          if (NBLK * 32 < Pkl) {                          // 16-column tail: PF = 168 (8 valid), group 0 of PF = 336 (16 valid)
             float t16[16];
-            tmem_ld16(TM_S + lane_base + c_tail, t16);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) t[c] = t16[c];
-#pragma unroll
-            for (int c = 16; c < 32; ++c) t[c] = 0.f;
+            tmem_ld16_issue(TM_S + lane_base + NBLK * 32, t16);
+            tmem_wait_ld16(t16);
+            softmax_cols<16, DROP, true>(t16, negm, Pl - NBLK * 32, (Pkl - NBLK * 32) / 8, l0, l1, l2, l3,
+                                         DROP ? hash32((ctr + NBLK) ^ salt) : 0u, cadd, thr2, prow + (size_t)(NBLK * 4) * 128);
           }
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float pv = (c_tail + c < Pl) ? fast_exp2(t[c] - m) : 0.f;
-            l0 += pv;
-            t[c] = pv;
+        } else {
+          for (int c0 = 0; c0 < c_tail; c0 += 32) {
+            float t[32];
+            tmem_ld32_issue(TM_S + lane_base + c0, t);
+            tmem_wait_ld32(t);
+            softmax_cols<32, DROP, false>(t, negm, 32, 4, l0, l1, l2, l3, DROP ? hash32((ctr + (c0 >> 5)) ^ salt) : 0u, cadd, thr2,
+                                          prow + (size_t)(c0 >> 3) * 128);
           }
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            if (c_tail + cc * 8 < Pkl) {
-              if (DROP) drop8(&t[cc * 8], drop_base + (c_tail >> 3) + cc, a.thr16, 1.0f, a.key);
-              prow[(size_t)((c_tail >> 3) + cc) * 128] = pack8_bf16(&t[cc * 8]);
+          if (c_tail < Pkl) {
+            const uint32_t st = DROP ? hash32((ctr + (c_tail >> 5)) ^ salt) : 0u;
+            if (tail32) {
+              float t[32];
+              tmem_ld32_issue(TM_S + lane_base + c_tail, t);
+              tmem_wait_ld32(t);
+              softmax_cols<32, DROP, true>(t, negm, Pl - c_tail, (Pkl - c_tail) / 8, l0, l1, l2, l3, st, cadd, thr2,
+                                           prow + (size_t)(c_tail >> 3) * 128);
+            } else {
+              float t16[16];
+              tmem_ld16_issue(TM_S + lane_base + c_tail, t16);
+              tmem_wait_ld16(t16);
+              softmax_cols<16, DROP, true>(t16, negm, Pl - c_tail, (Pkl - c_tail) / 8, l0, l1, l2, l3, st, cadd, thr2,
+                                           prow + (size_t)(c_tail >> 3) * 128);
             }
           }
         }
@@ -735,7 +834,7 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       }
       if (row_valid && (!SPLIT || g == 0)) {
         const float inv = a.dscale / l;
-        const long long token = (long long)seq * P + rt * 128 + row;
+        const long long token = (long long)seq * P + rt * 128 + lrow;
         const long long mt = token >> 7;
         const int r = (int)(token & 127);
         uint4 *dst = reinterpret_cast<uint4 *>(a.o_img) + ((size_t)mt * 12 + 3 * h) * 128 + r;
@@ -1127,9 +1226,10 @@ __global__ void __launch_bounds__(TLK_THREADS, 2) tc_layer_kernel(TcLayerArgs a)
           for (int c = 0; c < 96; ++c) v[c] += sBq[qq * 96 + c];
           if (!valid) continue;
           if (qq == 0) {
-            const int rt = p >> 7, r = p & 127;
+            const int rt = p >> 7;
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
+              const int r = (p & 127) + q_tail_offset(a.P, rt, h);
               uint4 *o = reinterpret_cast<uint4 *>(a.q_img) + (((size_t)s * 4 + h) * a.RT + rt) * 3 * 128 + r;
 #pragma unroll
               for (int cc = 0; cc < 3; ++cc) {
@@ -1281,13 +1381,24 @@ extern "C" int step_tc_linear_drop(const void *a_img, const void *w_img, const f
 extern "C" size_t step_tc_attn_image_bytes(int S, int P, int which) {
   const int Pk = (P + 15) / 16 * 16, RT = (P + 127) / 128;
   if (which == 0) return (size_t)S * 4 * RT * 6144;
+  if (which == 2) return (size_t)S * 4 * (P + 1) * sizeof(float);   // row-maximum bound workspace
   return (size_t)S * 4 * 3 * Pk * 16;
 }
 
+// memset of the max |k| slots + the TCM_QKV arguments shared by the public entry point and the encoder driver
+static int tc_qkv_bound_reset(float *bound, long long S, cudaStream_t st) {
+  if (bound == nullptr) return STEP_OK;
+  cudaError_t e = cudaMemsetAsync(bound, 0, (size_t)S * 4 * sizeof(float), st);
+  return e == cudaSuccess ? STEP_OK : fail_msg((int)e, cudaGetErrorString(e));
+}
+
 extern "C" int step_tc_qkv(const void *x_img, const void *w_img, const float *bias, int S, int P, void *q_img, void *k_img,
-                           void *v_img, void *stream) {
+                           void *v_img, float *bound, void *stream) {
   STEP_REQUIRE(x_img && w_img && bias && q_img && k_img && v_img && S > 0 && P > 0, "tc_qkv: bad argument");
+  int rc0 = tc_qkv_bound_reset(bound, S, (cudaStream_t)stream);
+  if (rc0) return rc0;
   TcLinearArgs a{};
+  a.bound = bound; a.nseq = S;
   const long long T = (long long)S * P;
   a.A = (const uint8_t *)x_img; a.W = (const uint8_t *)w_img; a.bias = bias;
   a.MT = (int)((T + 127) / 128); a.K = 96; a.Nout = 288; a.mode = TCM_QKV; a.T = T;
@@ -1298,9 +1409,10 @@ extern "C" int step_tc_qkv(const void *x_img, const void *w_img, const float *bi
   return tc_linear_launch(a, (cudaStream_t)stream);
 }
 
-static int tc_attn_launch(const void *q_img, const void *k_img, const void *v_img, void *o_img, int S, int P, float drop_p,
-                          uint64_t seed, uint32_t site, cudaStream_t st) {
+static int tc_attn_launch(const void *q_img, const void *k_img, const void *v_img, void *o_img, const float *bound, int S, int P,
+                          float drop_p, uint64_t seed, uint32_t site, cudaStream_t st) {
   TcAttnArgs a{};
+  a.bound = bound;
   a.q_img = (const uint8_t *)q_img; a.k_img = (const uint8_t *)k_img; a.v_img = (const uint8_t *)v_img; a.o_img = (uint8_t *)o_img;
   a.S = S; a.P = P; a.Pk = (P + 15) / 16 * 16; a.RT = (P + 127) / 128;
   if (a.Pk > 2 * TCA_KSPLIT) return fail(STEP_EUNSUPPORTED, "tc_attention: P=%lld > 352 is served by the fp32 path", P);
@@ -1325,10 +1437,10 @@ static int tc_attn_launch(const void *q_img, const void *k_img, const void *v_im
   return check_launch("tc_attn_kernel");
 }
 
-extern "C" int step_tc_attention(const void *q_img, const void *k_img, const void *v_img, void *o_img, int S, int P,
-                                 float drop_p, unsigned long long seed, void *stream) {
+extern "C" int step_tc_attention(const void *q_img, const void *k_img, const void *v_img, void *o_img, const float *bound, int S,
+                                 int P, float drop_p, unsigned long long seed, void *stream) {
   STEP_REQUIRE(q_img && k_img && v_img && o_img && S > 0 && P > 0, "tc_attention: bad argument");
-  return tc_attn_launch(q_img, k_img, v_img, o_img, S, P, drop_p, seed, 0, (cudaStream_t)stream);
+  return tc_attn_launch(q_img, k_img, v_img, o_img, bound, S, P, drop_p, seed, 0, (cudaStream_t)stream);
 }
 
 extern "C" size_t step_tc_seq_image_bytes(int B, int N, int P) {
@@ -1389,6 +1501,7 @@ extern "C" size_t step_ts_encoder_bf16_workspace_bytes(int B, int N, int P) {
   b += (size_t)MT * 4 * SLICE_BYTES;                // H image (K = 384)
   b += (size_t)S * 4 * RT * 6144;                   // Q
   b += 2 * (size_t)S * 4 * 3 * Pk * 16;             // K, V
+  b += (size_t)S * 4 * (P + 1) * sizeof(float) + 1024;   // row-maximum bound: max |k| per (sequence, head), |q| per query
   return b + 4096;
 }
 
@@ -1413,7 +1526,8 @@ extern "C" int step_ts_encoder_fwd_bf16(const float *series, long long sB, long 
   uint8_t *H = ws; ws += (size_t)MT * 4 * SLICE_BYTES;
   uint8_t *Q = ws; ws += (size_t)S * 4 * RT * 6144;
   uint8_t *Kimg = ws; ws += (size_t)S * 4 * 3 * Pk * 16;
-  uint8_t *Vimg = ws;
+  uint8_t *Vimg = ws; ws += (size_t)S * 4 * 3 * Pk * 16;
+  float *bound = reinterpret_cast<float *>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
   uint32_t thr16 = 0; float dscale = 1.f;
   if (drop_p > 0.f) { thr16 = (uint32_t)(drop_p * 65536.0f); dscale = 1.f / (1.f - drop_p); }
 
@@ -1436,7 +1550,7 @@ extern "C" int step_ts_encoder_fwd_bf16(const float *series, long long sB, long 
     for (int l = 0; l < n_layers; ++l) {
       const uint32_t site = 16u * (l + 1);
       const bool last = (l == n_layers - 1);
-      if ((rc = tc_attn_launch(Q, Kimg, Vimg, O, (int)S, P, drop_p, seed, site + 1, st))) return rc;
+      if ((rc = tc_attn_launch(Q, Kimg, Vimg, O, nullptr, (int)S, P, drop_p, seed, site + 1, st))) return rc;
       TcLayerArgs t{};
       t.O = O; t.X = cur; t.W = (const uint8_t *)I[l].fused;
       t.bo = L[l].out_proj_b; t.b1 = L[l].lin1_b; t.b2 = L[l].lin2_b; t.bqkv = last ? nullptr : L[l + 1].in_proj_b;
@@ -1463,8 +1577,10 @@ extern "C" int step_ts_encoder_fwd_bf16(const float *series, long long sB, long 
     a.A = cur; a.W = (const uint8_t *)I[l].in_proj; a.bias = L[l].in_proj_b; a.MT = (int)MT; a.K = 96; a.Nout = 288;
     a.mode = TCM_QKV; a.T = T; a.q_img = Q; a.k_img = Kimg; a.v_img = Vimg; a.P = P; a.Pk = Pk; a.RT = RT;
     a.qscale = 0.20412414523193154f * 1.4426950408889634f; a.dscale = 1.f;
+    a.bound = bound; a.nseq = S;
+    if ((rc = tc_qkv_bound_reset(bound, S, st))) return rc;
     if ((rc = tc_linear_launch(a, st))) return rc;
-    if ((rc = tc_attn_launch(Q, Kimg, Vimg, O, (int)S, P, drop_p, seed, site + 1, st))) return rc;
+    if ((rc = tc_attn_launch(Q, Kimg, Vimg, O, bound, (int)S, P, drop_p, seed, site + 1, st))) return rc;
     // X1 = LN1(cur + drop(O Wo^T + bo))
     a = TcLinearArgs{};
     a.A = O; a.W = (const uint8_t *)I[l].out_proj; a.bias = L[l].out_proj_b; a.MT = (int)MT; a.K = 96; a.Nout = 96;

@@ -683,18 +683,23 @@ def tc_linear(a_img: Tensor, w_img: Tensor, bias: Tensor, T: int, K: int, Nout: 
     return out_img, out_f32
 
 
-def tc_qkv_attention(x_img: Tensor, w_img: Tensor, bias: Tensor, S: int, P: int, drop_p: float = 0.0, seed: int = 0) -> Tensor:
-    """X image [S*P,96] -> O image [S*P,96] (QKV projection + softmax(QK^T)V, both on tcgen05)."""
+def tc_qkv_attention(x_img: Tensor, w_img: Tensor, bias: Tensor, S: int, P: int, drop_p: float = 0.0, seed: int = 0,
+                     bounded_max: bool = True) -> Tensor:
+    """X image [S*P,96] -> O image [S*P,96] (QKV projection + softmax(QK^T)V, both on tcgen05).  ``bounded_max``: let the
+    attention kernel replace the row-maximum pass by the Cauchy-Schwarz bound of the operand norms where that is safe."""
     st = _enter(x_img)
     dev = x_img.device
     q = torch.empty(_L().step_tc_attn_image_bytes(S, P, 0), device=dev, dtype=torch.uint8)
     k = torch.empty(_L().step_tc_attn_image_bytes(S, P, 1), device=dev, dtype=torch.uint8)
     v = torch.empty(_L().step_tc_attn_image_bytes(S, P, 1), device=dev, dtype=torch.uint8)
     o = torch.empty(((S * P + 127) // 128) * 96 * 256, device=dev, dtype=torch.uint8)
+    bound = None
+    if bounded_max:
+        bound = torch.empty(_L().step_tc_attn_image_bytes(S, P, 2) // 4, device=dev, dtype=torch.float32)
     check(_L().step_tc_qkv(x_img.data_ptr(), w_img.data_ptr(), _f32(bias, "bias").data_ptr(), S, P, q.data_ptr(), k.data_ptr(),
-                           v.data_ptr(), st), "step_tc_qkv")
-    check(_L().step_tc_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), S, P, float(drop_p), int(seed), st),
-          "step_tc_attention")
+                           v.data_ptr(), _p(bound), st), "step_tc_qkv")
+    check(_L().step_tc_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), _p(bound), S, P, float(drop_p),
+                                 int(seed), st), "step_tc_attention")
     launch_counter["kernels"] += 2
     return o
 

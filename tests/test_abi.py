@@ -42,7 +42,7 @@ def test_argument_validation_returns_status_and_message():
     h = lib.load()
     launched = h.step_launch_count()
     # null pointers -> STEP_EINVAL (-1) and a message naming the entry point
-    rc = h.step_tc_attention(None, None, None, None, 4, 168, 0.0, 0, None)
+    rc = h.step_tc_attention(None, None, None, None, None, 4, 168, 0.0, 0, None)
     assert rc < 0 and b"tc_attention" in h.step_last_error_string()
     rc = h.step_layernorm96_f32(None, None, None, None, 10, None)
     assert rc < 0 and b"layernorm" in h.step_last_error_string()
@@ -53,6 +53,7 @@ def test_argument_validation_returns_status_and_message():
     q, kv = h.step_tc_attn_image_bytes(3, 168, 0), h.step_tc_attn_image_bytes(3, 168, 1)
     assert q == 3 * 4 * 2 * 6144 and kv == 3 * 4 * 3 * 176 * 16          # 2 row tiles of 128; keys padded to 176
     assert h.step_tc_attn_image_bytes(1, 336, 1) == 4 * 3 * 336 * 16
+    assert h.step_tc_attn_image_bytes(3, 168, 2) == 3 * 4 * 169 * 4               # max |k| per head + |q| per query
     assert h.step_tc_seq_image_bytes(2, 207, 168) == 2 * 168 * 12 * 256 * 16
     assert h.step_gwnet_stash_floats(2, 207, 8) > 9 * 2 * 51 * 207 * 32
     assert h.step_launch_count() == launched                               # nothing was launched by the rejected calls

@@ -309,7 +309,12 @@ def test_gwnet_fused_layer_kernel_matches_split_path(N, B, drop):
     assert torch.isfinite(a[0]).all()
     assert rel_err(a[0], b[0]) < 1e-5 and rel_err(a[1], b[1]) < 1e-4 and rel_err(a[2], b[2]) < 1e-5
     assert a[3].keys() == b[3].keys()
+    gmax = max(float(v.abs().max()) for v in b[3].values())
     for k in a[3]:
+        # the mlp bias feeds a training-mode BatchNorm: its gradient is mathematically zero, both paths return rounding noise
+        if float(b[3][k].abs().max()) < 1e-6 * gmax:
+            assert float(a[3][k].abs().max()) < 1e-5 * gmax, k
+            continue
         assert rel_l2(a[3][k], b[3][k]) < 1e-4, k
 
 

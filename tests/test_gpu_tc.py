@@ -141,6 +141,59 @@ def test_tc_cosine_gram_from_encoder_image(B, N, P):
     assert (sim.diagonal(dim1=1, dim2=2) - 1).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("S,P,scale", [(5, 168, 0.15), (3, 336, 0.15), (4, 100, 0.15), (5, 168, 1.5), (2, 336, 1.5)])
+def test_tc_attention_bounded_max_matches_exact_max(S, P, scale):
+    """The one-pass softmax against the Cauchy-Schwarz bound |q_i| max_j |k_j| (attention kernel, bound <= 40) and the exact
+    two-pass row maximum are the same softmax up to the bf16 rounding of the probabilities; projection weights scaled x10
+    push the bound past 40 and exercise the warp-uniform fall-back to the exact route (then both runs are identical)."""
+    from step_b200 import ops
+    g = torch.Generator().manual_seed(S + P)
+    T = S * P
+    x = torch.randn(T, 96, generator=g)
+    w, b = torch.randn(288, 96, generator=g) * scale, torch.randn(288, generator=g) * 0.1
+    x_img, w_img = ops.tc_rows_to_image(x.to(DEV)), ops.tc_pack_weight(w.to(DEV))
+    got = [ops.tc_image_to_rows(ops.tc_qkv_attention(x_img, w_img, b.to(DEV), S, P, bounded_max=bm), T, 96).cpu() for bm in (True, False)]
+    assert torch.isfinite(got[0]).all()
+    qkv = bf(x) @ bf(w).t() + b
+    q, k, v = qkv.view(S, P, 288).split(96, -1)
+    sh = lambda t: t.reshape(S, P, 4, 24).transpose(1, 2)
+    bound = (sh(q).norm(dim=-1) * sh(k).norm(dim=-1).amax(-1, keepdim=True)) * (1.4426950408889634 / math.sqrt(24))
+    if scale > 1.0:
+        assert bound.min().item() > 60                    # every warp holds a row past the limit -> exact route everywhere
+        assert torch.equal(got[0], got[1])
+    else:
+        assert bound.max().item() < 38                    # every row takes the bounded route
+        err = (got[0] - got[1]).abs()
+        assert (err / (got[1].abs() + 1.0)).max().item() < 8e-3 and err.mean().item() < 3e-4
+    att = torch.softmax(sh(q) @ sh(k).transpose(-1, -2) / math.sqrt(24), -1)
+    ref = (att @ sh(v)).transpose(1, 2).reshape(T, 96)
+    err = (got[0] - ref).abs()
+    assert err.max().item() < (1e-1 if scale < 1 else 0.5) and err.mean().item() < (4e-3 if scale < 1 else 2e-2)
+
+
+def test_tc_attention_dropout_per_key_rates():
+    """Keep rate of the attention-probability dropout per key residue class (both 16-bit halves of the random word and all
+    positions of an 8-key chunk): v_j = one-hot(j mod 24), q = k = 0 -> O[row, head, d] = mean keep over keys j = d mod 24."""
+    from step_b200 import ops
+    S, P, p = 24, 168, 0.1
+    T = S * P
+    x = torch.zeros(T, 96)
+    x[torch.arange(T), torch.arange(T) % P % 24] = 1.0
+    w = torch.zeros(288, 96)
+    for h in range(4):
+        for d in range(24):
+            w[192 + h * 24 + d, d] = 1.0
+    o_img = ops.tc_qkv_attention(ops.tc_rows_to_image(x.to(DEV)), ops.tc_pack_weight(w.to(DEV)), torch.zeros(288, device=DEV), S, P,
+                                 drop_p=p, seed=11)
+    out = ops.tc_image_to_rows(o_img, T, 96).cpu().view(T, 4, 24) * (1 - p) * P / 7.0      # mean keep of the 7 keys of class d
+    rate = out.mean((0, 1))
+    n = T * 4 * 7
+    assert (rate - (1 - p)).abs().max().item() < 5 * math.sqrt(p * (1 - p) / n) + 2e-3, rate
+    # different keys of one row are dropped independently: variance of the per-row kept count is binomial
+    cnt = out.sum(-1) * 7.0
+    assert cnt.var().item() == pytest.approx(P * p * (1 - p), rel=0.1)
+
+
 def test_tc_attention_dropout_statistics():
     """Counter-hash dropout of the tensor-core path: keep probability 1 - p, binomial spread, reproducible per seed."""
     from step_b200 import ops
