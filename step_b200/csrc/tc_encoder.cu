@@ -674,6 +674,17 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
     const uint32_t cadd = (salt_lo * 0x85EBCA6Bu) | 1u;
     const uint32_t *kmax = reinterpret_cast<const uint32_t *>(a.bound);
     const float *qnorm = a.bound != nullptr ? a.bound + (size_t)a.S * 4 : nullptr;
+    // operand norms of iteration `it` (loaded one iteration ahead: the global-memory latency stays off the critical path)
+    auto load_bound = [&](int it, float &qn, float &km) {
+      qn = 0.f; km = 0.f;
+      if (qnorm == nullptr || it >= NIT) return;
+      const int seq = blockIdx.x + (it / per_seq) * gridDim.x, w = it % per_seq, h = w / RT, rt = w % RT;
+      const int lrow = row - q_tail_offset(P, rt, h);
+      if (lrow >= 0 && lrow < min(128, P - rt * 128)) qn = __ldg(qnorm + ((size_t)seq * 4 + h) * P + rt * 128 + lrow);
+      km = __uint_as_float(__ldg(kmax + (size_t)seq * 4 + h));
+    };
+    float qn_next, km_next;
+    load_bound(SPLIT ? 0 : g, qn_next, km_next);
     for (int i = SPLIT ? 0 : g; i < NIT; i += SPLIT ? 1 : 2) {
       const int u = SPLIT ? i : i >> 1;
       const int seq = blockIdx.x + (i / per_seq) * gridDim.x, w = i % per_seq, h = w / RT, rt = w % RT;
@@ -682,6 +693,8 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       const int lrow = row - roff;                       // query index inside the row tile
       const bool warp_active = q * 32 + 32 > roff && q * 32 < roff + rows_valid;
       const bool row_valid = lrow >= 0 && lrow < rows_valid;
+      const float qn = qn_next, km = km_next;
+      load_bound(i + (SPLIT ? 1 : 2), qn_next, km_next);
       // Upper bound of the row maximum without reading the scores (Cauchy-Schwarz on the bf16 operands, written by the
       // QKV epilogue): s_ij <= |q_i| max_j |k_j|.  Softmax is shift invariant, so any m >= max works as long as
       // 2^(s - m) stays representable: with m_b <= 40 every s - m_b lies in [-80, 0].  Rows with a larger bound (never
@@ -689,8 +702,6 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       float mb = 0.f;
       bool bounded = false;
       if (qnorm != nullptr && warp_active) {
-        const float qn = row_valid ? __ldg(qnorm + ((size_t)seq * 4 + h) * P + rt * 128 + lrow) : 0.f;
-        const float km = __uint_as_float(__ldg(kmax + (size_t)seq * 4 + h));
         mb = fmaf(qn * km, 1.01f, 1e-3f);
         bounded = !__any_sync(0xffffffffu, !(mb <= 40.f));
       }
@@ -987,6 +998,8 @@ struct TcLayerArgs {
   const float *ln1w, *ln1b, *ln2w, *ln2b, *fnw, *fnb;
   uint8_t *Xout;                   // next layer's input image (nullptr for the last layer)
   uint8_t *q_img, *k_img, *v_img;  // next layer's attention operands
+  float *bound;                    // next layer's row-maximum bound workspace (max |k| slots zeroed by the host); may be null
+  long long nseq;
   float *hidden;                   // last layer: fp32 [T][96]
   uint8_t *seq_img;                // last layer: Gram operand image (may be null)
   int seq_nodes, seq_rows;
@@ -1231,13 +1244,15 @@ __global__ void __launch_bounds__(TLK_THREADS, 2) tc_layer_kernel(TcLayerArgs a)
             for (int h = 0; h < 4; ++h) {
               const int r = (p & 127) + q_tail_offset(a.P, rt, h);
               uint4 *o = reinterpret_cast<uint4 *>(a.q_img) + (((size_t)s * 4 + h) * a.RT + rt) * 3 * 128 + r;
+              float n2 = 0.f;
 #pragma unroll
               for (int cc = 0; cc < 3; ++cc) {
                 float x[8];
 #pragma unroll
-                for (int jx = 0; jx < 8; ++jx) x[jx] = v[h * HD + cc * 8 + jx] * a.qscale;
+                for (int jx = 0; jx < 8; ++jx) { x[jx] = v[h * HD + cc * 8 + jx] * a.qscale; n2 = fmaf(x[jx], x[jx], n2); }
                 o[cc * 128] = pack8_bf16(x);
               }
+              if (a.bound != nullptr) a.bound[(size_t)a.nseq * 4 + ((size_t)s * 4 + h) * a.P + p] = sqrtf(n2);
             }
           } else {
             uint8_t *base = (qq == 1) ? a.k_img : a.v_img;
@@ -1246,6 +1261,12 @@ __global__ void __launch_bounds__(TLK_THREADS, 2) tc_layer_kernel(TcLayerArgs a)
               uint4 *o = reinterpret_cast<uint4 *>(base) + ((size_t)s * 4 + h) * 3 * a.Pk + p;
 #pragma unroll
               for (int cc = 0; cc < 3; ++cc) o[(size_t)cc * a.Pk] = pack8_bf16(&v[h * HD + cc * 8]);
+              if (qq == 1 && a.bound != nullptr) {      // max_j |k_j| of the next layer (see the TCM_QKV epilogue)
+                float n2 = 0.f;
+#pragma unroll
+                for (int c = 0; c < HD; ++c) n2 = fmaf(v[h * HD + c], v[h * HD + c], n2);
+                atomicMax(reinterpret_cast<uint32_t *>(a.bound) + s * 4 + h, __float_as_uint(sqrtf(n2)));
+              }
             }
           }
         }
@@ -1546,12 +1567,16 @@ extern "C" int step_ts_encoder_fwd_bf16(const float *series, long long sB, long 
     a.A = cur; a.W = (const uint8_t *)I[0].in_proj; a.bias = L[0].in_proj_b; a.MT = (int)MT; a.K = 96; a.Nout = 288;
     a.mode = TCM_QKV; a.T = T; a.q_img = Q; a.k_img = Kimg; a.v_img = Vimg; a.P = P; a.Pk = Pk; a.RT = RT;
     a.qscale = 0.20412414523193154f * 1.4426950408889634f; a.dscale = 1.f;
+    a.bound = bound; a.nseq = S;
+    if ((rc = tc_qkv_bound_reset(bound, S, st))) return rc;
     if ((rc = tc_linear_launch(a, st))) return rc;
     for (int l = 0; l < n_layers; ++l) {
       const uint32_t site = 16u * (l + 1);
       const bool last = (l == n_layers - 1);
-      if ((rc = tc_attn_launch(Q, Kimg, Vimg, O, nullptr, (int)S, P, drop_p, seed, site + 1, st))) return rc;
+      if ((rc = tc_attn_launch(Q, Kimg, Vimg, O, bound, (int)S, P, drop_p, seed, site + 1, st))) return rc;
+      if (!last && (rc = tc_qkv_bound_reset(bound, S, st))) return rc;
       TcLayerArgs t{};
+      t.bound = bound; t.nseq = S;
       t.O = O; t.X = cur; t.W = (const uint8_t *)I[l].fused;
       t.bo = L[l].out_proj_b; t.b1 = L[l].lin1_b; t.b2 = L[l].lin2_b; t.bqkv = last ? nullptr : L[l + 1].in_proj_b;
       t.ln1w = L[l].norm1_w; t.ln1b = L[l].norm1_b; t.ln2w = L[l].norm2_w; t.ln2b = L[l].norm2_b;

@@ -33,11 +33,13 @@ ALL_GOLDEN = ["step_PEMS08_b1.pt", "step_METR-LA_b2.pt", "step_PEMS04_b1.pt", "s
 # that element feeds and O(1/(B N)) everywhere upstream.  Hence: relative L2 error over the sampled entries ("gl2") and the
 # tensor norm ("gnorm") are held tightly, single entries ("grad", relative to the tensor's max) loosely.  In bf16 mode the
 # hidden states that enter fc_his carry |error| <= 9e-2, which moves many of its 512 first-layer ReLU boundaries: measured
-# relative L2 of fc_his.0.weight's gradient 7-10 % (the worst tensor), every tensor norm within 2.6 %.
+# relative L2 of fc_his.0.weight's gradient 7-10 % (the worst tensor), every tensor norm within 2.6-4.0 % (the largest on
+# the 32-entry BatchNorm biases downstream; it moves with every re-draw of the bf16 rounding noise, e.g. the attention
+# kernel's choice of softmax offset).
 TOL = {"fp32": dict(y=1e-4, y_synth=1e-4, theta=2e-4, hidden=2e-4, hsum=1e-5, bern=1e-4, knn=8, sampled=2, loss=5e-5, grad=6e-2,
                     gl2=1.5e-2, gnorm=1e-2),
        "bf16": dict(y=1e-4, y_synth=1.5e-4, theta=2e-4, hidden=0.15, hsum=2e-3, bern=1e-4, knn=None, sampled=2, loss=5e-4,
-                    grad=0.2, gl2=0.15, gnorm=3e-2)}
+                    grad=0.2, gl2=0.15, gnorm=6e-2)}
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

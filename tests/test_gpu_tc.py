@@ -69,7 +69,8 @@ def test_tc_qkv_attention(S, P):
     sh = lambda t: t.reshape(S, P, 4, 24).transpose(1, 2)
     att = torch.softmax(sh(q) @ sh(k).transpose(-1, -2) / math.sqrt(24), -1)
     ref = (att @ sh(v)).transpose(1, 2).reshape(T, 96)
-    o_img = ops.tc_qkv_attention(ops.tc_rows_to_image(x.to(DEV)), ops.tc_pack_weight(w.to(DEV)), b.to(DEV), S, P)
+    # the exact-row-maximum route is checked here; test_tc_attention_bounded_max_matches_exact_max covers the bounded one
+    o_img = ops.tc_qkv_attention(ops.tc_rows_to_image(x.to(DEV)), ops.tc_pack_weight(w.to(DEV)), b.to(DEV), S, P, bounded_max=False)
     out = ops.tc_image_to_rows(o_img, T, 96).cpu()
     err = (out - ref).abs()
     # vs exact fp32 softmax: bf16 q/k/v/p carry ~2^-8 relative error per operand; values are O(1).  The max grows with
@@ -141,11 +142,13 @@ def test_tc_cosine_gram_from_encoder_image(B, N, P):
     assert (sim.diagonal(dim1=1, dim2=2) - 1).abs().max().item() < 1e-5
 
 
-@pytest.mark.parametrize("S,P,scale", [(5, 168, 0.15), (3, 336, 0.15), (4, 100, 0.15), (5, 168, 1.5), (2, 336, 1.5)])
+@pytest.mark.parametrize("S,P,scale", [(5, 168, 0.1), (3, 336, 0.1), (4, 100, 0.1), (3, 200, 0.1), (5, 168, 1.5), (2, 336, 1.5)])
 def test_tc_attention_bounded_max_matches_exact_max(S, P, scale):
     """The one-pass softmax against the Cauchy-Schwarz bound |q_i| max_j |k_j| (attention kernel, bound <= 40) and the exact
-    two-pass row maximum are the same softmax up to the bf16 rounding of the probabilities; projection weights scaled x10
-    push the bound past 40 and exercise the warp-uniform fall-back to the exact route (then both runs are identical)."""
+    two-pass row maximum are the same softmax up to the bf16 rounding of the probabilities (a different power-of-two-free
+    scale re-draws every rounding: the outputs differ by independent rounding noise, not by a bias); projection weights
+    scaled x10 push the bound past 40 and exercise the warp-uniform fall-back to the exact route (then both runs are
+    bit-identical)."""
     from step_b200 import ops
     g = torch.Generator().manual_seed(S + P)
     T = S * P
@@ -161,14 +164,17 @@ def test_tc_attention_bounded_max_matches_exact_max(S, P, scale):
     if scale > 1.0:
         assert bound.min().item() > 60                    # every warp holds a row past the limit -> exact route everywhere
         assert torch.equal(got[0], got[1])
-    else:
-        assert bound.max().item() < 38                    # every row takes the bounded route
-        err = (got[0] - got[1]).abs()
-        assert (err / (got[1].abs() + 1.0)).max().item() < 8e-3 and err.mean().item() < 3e-4
+        return
+    assert bound.max().item() < 38                        # every row takes the bounded route
+    assert not torch.equal(got[0], got[1])
+    err = (got[0] - got[1]).abs()
+    assert (err / (got[1].abs() + 1.0)).max().item() < 1e-2 and err.mean().item() < 1.5e-3
+    assert abs((got[0] - got[1]).mean().item()) < 5e-5   # no bias between the two routes
     att = torch.softmax(sh(q) @ sh(k).transpose(-1, -2) / math.sqrt(24), -1)
     ref = (att @ sh(v)).transpose(1, 2).reshape(T, 96)
-    err = (got[0] - ref).abs()
-    assert err.max().item() < (1e-1 if scale < 1 else 0.5) and err.mean().item() < (4e-3 if scale < 1 else 2e-2)
+    e_b, e_x = (got[0] - ref).abs(), (got[1] - ref).abs()
+    assert e_b.max().item() < 1e-1 and e_b.mean().item() < 4e-3
+    assert e_b.mean().item() < 1.25 * e_x.mean().item() + 1e-4   # as close to the fp32 softmax as the exact route
 
 
 def test_tc_attention_dropout_per_key_rates():
