@@ -511,6 +511,8 @@ struct TcAttnArgs {
   const uint8_t *q_img, *k_img, *v_img;
   uint8_t *o_img;
   const float *bound;      // [S*4] max_j |k_j| (as uint bits) then [S*4][P] |q_i| of the bf16 operands; null -> exact row maxima
+  long long *trace;        // profiling aid (null in production): clock64 stamps of CTA 0, [iteration][3 roles][8]
+  int trace_iters;
   int S, P, Pk, RT;
   uint32_t thr16; float dscale; uint64_t key;
 };
@@ -633,10 +635,14 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       for (int j = 0; j <= NIT; ++j) {
         if (j < NIT) {
           const int i = j, g = i & 1, u = i >> 1, rt = (i % per_seq) % RT, hi = i / RT, kvb = hi % TCA_KVBUF, qb = i & 3;
+          const bool tr = a.trace != nullptr && blockIdx.x == 0 && i < a.trace_iters;
+          if (tr) a.trace[((size_t)i * 3 + 2) * 8 + 0] = clock64();
           if (rt == 0) mbar_wait(&kv_full[kvb], (hi / TCA_KVBUF) & 1);
           mbar_wait(&q_full[qb], (i >> 2) & 1);
+          if (tr) a.trace[((size_t)i * 3 + 2) * 8 + 1] = clock64();
           mbar_wait(&s_empty[g], (u & 1) ^ 1);
           tc_fence_after();
+          if (tr) a.trace[((size_t)i * 3 + 2) * 8 + 2] = clock64();
           const uint32_t qa = smem_u32(sQ + qb * 6144), ka = smem_u32(sK + kvb * KVB), ts = tmem + g * 256;
           // k-step 0: head dims 0..15 (chunks 0,1); k-step 1: dims 16..23 + the shared zero chunk
           umma_bf16(ts, umma_desc(qa, 2048, 128), umma_desc(ka, Pk * 16, 128), idesc_s, 0u);
@@ -647,9 +653,12 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
         }
         if (j >= 1) {
           const int i = j - 1, g = i & 1, u = i >> 1, rt = (i % per_seq) % RT, hi = i / RT, kvb = hi % TCA_KVBUF;
+          const bool tr = a.trace != nullptr && blockIdx.x == 0 && i < a.trace_iters;
+          if (tr) a.trace[((size_t)i * 3 + 2) * 8 + 3] = clock64();
           mbar_wait(&p_ready[g], u & 1);
           mbar_wait(&o_empty[g], (u & 1) ^ 1);
           tc_fence_after();
+          if (tr) a.trace[((size_t)i * 3 + 2) * 8 + 4] = clock64();
           const uint32_t pa = smem_u32(sP + g * PB), va = smem_u32(sV + kvb * KVB), to = tmem + g * 256 + 192;
           for (int kk = 0; kk < Pk / 16; ++kk)
             umma_bf16(to, umma_desc(pa + kk * 2 * 2048, 2048, 128), umma_desc(va + kk * 256, 128, Pk * 16), idesc_o,
@@ -680,8 +689,10 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       if (qnorm == nullptr || it >= NIT) return;
       const int seq = blockIdx.x + (it / per_seq) * gridDim.x, w = it % per_seq, h = w / RT, rt = w % RT;
       const int lrow = row - q_tail_offset(P, rt, h);
-      if (lrow >= 0 && lrow < min(128, P - rt * 128)) qn = __ldg(qnorm + ((size_t)seq * 4 + h) * P + rt * 128 + lrow);
-      km = __uint_as_float(__ldg(kmax + (size_t)seq * 4 + h));
+      // volatile asm: the loads must issue HERE (one iteration early), not be sunk to their use
+      if (lrow >= 0 && lrow < min(128, P - rt * 128))
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(qn) : "l"(qnorm + ((size_t)seq * 4 + h) * P + rt * 128 + lrow));
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(km) : "l"(kmax + (size_t)seq * 4 + h));
     };
     float qn_next, km_next;
     load_bound(SPLIT ? 0 : g, qn_next, km_next);
@@ -705,8 +716,12 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
         mb = fmaf(qn * km, 1.01f, 1e-3f);
         bounded = !__any_sync(0xffffffffu, !(mb <= 40.f));
       }
+      const bool tr = a.trace != nullptr && blockIdx.x == 0 && i < a.trace_iters && lane == 0 && q == (roff ? 2 : 0);
+      long long *trp = tr ? a.trace + ((size_t)i * 3 + g) * 8 : nullptr;
+      if (tr) trp[0] = clock64();
       mbar_wait(&s_full[g], u & 1);
       tc_fence_after();
+      if (tr) trp[1] = clock64();
       // V rows of the padded keys must be finite zeros (P is 0 there, but 0 * NaN = NaN)
       if (rt == 0 && q == 2 && (!SPLIT || g == 1)) {
         const int npad = Pk - P, kvb = (i / RT) % KVBUFS;
@@ -816,9 +831,11 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) { mbar_arrive(&s_empty[g]); mbar_arrive(&p_ready[g]); }
+      if (tr) trp[2] = clock64();
       // epilogue: O / l  -> O tile image (token-tile format of the following out-projection GEMM)
       mbar_wait(&o_full[g], u & 1);
       tc_fence_after();
+      if (tr) trp[3] = clock64();
       float o[32];
       if (warp_active) tmem_ld32(TM_O + lane_base, o);
       tc_fence_before();
@@ -857,6 +874,7 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
           dst[cc * 128] = pack8_bf16(x8);
         }
       }
+      if (tr) trp[4] = clock64();
     }
   }
   tc_fence_before();
@@ -1278,6 +1296,228 @@ __global__ void __launch_bounds__(TLK_THREADS, 2) tc_layer_kernel(TcLayerArgs a)
   if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
+// ===========================================================================
+// Fused feed-forward block of one encoder layer (transformer_layers.py:10-11 -> nn.TransformerEncoderLayer:
+// linear1 -> ReLU -> dropout -> linear2 -> dropout2 -> + residual -> norm2 [-> encoder_norm]) per 128-token tile:
+//   H  = drop(relu(X1 W1^T + b1))         four [128 x 96] accumulators in TMEM slots 0..3, K = 96
+//   Y  = H W2^T                           one  [128 x 96] accumulator in slot 4, K = 4 x 96: the bf16 H slice of
+//                                         sub-tile nb goes through ONE 24 KB shared-memory buffer, never to HBM
+//   X2 = LN2(X1 + drop(Y + b2))           residual read from the X1 tile that is still in shared memory
+// Both weight images stay resident (2 x 72 KB); persistent CTA, one per SM.  Same MMAs in the same K order, same
+// dropout counters and the same epilogue arithmetic as tc_linear_kernel<TCM_RELU_IMG> followed by
+// tc_linear_kernel<TCM_RESLN>: results are bit-identical, the 768 B/token H round trip through HBM is gone.
+// Warp roles: warp 0 TMA producer (X1 tiles, 2 stages), warp 1 MMA issuer, warps 2-5 / 6-9 two epilogue groups
+// (group g takes sub-tiles g and g + 2 of every tile; tiles alternate between the groups for the LN epilogue).
+// ===========================================================================
+struct TcFfnArgs {
+  const uint8_t *A;              // X1 tile image [MT][12][128][8]
+  const uint8_t *W1, *W2;        // lin1 image [12][384][8], lin2 image [48][96][8]
+  const float *b1, *b2, *ln_w, *ln_b, *ln2_w, *ln2_b;
+  int MT; long long T;
+  uint8_t *out_img;              // X2 tile image (may be null when out_f32 is given)
+  float *out_f32;                // last layer: fp32 [T][96] after the final LayerNorm
+  uint8_t *seq_img; int seq_nodes, seq_rows, P;
+  uint32_t thr16; float dscale; uint64_t key_h, key_f;
+};
+constexpr uint32_t TFF_W_BYTES = 96 * 384 * 2;
+
+template <bool FINAL>
+__global__ void __launch_bounds__(TCL_THREADS, 1) tc_ffn_kernel(TcFfnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *sW1 = smem;
+  uint8_t *sW2 = sW1 + TFF_W_BYTES;
+  uint8_t *sA = sW2 + TFF_W_BYTES;                    // 2 stages
+  uint8_t *sH = sA + 2 * SLICE_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sH + SLICE_BYTES);
+  uint64_t *full = bars, *empty = bars + 2, *tfull1 = bars + 4, *tempty1 = bars + 8, *h_ready = bars + 12, *h_free = bars + 13;
+  uint64_t *acc2_full = bars + 14, *acc2_empty = bars + 15, *wbar = bars + 16;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 17);
+  float *sB1 = reinterpret_cast<float *>(bars + 20);   // b1[384], b2[96], ln_w, ln_b, ln2_w, ln2_b
+  float *sB2 = sB1 + 384, *sLn = sB2 + 96;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 384; i += blockDim.x) sB1[i] = a.b1[i];
+  for (int i = threadIdx.x; i < 96; i += blockDim.x) {
+    sB2[i] = a.b2[i];
+    sLn[i] = a.ln_w[i]; sLn[96 + i] = a.ln_b[i];
+    sLn[192 + i] = a.ln2_w ? a.ln2_w[i] : 1.f; sLn[288 + i] = a.ln2_b ? a.ln2_b[i] : 0.f;
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&tfull1[i], 1); mbar_init(&tempty1[i], 4); }
+    mbar_init(h_ready, 4); mbar_init(h_free, 1); mbar_init(acc2_full, 1); mbar_init(acc2_empty, 4); mbar_init(wbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int ntiles = (a.MT - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wbar, 2 * TFF_W_BYTES);
+      tma_bulk_g2s(sW1, a.W1, TFF_W_BYTES, wbar);
+      tma_bulk_g2s(sW2, a.W2, TFF_W_BYTES, wbar);
+      for (int it = 0; it < ntiles; ++it) {
+        const int mt = blockIdx.x + it * gridDim.x, s = it & 1;
+        mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&full[s], SLICE_BYTES);
+        tma_bulk_g2s(sA + s * SLICE_BYTES, a.A + (size_t)mt * SLICE_BYTES, SLICE_BYTES, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(wbar, 0);
+      const uint32_t idesc = umma_idesc_bf16(128, 96, 0, 0);
+      const uint32_t sA_addr = smem_u32(sA), sW1_addr = smem_u32(sW1), sW2_addr = smem_u32(sW2), sH_addr = smem_u32(sH);
+      auto mma1 = [&](int it, int nb) {            // H sub-tile nb of tile it: [128 x 96] x W1 rows [96 nb, 96 nb + 96)
+        const uint32_t abase = sA_addr + (it & 1) * SLICE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 6; ++kk)
+          umma_bf16(tmem + nb * 96, umma_desc(abase + kk * 2 * 2048, 2048, 128),
+                    umma_desc(sW1_addr + (uint32_t)(kk * 2) * 6144 + nb * 96 * 16, 6144, 128), idesc, kk != 0 ? 1u : 0u);
+        umma_commit(&tfull1[nb]);
+      };
+      if (ntiles > 0) {
+        mbar_wait(&full[0], 0);
+        tc_fence_after();
+        for (int nb = 0; nb < 4; ++nb) mma1(0, nb);
+      }
+      for (int it = 0; it < ntiles; ++it) {
+        for (int nb = 0; nb < 4; ++nb) {
+          const uint32_t j = (uint32_t)it * 4 + nb;
+          if (nb == 0) mbar_wait(acc2_empty, (it & 1) ^ 1);
+          mbar_wait(h_ready, j & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 6; ++kk)
+            umma_bf16(tmem + 384, umma_desc(sH_addr + kk * 2 * 2048, 2048, 128),
+                      umma_desc(sW2_addr + (uint32_t)(nb * 12 + kk * 2) * 1536, 1536, 128), idesc, (nb | kk) != 0 ? 1u : 0u);
+          umma_commit(h_free);
+          if (nb == 3) umma_commit(acc2_full);
+          if (it + 1 < ntiles) {
+            if (nb == 0) mbar_wait(&full[(it + 1) & 1], ((it + 1) >> 1) & 1);
+            mbar_wait(&tempty1[nb], ((it + 1) & 1) ^ 1);
+            tc_fence_after();
+            mma1(it + 1, nb);
+          }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3, grp = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    auto load_acc = [&](uint32_t col, float *v) {
+      float t0[32];
+      tmem_ld32(tmem + lane_base + col, t0);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[c] = t0[c];
+      tmem_ld32(tmem + lane_base + col + 32, t0);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[32 + c] = t0[c];
+      tmem_ld32(tmem + lane_base + col + 64, t0);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[64 + c] = t0[c];
+    };
+    for (int it = 0; it < ntiles; ++it) {
+      const int mt = blockIdx.x + it * gridDim.x;
+      const long long token = (long long)mt * 128 + row;
+      const bool valid = token < a.T;
+      // ---- E1: H sub-tiles of this group ----
+      for (int nb = grp; nb < 4; nb += 2) {
+        const uint32_t j = (uint32_t)it * 4 + nb;
+        mbar_wait(&tfull1[nb], it & 1);
+        tc_fence_after();
+        float v[96];
+        load_acc(nb * 96, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty1[nb]);
+        const float4 *bias4 = reinterpret_cast<const float4 *>(sB1 + nb * 96);
+#pragma unroll
+        for (int c4 = 0; c4 < 24; ++c4) {
+          const float4 bb = bias4[c4];
+          v[4 * c4] += bb.x; v[4 * c4 + 1] += bb.y; v[4 * c4 + 2] += bb.z; v[4 * c4 + 3] += bb.w;
+        }
+        uint4 pk[12];
+#pragma unroll
+        for (int cc = 0; cc < 12; ++cc) {
+          float x[8];
+#pragma unroll
+          for (int jx = 0; jx < 8; ++jx) x[jx] = fmaxf(v[cc * 8 + jx], 0.f);
+          if (a.thr16) drop8(x, ((uint64_t)token * 384 + nb * 96) / 8 + cc, a.thr16, a.dscale, a.key_h);
+          pk[cc] = pack8_bf16(x);
+        }
+        mbar_wait(h_free, (j & 1) ^ 1);              // the previous slice has been consumed by its MMAs
+        uint4 *o = reinterpret_cast<uint4 *>(sH) + row;
+#pragma unroll
+        for (int cc = 0; cc < 12; ++cc) o[cc * 128] = pk[cc];
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(h_ready);
+      }
+      // ---- E2: residual + LayerNorm epilogue, tiles alternate between the groups ----
+      if ((it & 1) != grp) continue;
+      const int s = it & 1;
+      mbar_wait(acc2_full, it & 1);
+      mbar_wait(&full[s], (it >> 1) & 1);            // X1 tile (TMA-written) visible to this thread: residual operand
+      tc_fence_after();
+      float v[96];
+      load_acc(384, v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc2_empty);
+      {
+        const float4 *bias4 = reinterpret_cast<const float4 *>(sB2);
+#pragma unroll
+        for (int c4 = 0; c4 < 24; ++c4) {
+          const float4 bb = bias4[c4];
+          v[4 * c4] += bb.x; v[4 * c4 + 1] += bb.y; v[4 * c4 + 2] += bb.z; v[4 * c4 + 3] += bb.w;
+        }
+      }
+      const uint4 *res = reinterpret_cast<const uint4 *>(sA + s * SLICE_BYTES) + row;
+#pragma unroll
+      for (int cc = 0; cc < 12; ++cc) {
+        if (a.thr16) drop8(&v[cc * 8], (uint64_t)token * 12 + cc, a.thr16, a.dscale, a.key_f);
+        float r8[8];
+        unpack8_bf16(res[cc * 128], r8);
+#pragma unroll
+        for (int jx = 0; jx < 8; ++jx) v[cc * 8 + jx] += r8[jx];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      layer_norm96(v, sLn, sLn + 96);
+      if (FINAL && a.ln2_w != nullptr) layer_norm96(v, sLn + 192, sLn + 288);
+      if (!FINAL || a.out_img != nullptr) {
+        uint4 *o = reinterpret_cast<uint4 *>(a.out_img) + ((size_t)mt * 12) * 128 + row;
+#pragma unroll
+        for (int cc = 0; cc < 12; ++cc) o[cc * 128] = pack8_bf16(&v[cc * 8]);
+      }
+      if (FINAL && a.out_f32 != nullptr && valid) {
+        float *o = a.out_f32 + token * 96;
+#pragma unroll
+        for (int c = 0; c < 96; c += 4) *reinterpret_cast<float4 *>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      }
+      if (FINAL && a.seq_img != nullptr && valid) {
+        const long long sq = token / a.P;
+        const int pp = (int)(token - sq * a.P);
+        const long long bb = sq / a.seq_nodes;
+        const int nn = (int)(sq - bb * a.seq_nodes);
+        uint4 *o = reinterpret_cast<uint4 *>(a.seq_img) + ((size_t)bb * a.P * 12 + (size_t)pp * 12) * a.seq_rows + nn;
+#pragma unroll
+        for (int cc = 0; cc < 12; ++cc) o[(size_t)cc * a.seq_rows] = pack8_bf16(&v[cc * 8]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+static size_t tff_smem_bytes() { return 2 * (size_t)TFF_W_BYTES + 3 * (size_t)SLICE_BYTES + 20 * 8 + (384 + 96 + 4 * 96) * 4 + 16; }
+
 // ---------------------------------------------------------------------------
 static size_t tcl_smem_bytes(int K, int Nout) {
   return (size_t)K * Nout * 2 + TCL_STAGES * SLICE_BYTES + 32 * 8 + (384 + 4 * 96) * 4 + 16;
@@ -1328,6 +1568,29 @@ static int tc_layer_launch(const TcLayerArgs &a, cudaStream_t st) {
   const int grid = a.MT < 2 * sms ? a.MT : 2 * sms;
   tc_layer_kernel<<<grid, TLK_THREADS, smem, st>>>(a);
   return check_launch("tc_layer_kernel");
+}
+
+static int tc_ffn_launch(const TcFfnArgs &a, cudaStream_t st) {
+  int dev = 0, sms = 148, rc;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t smem = tff_smem_bytes();
+  const int grid = a.MT < sms ? a.MT : sms;
+  const bool fin = a.ln2_w != nullptr || a.out_f32 != nullptr || a.seq_img != nullptr;
+  if (fin) {
+    if ((rc = allow_smem(tc_ffn_kernel<true>, smem))) return rc;
+    tc_ffn_kernel<true><<<grid, TCL_THREADS, smem, st>>>(a);
+  } else {
+    if ((rc = allow_smem(tc_ffn_kernel<false>, smem))) return rc;
+    tc_ffn_kernel<false><<<grid, TCL_THREADS, smem, st>>>(a);
+  }
+  return check_launch("tc_ffn_kernel");
+}
+
+// STEP_B200_FFN_FUSED=0 keeps the two-launch feed-forward path (tc_linear_kernel x 2) for A/B runs
+static bool tc_use_fused_ffn() {
+  const char *e = getenv("STEP_B200_FFN_FUSED");
+  return !(e && e[0] == '0');
 }
 
 }  // namespace stepk
@@ -1430,10 +1693,13 @@ extern "C" int step_tc_qkv(const void *x_img, const void *w_img, const float *bi
   return tc_linear_launch(a, (cudaStream_t)stream);
 }
 
+static long long *g_attn_trace = nullptr;     // set only inside step_tc_attention_trace
+static int g_attn_trace_iters = 0;
+
 static int tc_attn_launch(const void *q_img, const void *k_img, const void *v_img, void *o_img, const float *bound, int S, int P,
                           float drop_p, uint64_t seed, uint32_t site, cudaStream_t st) {
   TcAttnArgs a{};
-  a.bound = bound;
+  a.bound = bound; a.trace = g_attn_trace; a.trace_iters = g_attn_trace_iters;
   a.q_img = (const uint8_t *)q_img; a.k_img = (const uint8_t *)k_img; a.v_img = (const uint8_t *)v_img; a.o_img = (uint8_t *)o_img;
   a.S = S; a.P = P; a.Pk = (P + 15) / 16 * 16; a.RT = (P + 127) / 128;
   if (a.Pk > 2 * TCA_KSPLIT) return fail(STEP_EUNSUPPORTED, "tc_attention: P=%lld > 352 is served by the fp32 path", P);
@@ -1462,6 +1728,19 @@ extern "C" int step_tc_attention(const void *q_img, const void *k_img, const voi
                                  int P, float drop_p, unsigned long long seed, void *stream) {
   STEP_REQUIRE(q_img && k_img && v_img && o_img && S > 0 && P > 0, "tc_attention: bad argument");
   return tc_attn_launch(q_img, k_img, v_img, o_img, bound, S, P, drop_p, seed, 0, (cudaStream_t)stream);
+}
+
+// Profiling aid: the same launch with clock64 stamps of CTA 0 written to `trace` ([trace_iters][3][8] int64: roles 0 / 1 = the two
+// softmax groups {wait S, S ready, P published, O ready, tile stored}, role 2 = the MMA issuer {enter, Q/K/V landed, S slot free,
+// (previous tile) enter PV, P ready}).  tools/attn_trace.py prints the timeline.
+extern "C" int step_tc_attention_trace(const void *q_img, const void *k_img, const void *v_img, void *o_img, const float *bound,
+                                       int S, int P, float drop_p, unsigned long long seed, long long *trace, int trace_iters,
+                                       void *stream) {
+  STEP_REQUIRE(q_img && k_img && v_img && o_img && trace && trace_iters > 0 && S > 0 && P > 0, "tc_attention_trace: bad argument");
+  g_attn_trace = trace; g_attn_trace_iters = trace_iters;
+  const int rc = tc_attn_launch(q_img, k_img, v_img, o_img, bound, S, P, drop_p, seed, 0, (cudaStream_t)stream);
+  g_attn_trace = nullptr; g_attn_trace_iters = 0;
+  return rc;
 }
 
 extern "C" size_t step_tc_seq_image_bytes(int B, int N, int P) {
@@ -1612,13 +1891,28 @@ extern "C" int step_ts_encoder_fwd_bf16(const float *series, long long sB, long 
     a.mode = TCM_RESLN; a.T = T; a.res = cur; a.ln_w = L[l].norm1_w; a.ln_b = L[l].norm1_b; a.out_img = X1;
     a.thr16 = thr16; a.dscale = dscale; a.key = rng_key(seed, site + 2);
     if ((rc = tc_linear_launch(a, st))) return rc;
+    const bool last = (l == n_layers - 1);
+    if (tc_use_fused_ffn()) {
+      // X2 = LN2(X1 + drop(drop(relu(X1 W1^T + b1)) W2^T + b2)) in one launch: the hidden activations stay on chip
+      TcFfnArgs f{};
+      f.A = X1; f.W1 = (const uint8_t *)I[l].lin1; f.W2 = (const uint8_t *)I[l].lin2;
+      f.b1 = L[l].lin1_b; f.b2 = L[l].lin2_b; f.ln_w = L[l].norm2_w; f.ln_b = L[l].norm2_b;
+      f.MT = (int)MT; f.T = T; f.P = P;
+      if (last) {
+        f.ln2_w = fnw; f.ln2_b = fnb; f.out_f32 = hidden; f.out_img = nullptr;
+        f.seq_img = (uint8_t *)seq_img; f.seq_nodes = N; f.seq_rows = (N + 127) / 128 * 128;
+      } else {
+        f.out_img = nxt;
+      }
+      f.thr16 = thr16; f.dscale = dscale; f.key_h = rng_key(seed, site + 3); f.key_f = rng_key(seed, site + 4);
+      if ((rc = tc_ffn_launch(f, st))) return rc;
+    } else {
     // H = drop(relu(X1 W1^T + b1))
     a = TcLinearArgs{};
     a.A = X1; a.W = (const uint8_t *)I[l].lin1; a.bias = L[l].lin1_b; a.MT = (int)MT; a.K = 96; a.Nout = 384;
     a.mode = TCM_RELU_IMG; a.T = T; a.out_img = H; a.thr16 = thr16; a.dscale = dscale; a.key = rng_key(seed, site + 3);
     if ((rc = tc_linear_launch(a, st))) return rc;
     // X2 = LN2(X1 + drop(H W2^T + b2)); last layer: + encoder_norm, fp32 row-major hidden
-    const bool last = (l == n_layers - 1);
     a = TcLinearArgs{};
     a.A = H; a.W = (const uint8_t *)I[l].lin2; a.bias = L[l].lin2_b; a.MT = (int)MT; a.K = 384; a.Nout = 96;
     a.mode = TCM_RESLN; a.T = T; a.res = X1; a.ln_w = L[l].norm2_w; a.ln_b = L[l].norm2_b;
@@ -1629,6 +1923,7 @@ extern "C" int step_ts_encoder_fwd_bf16(const float *series, long long sB, long 
     else a.out_img = nxt;
     a.thr16 = thr16; a.dscale = dscale; a.key = rng_key(seed, site + 4);
     if ((rc = tc_linear_launch(a, st))) return rc;
+    }
     uint8_t *t = cur; cur = nxt; nxt = t;
   }
   return STEP_OK;

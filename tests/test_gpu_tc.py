@@ -245,3 +245,31 @@ def test_fused_token_block_kernel_matches_separate_kernels(B, N, P, drop):
     assert torch.equal(outs[True][0], outs[False][0])
     # the image's padding rows (nodes .. 128-row boundary) are never written: compare what the Gram GEMM reads from it
     assert torch.equal(ops.tc_cosine_gram(outs[True][1], B, N, P), ops.tc_cosine_gram(outs[False][1], B, N, P))
+
+
+@pytest.mark.parametrize("B,N,P,drop", [(2, 9, 168, 0.0), (1, 11, 336, 0.0), (3, 5, 24, 0.0), (2, 13, 168, 0.1), (4, 40, 168, 0.1)])
+def test_fused_ffn_kernel_matches_two_launch_path(B, N, P, drop):
+    """tc_ffn_kernel (linear1 + ReLU + dropout + linear2 + dropout + residual + LayerNorm in one launch, the hidden
+    activations never leave the SM) vs tc_linear_kernel<RELU_IMG> + tc_linear_kernel<RESLN> (STEP_B200_FFN_FUSED=0): same
+    MMAs in the same K order and the same dropout counters -> bit-identical hidden states and Gram operand image."""
+    import os
+    from step_b200 import ops
+    sd = O.synthetic_tsformer_params(2)
+    g = torch.Generator().manual_seed(9)
+    series = torch.randn(B, P * 12, N, generator=g).to(DEV)
+    layers = _layers(sd)
+    images = ops.ts_pack_layer_images(layers)
+    args = (series, sd["patch_embedding.input_embedding.weight"].to(DEV), sd["patch_embedding.input_embedding.bias"].to(DEV),
+            sd["positional_encoding.position_embedding"].to(DEV), layers, images, sd["encoder_norm.weight"].to(DEV),
+            sd["encoder_norm.bias"].to(DEV))
+    outs = {}
+    try:
+        for fused in ("1", "0"):
+            os.environ["STEP_B200_FFN_FUSED"] = fused
+            h, img = ops.ts_encoder_forward_bf16(*args, drop_p=drop, seed=21, want_seq_image=True)
+            outs[fused] = (h.clone(), img.clone())
+    finally:
+        os.environ.pop("STEP_B200_FFN_FUSED", None)
+    assert torch.isfinite(outs["1"][0]).all()
+    assert torch.equal(outs["1"][0], outs["0"][0])
+    assert torch.equal(ops.tc_cosine_gram(outs["1"][1], B, N, P), ops.tc_cosine_gram(outs["0"][1], B, N, P))
