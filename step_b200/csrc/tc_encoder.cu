@@ -520,6 +520,7 @@ struct TcAttnArgs {
 constexpr int TCA_THREADS = 320;
 constexpr int TCA_QBUF = 4, TCA_KVBUF = 3;
 constexpr int TCA_KSPLIT = 176, TCA_KVBUF_SPLIT = 2, TCA_XROW = 27;   // key-split mode (P > 176)
+constexpr int TCA_KHALF = 6;                                           // P = 168: P.V key steps (of 16) issued at half time
 
 // PF > 0: sequence length known at compile time (168 for every 2016-step STEP config) -> unrolled column loops
 // without bounds predicates; DROP: attention-probability dropout compiled in or out.
@@ -547,14 +548,15 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
   uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * PB + (SPLIT ? 2 * 128 * TCA_XROW * 4 : 0));
   uint64_t *q_full = bars, *q_empty = bars + 4, *kv_full = bars + 8, *kv_empty = bars + 11;
   uint64_t *s_full = bars + 14, *s_empty = bars + 16, *p_ready = bars + 18, *o_full = bars + 20, *o_empty = bars + 22;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
+  uint64_t *p_half = bars + 24;                // first TCA_KHALF key steps of P published (PF == 168 route)
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 26);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TCA_QBUF; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < KVBUFS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int g = 0; g < 2; ++g) {
-      mbar_init(&s_full[g], 1); mbar_init(&s_empty[g], 4); mbar_init(&p_ready[g], 4);
+      mbar_init(&s_full[g], 1); mbar_init(&s_empty[g], 4); mbar_init(&p_ready[g], 4); mbar_init(&p_half[g], 4);
       mbar_init(&o_full[g], 1); mbar_init(&o_empty[g], 4);
     }
     fence_barrier_init();
@@ -655,12 +657,19 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
           const int i = j - 1, g = i & 1, u = i >> 1, rt = (i % per_seq) % RT, hi = i / RT, kvb = hi % TCA_KVBUF;
           const bool tr = a.trace != nullptr && blockIdx.x == 0 && i < a.trace_iters;
           if (tr) a.trace[((size_t)i * 3 + 2) * 8 + 3] = clock64();
-          mbar_wait(&p_ready[g], u & 1);
+          // P.V starts on the first TCA_KHALF key steps while the softmax group still exponentiates the rest
+          constexpr int KH = (PF == 168) ? TCA_KHALF : 0;
+          mbar_wait(&p_half[g], u & 1);
           mbar_wait(&o_empty[g], (u & 1) ^ 1);
           tc_fence_after();
-          if (tr) a.trace[((size_t)i * 3 + 2) * 8 + 4] = clock64();
           const uint32_t pa = smem_u32(sP + g * PB), va = smem_u32(sV + kvb * KVB), to = tmem + g * 256 + 192;
-          for (int kk = 0; kk < Pk / 16; ++kk)
+          for (int kk = 0; kk < KH; ++kk)
+            umma_bf16(to, umma_desc(pa + kk * 2 * 2048, 2048, 128), umma_desc(va + kk * 256, 128, Pk * 16), idesc_o,
+                      kk != 0 ? 1u : 0u);
+          mbar_wait(&p_ready[g], u & 1);
+          tc_fence_after();
+          if (tr) a.trace[((size_t)i * 3 + 2) * 8 + 4] = clock64();
+          for (int kk = KH; kk < Pk / 16; ++kk)
             umma_bf16(to, umma_desc(pa + kk * 2 * 2048, 2048, 128), umma_desc(va + kk * 256, 128, Pk * 16), idesc_o,
                       kk != 0 ? 1u : 0u);
           umma_commit(&o_full[g]);
@@ -704,8 +713,6 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       const int lrow = row - roff;                       // query index inside the row tile
       const bool warp_active = q * 32 + 32 > roff && q * 32 < roff + rows_valid;
       const bool row_valid = lrow >= 0 && lrow < rows_valid;
-      const float qn = qn_next, km = km_next;
-      load_bound(i + (SPLIT ? 1 : 2), qn_next, km_next);
       // Upper bound of the row maximum without reading the scores (Cauchy-Schwarz on the bf16 operands, written by the
       // QKV epilogue): s_ij <= |q_i| max_j |k_j|.  Softmax is shift invariant, so any m >= max works as long as
       // 2^(s - m) stays representable: with m_b <= 40 every s - m_b lies in [-80, 0].  Rows with a larger bound (never
@@ -713,9 +720,12 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       float mb = 0.f;
       bool bounded = false;
       if (qnorm != nullptr && warp_active) {
-        mb = fmaf(qn * km, 1.01f, 1e-3f);
+        mb = fmaf(qn_next * km_next, 1.01f, 1e-3f);
         bounded = !__any_sync(0xffffffffu, !(mb <= 40.f));
       }
+      // consume this iteration's norms (above) BEFORE issuing the next iteration's loads: the scoreboard wait of the
+      // consumer would otherwise also cover the newly issued loads and expose their full latency
+      load_bound(i + (SPLIT ? 1 : 2), qn_next, km_next);
       const bool tr = a.trace != nullptr && blockIdx.x == 0 && i < a.trace_iters && lane == 0 && q == (roff ? 2 : 0);
       long long *trp = tr ? a.trace + ((size_t)i * 3 + g) * 8 : nullptr;
       if (tr) trp[0] = clock64();
@@ -731,6 +741,7 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
         }
       }
       float m = -INFINITY, l = 0.f;
+      bool half_done = false;
       if (warp_active) {
         // Full 32-column blocks run unpredicated; only the tail block (columns [c_tail, P), then zero fill up to Pk)
         // carries per-element predicates.
@@ -792,6 +803,12 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
               softmax_cols<32, DROP, false>(tb, negm, 32, 4, l0, l1, l2, l3, DROP ? hash32((ctr + k) ^ salt) : 0u, cadd, thr2,
                                             prow + (size_t)(k * 4) * 128);
             }
+            if (!SPLIT && PF == 168 && k == TCA_KHALF / 2 - 1) {      // columns [0, 16 TCA_KHALF) of P are in shared memory
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&p_half[g]);
+              half_done = true;
+            }
           }
           if (NBLK * 32 < Pkl) {                          // 16-column tail: PF = 168 (8 valid), group 0 of PF = 336 (16 valid)
             float t16[16];
@@ -830,7 +847,7 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&s_empty[g]); mbar_arrive(&p_ready[g]); }
+      if (lane == 0) { mbar_arrive(&s_empty[g]); if (!half_done) mbar_arrive(&p_half[g]); mbar_arrive(&p_ready[g]); }
       if (tr) trp[2] = clock64();
       // epilogue: O / l  -> O tile image (token-tile format of the following out-projection GEMM)
       mbar_wait(&o_full[g], u & 1);
@@ -1306,8 +1323,9 @@ __global__ void __launch_bounds__(TLK_THREADS, 2) tc_layer_kernel(TcLayerArgs a)
 // Both weight images stay resident (2 x 72 KB); persistent CTA, one per SM.  Same MMAs in the same K order, same
 // dropout counters and the same epilogue arithmetic as tc_linear_kernel<TCM_RELU_IMG> followed by
 // tc_linear_kernel<TCM_RESLN>: results are bit-identical, the 768 B/token H round trip through HBM is gone.
-// Warp roles: warp 0 TMA producer (X1 tiles, 2 stages), warp 1 MMA issuer, warps 2-5 / 6-9 two epilogue groups
-// (group g takes sub-tiles g and g + 2 of every tile; tiles alternate between the groups for the LN epilogue).
+// Warp roles: warp 0 TMA producer (X1 tiles, 2 stages), warp 1 MMA issuer, warps 2-5 / 6-9 two H groups (group g takes
+// sub-tiles g and g + 2 of every tile and hands its bf16 slice to the MMA issuer), warps 10-13 the residual + LayerNorm
+// epilogue of every tile - the H pipeline never waits for a LayerNorm.
 // ===========================================================================
 struct TcFfnArgs {
   const uint8_t *A;              // X1 tile image [MT][12][128][8]
@@ -1318,21 +1336,36 @@ struct TcFfnArgs {
   float *out_f32;                // last layer: fp32 [T][96] after the final LayerNorm
   uint8_t *seq_img; int seq_nodes, seq_rows, P;
   uint32_t thr16; float dscale; uint64_t key_h, key_f;
+  volatile int *dbg;             // STEP_FFN_DEBUG builds only: host-mapped progress slots [grid][16]
 };
 constexpr uint32_t TFF_W_BYTES = 96 * 384 * 2;
+constexpr int TFF_THREADS = 448;   // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 the two H groups, warps 10-13 the LayerNorm epilogue
 
+#ifdef STEP_FFN_DEBUG
+// debug build: every wait site records (site, tile) in a host-mapped buffer slot per warp before blocking and clears it after
+#define FFN_WAIT(bar, par, site)                                                                      \
+  do {                                                                                                \
+    if (a.dbg && (threadIdx.x & 31) == 0) { a.dbg[blockIdx.x * 16 + (threadIdx.x >> 5)] = (site); __threadfence_system(); } \
+    mbar_wait(bar, par);                                                                              \
+    if (a.dbg && (threadIdx.x & 31) == 0) { a.dbg[blockIdx.x * 16 + (threadIdx.x >> 5)] = 100 + (site); }  \
+  } while (0)
+#else
+#define FFN_WAIT(bar, par, site) mbar_wait(bar, par)
+#endif
 template <bool FINAL>
-__global__ void __launch_bounds__(TCL_THREADS, 1) tc_ffn_kernel(TcFfnArgs a) {
+__global__ void __launch_bounds__(TFF_THREADS, 1) tc_ffn_kernel(TcFfnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *sW1 = smem;
   uint8_t *sW2 = sW1 + TFF_W_BYTES;
   uint8_t *sA = sW2 + TFF_W_BYTES;                    // 2 stages
   uint8_t *sH = sA + 2 * SLICE_BYTES;
   uint64_t *bars = reinterpret_cast<uint64_t *>(sH + SLICE_BYTES);
-  uint64_t *full = bars, *empty = bars + 2, *tfull1 = bars + 4, *tempty1 = bars + 8, *h_ready = bars + 12, *h_free = bars + 13;
-  uint64_t *acc2_full = bars + 14, *acc2_empty = bars + 15, *wbar = bars + 16;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 17);
-  float *sB1 = reinterpret_cast<float *>(bars + 20);   // b1[384], b2[96], ln_w, ln_b, ln2_w, ln2_b
+  // h_ready / h_free exist once per H group: a group that alternates with the other one on a shared barrier could wait
+  // for a phase two completions ahead, which a parity wait cannot tell from one already completed
+  uint64_t *full = bars, *empty = bars + 2, *tfull1 = bars + 4, *tempty1 = bars + 8, *h_ready = bars + 12, *h_free = bars + 14;
+  uint64_t *acc2_full = bars + 16, *acc2_empty = bars + 18, *wbar = bars + 19;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 20);
+  float *sB1 = reinterpret_cast<float *>(bars + 22);   // b1[384], b2[96], ln_w, ln_b, ln2_w, ln2_b
   float *sB2 = sB1 + 384, *sLn = sB2 + 96;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 384; i += blockDim.x) sB1[i] = a.b1[i];
@@ -1344,7 +1377,9 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_ffn_kernel(TcFfnArgs a) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
     for (int i = 0; i < 4; ++i) { mbar_init(&tfull1[i], 1); mbar_init(&tempty1[i], 4); }
-    mbar_init(h_ready, 4); mbar_init(h_free, 1); mbar_init(acc2_full, 1); mbar_init(acc2_empty, 4); mbar_init(wbar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&h_ready[i], 4); mbar_init(&h_free[i], 1); }
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, 4); mbar_init(wbar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -1361,14 +1396,14 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_ffn_kernel(TcFfnArgs a) {
       tma_bulk_g2s(sW2, a.W2, TFF_W_BYTES, wbar);
       for (int it = 0; it < ntiles; ++it) {
         const int mt = blockIdx.x + it * gridDim.x, s = it & 1;
-        mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
+        FFN_WAIT(&empty[s], ((it >> 1) & 1) ^ 1, 1);
         mbar_expect_tx(&full[s], SLICE_BYTES);
         tma_bulk_g2s(sA + s * SLICE_BYTES, a.A + (size_t)mt * SLICE_BYTES, SLICE_BYTES, &full[s]);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      mbar_wait(wbar, 0);
+      FFN_WAIT(wbar, 0, 2);
       const uint32_t idesc = umma_idesc_bf16(128, 96, 0, 0);
       const uint32_t sA_addr = smem_u32(sA), sW1_addr = smem_u32(sW1), sW2_addr = smem_u32(sW2), sH_addr = smem_u32(sH);
       auto mma1 = [&](int it, int nb) {            // H sub-tile nb of tile it: [128 x 96] x W1 rows [96 nb, 96 nb + 96)
@@ -1380,25 +1415,25 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_ffn_kernel(TcFfnArgs a) {
         umma_commit(&tfull1[nb]);
       };
       if (ntiles > 0) {
-        mbar_wait(&full[0], 0);
+        FFN_WAIT(&full[0], 0, 3);
         tc_fence_after();
         for (int nb = 0; nb < 4; ++nb) mma1(0, nb);
       }
       for (int it = 0; it < ntiles; ++it) {
         for (int nb = 0; nb < 4; ++nb) {
-          const uint32_t j = (uint32_t)it * 4 + nb;
-          if (nb == 0) mbar_wait(acc2_empty, (it & 1) ^ 1);
-          mbar_wait(h_ready, j & 1);
+          const uint32_t k = (uint32_t)it * 2 + (nb >> 1);        // this is the k-th slice of epilogue group nb & 1
+          if (nb == 0) FFN_WAIT(acc2_empty, (it & 1) ^ 1, 4);
+          FFN_WAIT(&h_ready[nb & 1], k & 1, 5);
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < 6; ++kk)
             umma_bf16(tmem + 384, umma_desc(sH_addr + kk * 2 * 2048, 2048, 128),
                       umma_desc(sW2_addr + (uint32_t)(nb * 12 + kk * 2) * 1536, 1536, 128), idesc, (nb | kk) != 0 ? 1u : 0u);
-          umma_commit(h_free);
+          umma_commit(&h_free[(nb & 1) ^ 1]);                      // the H buffer passes to the other group
           if (nb == 3) umma_commit(acc2_full);
           if (it + 1 < ntiles) {
-            if (nb == 0) mbar_wait(&full[(it + 1) & 1], ((it + 1) >> 1) & 1);
-            mbar_wait(&tempty1[nb], ((it + 1) & 1) ^ 1);
+            if (nb == 0) FFN_WAIT(&full[(it + 1) & 1], ((it + 1) >> 1) & 1, 6);
+            FFN_WAIT(&tempty1[nb], ((it + 1) & 1) ^ 1, 7);
             tc_fence_after();
             mma1(it + 1, nb);
           }
@@ -1425,10 +1460,10 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_ffn_kernel(TcFfnArgs a) {
       const int mt = blockIdx.x + it * gridDim.x;
       const long long token = (long long)mt * 128 + row;
       const bool valid = token < a.T;
-      // ---- E1: H sub-tiles of this group ----
-      for (int nb = grp; nb < 4; nb += 2) {
-        const uint32_t j = (uint32_t)it * 4 + nb;
-        mbar_wait(&tfull1[nb], it & 1);
+      // ---- E1 (warps 2-5 / 6-9): H sub-tiles of this group ----
+      for (int nb = grp; nb < 4 && grp < 2; nb += 2) {
+        const uint32_t k = (uint32_t)it * 2 + (nb >> 1);
+        FFN_WAIT(&tfull1[nb], it & 1, 8);
         tc_fence_after();
         float v[96];
         load_acc(nb * 96, v);
@@ -1450,19 +1485,21 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_ffn_kernel(TcFfnArgs a) {
           if (a.thr16) drop8(x, ((uint64_t)token * 384 + nb * 96) / 8 + cc, a.thr16, a.dscale, a.key_h);
           pk[cc] = pack8_bf16(x);
         }
-        mbar_wait(h_free, (j & 1) ^ 1);              // the previous slice has been consumed by its MMAs
+        // the previous slice (the other group's) has been consumed by its MMAs: group 0's k-th turn follows the (k-1)-th
+        // hand-over to it (none before its first), group 1's k-th turn the k-th
+        FFN_WAIT(&h_free[grp], grp == 0 ? ((k & 1) ^ 1) : (k & 1), 9);
         uint4 *o = reinterpret_cast<uint4 *>(sH) + row;
 #pragma unroll
         for (int cc = 0; cc < 12; ++cc) o[cc * 128] = pk[cc];
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(h_ready);
+        if (lane == 0) mbar_arrive(&h_ready[grp]);
       }
-      // ---- E2: residual + LayerNorm epilogue, tiles alternate between the groups ----
-      if ((it & 1) != grp) continue;
+      // ---- E2 (warps 10-13): residual + LayerNorm epilogue of every tile ----
+      if (grp != 2) continue;
       const int s = it & 1;
-      mbar_wait(acc2_full, it & 1);
-      mbar_wait(&full[s], (it >> 1) & 1);            // X1 tile (TMA-written) visible to this thread: residual operand
+      FFN_WAIT(acc2_full, it & 1, 10);
+      FFN_WAIT(&full[s], (it >> 1) & 1, 11);            // X1 tile (TMA-written) visible to this thread: residual operand
       tc_fence_after();
       float v[96];
       load_acc(384, v);
@@ -1516,7 +1553,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_ffn_kernel(TcFfnArgs a) {
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-static size_t tff_smem_bytes() { return 2 * (size_t)TFF_W_BYTES + 3 * (size_t)SLICE_BYTES + 20 * 8 + (384 + 96 + 4 * 96) * 4 + 16; }
+static size_t tff_smem_bytes() { return 2 * (size_t)TFF_W_BYTES + 3 * (size_t)SLICE_BYTES + 22 * 8 + (384 + 96 + 4 * 96) * 4 + 16; }
 
 // ---------------------------------------------------------------------------
 static size_t tcl_smem_bytes(int K, int Nout) {
@@ -1579,18 +1616,20 @@ static int tc_ffn_launch(const TcFfnArgs &a, cudaStream_t st) {
   const bool fin = a.ln2_w != nullptr || a.out_f32 != nullptr || a.seq_img != nullptr;
   if (fin) {
     if ((rc = allow_smem(tc_ffn_kernel<true>, smem))) return rc;
-    tc_ffn_kernel<true><<<grid, TCL_THREADS, smem, st>>>(a);
+    tc_ffn_kernel<true><<<grid, TFF_THREADS, smem, st>>>(a);
   } else {
     if ((rc = allow_smem(tc_ffn_kernel<false>, smem))) return rc;
-    tc_ffn_kernel<false><<<grid, TCL_THREADS, smem, st>>>(a);
+    tc_ffn_kernel<false><<<grid, TFF_THREADS, smem, st>>>(a);
   }
   return check_launch("tc_ffn_kernel");
 }
 
-// STEP_B200_FFN_FUSED=0 keeps the two-launch feed-forward path (tc_linear_kernel x 2) for A/B runs
+// STEP_B200_FFN_FUSED=1 selects the one-launch feed-forward kernel.  Default off: measured 0.51 ms per layer against
+// 0.42 ms for the two HBM-bound tc_linear launches (profiles/r02_fused_ffn.md) - the per-row epilogue chains, not the
+// 768 B/token H round trip, set its pace.
 static bool tc_use_fused_ffn() {
   const char *e = getenv("STEP_B200_FFN_FUSED");
-  return !(e && e[0] == '0');
+  return e && e[0] == '1';
 }
 
 }  // namespace stepk
@@ -1905,6 +1944,9 @@ extern "C" int step_ts_encoder_fwd_bf16(const float *series, long long sB, long 
         f.out_img = nxt;
       }
       f.thr16 = thr16; f.dscale = dscale; f.key_h = rng_key(seed, site + 3); f.key_f = rng_key(seed, site + 4);
+#ifdef STEP_FFN_DEBUG
+      { const char *e = getenv("STEP_FFN_DEBUG_PTR"); f.dbg = e ? (volatile int *)strtoull(e, nullptr, 0) : nullptr; }
+#endif
       if ((rc = tc_ffn_launch(f, st))) return rc;
     } else {
     // H = drop(relu(X1 W1^T + b1))

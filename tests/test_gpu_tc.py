@@ -250,8 +250,9 @@ def test_fused_token_block_kernel_matches_separate_kernels(B, N, P, drop):
 @pytest.mark.parametrize("B,N,P,drop", [(2, 9, 168, 0.0), (1, 11, 336, 0.0), (3, 5, 24, 0.0), (2, 13, 168, 0.1), (4, 40, 168, 0.1)])
 def test_fused_ffn_kernel_matches_two_launch_path(B, N, P, drop):
     """tc_ffn_kernel (linear1 + ReLU + dropout + linear2 + dropout + residual + LayerNorm in one launch, the hidden
-    activations never leave the SM) vs tc_linear_kernel<RELU_IMG> + tc_linear_kernel<RESLN> (STEP_B200_FFN_FUSED=0): same
-    MMAs in the same K order and the same dropout counters -> bit-identical hidden states and Gram operand image."""
+    activations never leave the SM; opt-in with STEP_B200_FFN_FUSED=1) vs the default tc_linear_kernel<RELU_IMG> +
+    tc_linear_kernel<RESLN>: same MMAs in the same K order and the same dropout counters -> bit-identical hidden states
+    and Gram operand image."""
     import os
     from step_b200 import ops
     sd = O.synthetic_tsformer_params(2)
