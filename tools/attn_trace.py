@@ -33,6 +33,13 @@ def main():
         ops.check(L.step_tc_attention_trace(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), bound.data_ptr(), S, P, drop, 1,
                                             trace.data_ptr(), iters, st), "trace")
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        ops.check(L.step_tc_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), bound.data_ptr(), S, P, drop, 1, st), "attn")
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"kernel time {e0.elapsed_time(e1) / 20:.4f} ms (20 launches, CUDA events, no trace)")
     t = trace.cpu()
     t0 = int(t[0, 2, 0])
     print("cycles relative to the MMA issuer's first stamp; iteration i: group i&1 (even = full 128-row tile, odd = 40-row tail)")
