@@ -540,7 +540,6 @@ struct TcAttnArgs {
   int trace_iters;
   int khalf;               // P.V key steps issued at half time (0 = all after the softmax)
   int stagger;             // group 1's S is issued when group 0 is half through the same head
-  int manual;              // hand-scheduled softmax pipeline (else the compiler's schedule of the same arithmetic)
   int S, P, Pk, RT;
   uint32_t thr16; float dscale; uint64_t key;
 };
@@ -831,7 +830,7 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
           // the warp on the 4-lane/clk XU pipe (ptxas clusters them otherwise: measured 2700 cycles per row block
           // against the 1344-cycle MUFU floor).
           constexpr int NBLK = 5;
-          if (a.manual) {
+          {
           float t[3][32];
           tmem_ld32_issue(TM_S + lane_base, t[0]);
           tmem_wait_ld32(t[0]);
@@ -875,30 +874,6 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
             if (DROP) v_and(w[7], m_prev);
             v_sts128(dst + 3u * 2048u, w[4], w[5], w[6], w[7]);
             if (!SPLIT && PF == 168 && k == TCA_KHALF / 2 - 1) {      // columns [0, 16 TCA_KHALF) of P are in shared memory
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&p_half[g]);
-              if (g == 0 && q == 0 && lane == 0) *halfcnt = (uint32_t)u + 1u;
-              half_done = true;
-            }
-          }
-          } else {
-          float ta[32], tb[32];
-          tmem_ld32_issue(TM_S + lane_base, ta);
-#pragma unroll
-          for (int k = 0; k < NBLK; ++k) {
-            if ((k & 1) == 0) {
-              tmem_wait_ld32(ta);
-              if (k + 1 < NBLK) tmem_ld32_issue(TM_S + lane_base + (k + 1) * 32, tb);
-              softmax_cols<32, DROP, false>(ta, negm, 32, 4, l0, l1, l2, l3, DROP ? hash32((ctr + k) ^ salt) : 0u, cadd, thr2,
-                                            prow + (size_t)(k * 4) * 128);
-            } else {
-              tmem_wait_ld32(tb);
-              if (k + 1 < NBLK) tmem_ld32_issue(TM_S + lane_base + (k + 1) * 32, ta);
-              softmax_cols<32, DROP, false>(tb, negm, 32, 4, l0, l1, l2, l3, DROP ? hash32((ctr + k) ^ salt) : 0u, cadd, thr2,
-                                            prow + (size_t)(k * 4) * 128);
-            }
-            if (!SPLIT && PF == 168 && k == TCA_KHALF / 2 - 1) {
               fence_proxy_async();
               __syncwarp();
               if (lane == 0) mbar_arrive(&p_half[g]);
@@ -1841,7 +1816,6 @@ static int tc_attn_launch(const void *q_img, const void *k_img, const void *v_im
     const char *e;
     a.khalf = (e = getenv("STEP_B200_ATTN_KHALF")) ? atoi(e) : TCA_KHALF;
     a.stagger = (e = getenv("STEP_B200_ATTN_STAGGER")) ? atoi(e) : 1;
-    a.manual = (e = getenv("STEP_B200_ATTN_MANUAL")) ? atoi(e) : 1;
     if (a.khalf != 0) a.khalf = TCA_KHALF;
   }
   a.q_img = (const uint8_t *)q_img; a.k_img = (const uint8_t *)k_img; a.v_img = (const uint8_t *)v_img; a.o_img = (uint8_t *)o_img;

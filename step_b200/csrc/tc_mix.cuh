@@ -242,7 +242,8 @@ struct TcDpArgs {
   long long pstride[3];       // 0: shared across the batch (adaptive adjacency) -> atomic accumulation
   int B, T, N;
 };
-constexpr int DP_THREADS = 320;
+constexpr int DP_THREADS = 576;          // warp 0 idle, warp 1 MMA issuer, 16 operand-builder / epilogue warps
+constexpr int DP_BUILDERS = DP_THREADS - 64;
 
 __global__ void __launch_bounds__(DP_THREADS, 1) tc_dP_kernel(TcDpArgs a) {
   using namespace tc;
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) tc_dP_kernel(TcDpArgs a) {
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_full + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&built[i], 8); mbar_init(&consumed[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&built[i], DP_BUILDERS / 32); mbar_init(&consumed[i], 1); }
     mbar_init(d_full, 1);
     fence_barrier_init();
   }
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) tc_dP_kernel(TcDpArgs a) {
       umma_commit(d_full);
     }
   } else if (warp >= 2) {
-    const int wt = threadIdx.x - 64;       // 0..255
+    const int wt = threadIdx.x - 64;       // 0..DP_BUILDERS-1
     for (int t = 0; t < a.T; ++t) {
       const int st = t & 1;
       mbar_wait(&consumed[st], ((t >> 1) & 1) ^ 1);
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) tc_dP_kernel(TcDpArgs a) {
       uint4 *Bh = reinterpret_cast<uint4 *>(base + 2 * a_img), *Bl = reinterpret_cast<uint4 *>(base + 2 * a_img + b_img);
       const size_t toff = ((size_t)b * a.T + t) * col;
       // A: rows v = mt*128 + r; chunk = pair*4 + cg
-      for (int u = wt; u < 8 * 128; u += 256) {
+      for (int u = wt; u < 8 * 128; u += DP_BUILDERS) {
         const int chunk = u >> 7, r = u & 127, pair = chunk >> 2, cg = chunk & 3, v = mt * 128 + r;
         float hi[8], lo[8];
         if (v < N) {
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) tc_dP_kernel(TcDpArgs a) {
         Al[u] = pack8_bf16(lo);
       }
       // B: rows w; chunk = pair*4 + cg
-      for (int u = wt; u < 8 * Nb; u += 256) {
+      for (int u = wt; u < 8 * Nb; u += DP_BUILDERS) {
         const int chunk = u / Nb, wl = u - chunk * Nb, w = col0 + wl, pair = chunk >> 2, cg = chunk & 3;
         float hi[8], lo[8];
         if (w < N) {
@@ -360,12 +361,12 @@ __global__ void __launch_bounds__(DP_THREADS, 1) tc_dP_kernel(TcDpArgs a) {
         for (int c = 0; c < 32; ++c) if (c0 + c < Nb) tile[r * ldt + c0 + c] = tv[c];
       }
     }
-    // named barrier over the 8 builder/epilogue warps (256 threads); warps 0/1 do not take part
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // named barrier over the builder/epilogue warps; warps 0/1 do not take part
+    asm volatile("bar.sync 1, %0;" ::"n"(DP_BUILDERS) : "memory");
     {
       const bool shared = a.pstride[s] == 0;
       float *dstb = a.dP[s] + (size_t)b * a.pstride[s];
-      for (int r = warp - 2; r < 128; r += 8) {
+      for (int r = warp - 2; r < 128; r += DP_BUILDERS / 32) {
         const int v = mt * 128 + r;
         if (v >= N) break;
         float *dst = dstb + (size_t)v * N + col0;
