@@ -10,6 +10,7 @@
 // ReLU mask and x-hat in backward) and y2n (the Linear's input).
 #include <math.h>
 #include "common.cuh"
+#include "trunk_tc.cuh"
 
 namespace stepk {
 
@@ -607,9 +608,18 @@ extern "C" int step_dgl_conv_fwd(const float *x, int N, int L0, const float *w1,
     trunk_bn_finalize_kernel<<<1, 32, 0, st>>>(sums, (double)N * d.L1, C1, g1, be1, eps, bn1_stats);
     STEP_LAUNCH_CHECK("trunk_bn_finalize_kernel");
   }
-  trunk_conv2_fwd_kernel<<<dim3(wave_aware_ctas(trunk_conv2_fwd_kernel, 0, (d.L2 + TL - 1) / TL, N, 4), N), 256, 0, st>>>(
-      x, d, w1, b1, bn1_stats, w2, b2, y2, training ? sums + 16 : nullptr);
-  STEP_LAUNCH_CHECK("trunk_conv2_fwd_kernel");
+  if (trunk_use_tc()) {
+    // conv2 as an implicit GEMM on tcgen05 (trunk_tc.cuh): y1n planes rebuilt per tile, taps addressed in place
+    TcConv2Args t{};
+    t.x = x; t.w1 = w1; t.b1 = b1; t.bn1 = bn1_stats; t.w2 = w2; t.b2 = b2; t.y2 = y2;
+    t.sums2 = training ? sums + 16 : nullptr; t.N = N; t.L0 = L0; t.L1 = d.L1; t.L2 = d.L2;
+    int rc = trunk_conv2_tc_launch(t, st);
+    if (rc) return rc;
+  } else {
+    trunk_conv2_fwd_kernel<<<dim3(wave_aware_ctas(trunk_conv2_fwd_kernel, 0, (d.L2 + TL - 1) / TL, N, 4), N), 256, 0, st>>>(
+        x, d, w1, b1, bn1_stats, w2, b2, y2, training ? sums + 16 : nullptr);
+    STEP_LAUNCH_CHECK("trunk_conv2_fwd_kernel");
+  }
   if (training) {
     trunk_bn_finalize_kernel<<<1, 32, 0, st>>>(sums + 16, (double)N * d.L2, C2, g2, be2, eps, bn2_stats);
     STEP_LAUNCH_CHECK("trunk_bn_finalize_kernel");

@@ -352,7 +352,7 @@ def test_gwnet_eval_mode_and_dropout():
 
 
 # --------------------------------------------------------------------------- DGL trunk (conv1/bn1/conv2/bn2)
-@pytest.mark.parametrize("N,L0", [(5, 700), (7, 2100), (33, 1543)])
+@pytest.mark.parametrize("N,L0", [(5, 700), (7, 2100), (33, 1543), (3, 5000)])
 def test_trunk_conv_fwd_bwd(N, L0):
     from step_b200 import ops
     import torch.nn.functional as F
@@ -428,6 +428,38 @@ def test_fused_step_loss_matches_oracle(null_val):
 
 
 # --------------------------------------------------------------------------- trunk fc (split-bf16 tcgen05 GEMMs)
+@pytest.mark.parametrize("N,L0", [(9, 3100), (2, 1033), (300, 1300)])
+def test_trunk_conv2_tensor_core_matches_cuda_core(N, L0):
+    """trunk_conv2_tc_fwd_kernel (implicit GEMM on tcgen05: position-major bf16 hi/lo planes of y1n, the ten taps addressed in
+    place through overlapping K-chunks of one UMMA descriptor, split-bf16 products) against the CUDA-core conv2 forward
+    (STEP_B200_TRUNK_TC=0): y2n and the BatchNorm-2 batch statistics agree to the split's ~2^-17, and the (unchanged)
+    backward fed by either forward gives the same gradients."""
+    import os
+    from step_b200 import ops
+    g = torch.Generator().manual_seed(N * 7 + L0)
+    x = torch.randn(N, L0, generator=g).to(DEV)
+    prm = [torch.randn(8, 1, 10, generator=g) * 0.3, torch.randn(8, generator=g) * 0.1, torch.rand(8, generator=g) + 0.5,
+           torch.randn(8, generator=g) * 0.1, torch.randn(16, 8, 10, generator=g) * 0.1, torch.randn(16, generator=g) * 0.1,
+           torch.rand(16, generator=g) + 0.5, torch.randn(16, generator=g) * 0.1]
+    wgt = torch.randn(N, 16 * (L0 - 18), generator=g).to(DEV)
+    res = {}
+    try:
+        for tcv in ("1", "0"):
+            os.environ["STEP_B200_TRUNK_TC"] = tcv
+            leaves = [p.clone().to(DEV).requires_grad_(True) for p in prm]
+            out, s1, s2 = ops.TrunkConv.apply(x, *leaves, 1e-5, True, None, None)
+            (out * wgt).sum().backward()
+            res[tcv] = (out.detach().clone(), s2.clone(), [l.grad.clone() for l in leaves])
+    finally:
+        os.environ.pop("STEP_B200_TRUNK_TC", None)
+    a, b = res["1"], res["0"]
+    assert torch.isfinite(a[0]).all()
+    assert (a[0] - b[0]).abs().max().item() < 3e-5 * max(1.0, float(b[0].abs().max()))
+    assert rel_err(a[1][:2], b[1][:2]) < 1e-5                   # BN2 batch mean / variance
+    for ga, gb in zip(a[2], b[2]):
+        assert rel_l2(ga, gb) < 2e-4
+
+
 @pytest.mark.parametrize("N,K", [(207, 16 * 2003), (13, 16 * 64), (307, 16 * 1001), (883, 16 * 700), (600, 16 * 301)])
 def test_trunk_fc_fwd_bwd(N, K):
     """feat = BN3(relu(y2n W^T + b)) and all five gradients vs the oracle's formula in float64
