@@ -17,15 +17,21 @@ def main(path, pattern, steps, label):
     hdr = next(r)
     ki, mi, ui, vi, ii = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value"), hdr.index("ID")
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}
-    per = collections.OrderedDict()
+    allk = collections.OrderedDict()
     for row in r:
-        if len(row) <= vi or not re.search(pattern, row[ki]):
+        if len(row) <= vi:
             continue
-        d = per.setdefault(row[ii], {"k": row[ki]})
+        d = allk.setdefault(row[ii], {"k": row[ki]})
         d[row[mi]] = float(row[vi].replace(",", "")) * unit.get(row[ui], 1.0)
-    ids = list(per)
-    n = len(ids) // steps
-    last = [per[i] for i in ids[-n:]]
+    ids = list(allk)
+    # one patch-embedding launch per step: the launches after the last one are the last step (fallback: 1/steps of the log)
+    marks = [i for i, k in enumerate(ids) if "tc_embed_kernel" in allk[k]["k"] or "ts_embed_kernel" in allk[k]["k"]]
+    if len(marks) >= 2:
+        step_ids = ids[marks[-2]:marks[-1]]        # a complete step: [embed of step k, embed of step k+1)
+    else:
+        step_ids = ids[-(len(ids) // steps):]
+    last = [allk[i] for i in step_ids if re.search(pattern, allk[i]["k"])]
+    n = len(last)
     rd = sum(d.get("dram__bytes_read.sum", 0.0) for d in last)
     wr = sum(d.get("dram__bytes_write.sum", 0.0) for d in last)
     ns = sum(d.get("gpu__time_duration.sum", 0.0) for d in last)
