@@ -197,9 +197,6 @@ int step_tc_qkv(const void *x_img, const void *w_img, const float *bias, int S, 
  * two-pass row maximum.  Both are the same softmax up to bf16 rounding of the probabilities. */
 int step_tc_attention(const void *q_img, const void *k_img, const void *v_img, void *o_img, const float *bound, int S, int P,
                       float drop_p, unsigned long long seed, void *stream);
-/* Profiling aid: step_tc_attention with clock64 stamps of CTA 0 ([trace_iters][3 roles][8] int64, see tools/attn_trace.py). */
-int step_tc_attention_trace(const void *q_img, const void *k_img, const void *v_img, void *o_img, const float *bound, int S, int P,
-                            float drop_p, unsigned long long seed, long long *trace, int trace_iters, void *stream);
 size_t step_ts_encoder_bf16_workspace_bytes(int B, int N, int P);
 /* Whole encoder in bf16: series -> hidden [B,N,P,96] fp32 (same contract as step_ts_encoder_fwd). */
 int step_ts_encoder_fwd_bf16(const float *series, long long sB, long long sT, long long sN, int B, int N, int P,

@@ -65,28 +65,6 @@ __device__ __forceinline__ uint32_t keep_mask_bf16x2(uint32_t r, uint32_t thr2) 
   asm("set.ge.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(r), "r"(thr2));
   return m;
 }
-// volatile building blocks of the hand-scheduled softmax pipeline: ptxas keeps volatile asm statements in source order
-__device__ __forceinline__ void v_ex2(float &x) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x)); }
-__device__ __forceinline__ void v_fadd2(float &a0, float &a1, float b0, float b1) {
-  asm volatile("{\n\t.reg .b64 ra, rb;\n\t"
-               "mov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\t"
-               "add.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
-               : "+f"(a0), "+f"(a1)
-               : "f"(b0), "f"(b1));
-}
-__device__ __forceinline__ void v_pack(uint32_t &w, float lo, float hi) {
-  asm volatile("cvt.rn.bf16x2.f32 %0, %2, %1;" : "=r"(w) : "f"(lo), "f"(hi));
-}
-__device__ __forceinline__ void v_lcg(uint32_t &st, uint32_t cadd) {
-  asm volatile("mad.lo.u32 %0, %0, 2891336453, %1;" : "+r"(st) : "r"(cadd));
-}
-__device__ __forceinline__ void v_set(uint32_t &m, uint32_t st, uint32_t thr2) {
-  asm volatile("set.ge.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(st), "r"(thr2));
-}
-__device__ __forceinline__ void v_and(uint32_t &w, uint32_t m) { asm volatile("and.b32 %0, %0, %1;" : "+r"(w) : "r"(m)); }
-__device__ __forceinline__ void v_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 // Placement of a (head, row tile) in the 128 TMEM lanes: a last tile of <= 64 queries sits at lanes 64.. for odd heads, so
 // that the partial tiles of consecutive heads are exponentiated by warps of different SM sub-partitions.
 __host__ __device__ __forceinline__ int q_tail_offset(int P, int rt, int h) {
@@ -525,30 +503,21 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) tc_linear_kernel(TcLinearArgs 
 //   S = Q K^T   (M=128, N=Pk, K=32: head dim 24 padded with a shared zero chunk in smem)
 //   P = softmax rows (fp32 statistics read from TMEM, exp2 domain), written as a bf16 K-major image in smem
 //   O = P V     (M=128, N=32, K=Pk; V is the MN-major B operand)
-// Warp roles: warp 0 TMA producer, warps 2-5 and 6-9 two softmax groups that take alternate iterations with private
-// S/O accumulators in TMEM and private P images (ping-pong), warp 1 and warp 10 one MMA-issuing thread per group: while
-// one group exponentiates, the tensor core computes the other group's S and P.V.
-// Softmax: one pass over the scores against an upper bound of the row maximum (|q_i| max_j |k_j| from the QKV epilogue,
-// exact two-pass fall-back when the bound is large), p = ex2(s - m) with packed fp32 adds, dropout as bf16x2 compares
-// on the packed probabilities; P.V starts on the first 96 keys while the rest is still being exponentiated.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 and 6-9 two softmax groups that take
+// alternate iterations with private S/O accumulators in TMEM and private P images (ping-pong): while one
+// group exponentiates, the tensor core computes the other group's S and P.V.
 // ===========================================================================
 struct TcAttnArgs {
   const uint8_t *q_img, *k_img, *v_img;
   uint8_t *o_img;
   const float *bound;      // [S*4] max_j |k_j| (as uint bits) then [S*4][P] |q_i| of the bf16 operands; null -> exact row maxima
-  long long *trace;        // profiling aid (null in production): clock64 stamps of CTA 0, [iteration][3 roles][8]
-  int trace_iters;
-  int khalf;               // P.V key steps issued at half time (0 = all after the softmax)
-  int stagger;             // group 1's S is issued when group 0 is half through the same head
   int S, P, Pk, RT;
   uint32_t thr16; float dscale; uint64_t key;
 };
 
-constexpr int TCA_THREADS = 352;   // warp 0 TMA, warp 1 / warp 10 MMA issuers (one per softmax group), warps 2-5 / 6-9 the groups
-constexpr int TCA_ISSUER2 = 10;
+constexpr int TCA_THREADS = 320;
 constexpr int TCA_QBUF = 4, TCA_KVBUF = 3;
 constexpr int TCA_KSPLIT = 176, TCA_KVBUF_SPLIT = 2, TCA_XROW = 27;   // key-split mode (P > 176)
-constexpr int TCA_KHALF = 6;                                           // P = 168: P.V key steps (of 16) issued at half time
 
 // PF > 0: sequence length known at compile time (168 for every 2016-step STEP config) -> unrolled column loops
 // without bounds predicates; DROP: attention-probability dropout compiled in or out.
@@ -576,19 +545,14 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
   uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * PB + (SPLIT ? 2 * 128 * TCA_XROW * 4 : 0));
   uint64_t *q_full = bars, *q_empty = bars + 4, *kv_full = bars + 8, *kv_empty = bars + 11;
   uint64_t *s_full = bars + 14, *s_empty = bars + 16, *p_ready = bars + 18, *o_full = bars + 20, *o_empty = bars + 22;
-  uint64_t *p_half = bars + 24;                // first TCA_KHALF key steps of P published (PF == 168 route)
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 26);
-  // pacing only (no data behind it): number of tiles group 0 has exponentiated half-way.  Group 1's S = Q K^T is issued
-  // when group 0 is half through the same head, so the two groups' MUFU-bound phases interleave instead of colliding.
-  volatile uint32_t *halfcnt = reinterpret_cast<volatile uint32_t *>(bars + 27);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    *halfcnt = 0u;
     for (int i = 0; i < TCA_QBUF; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-    for (int i = 0; i < KVBUFS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], SPLIT ? 1 : RT); }
+    for (int i = 0; i < KVBUFS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int g = 0; g < 2; ++g) {
-      mbar_init(&s_full[g], 1); mbar_init(&s_empty[g], 4); mbar_init(&p_ready[g], 4); mbar_init(&p_half[g], 4);
+      mbar_init(&s_full[g], 1); mbar_init(&s_empty[g], 4); mbar_init(&p_ready[g], 4);
       mbar_init(&o_full[g], 1); mbar_init(&o_empty[g], 4);
     }
     fence_barrier_init();
@@ -621,8 +585,8 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
         tma_bulk_g2s(sQ + qb * 6144, a.q_img + (((size_t)seq * 4 + h) * RT + rt) * 6144, 6144, &q_full[qb]);
       }
     }
-  } else if (warp == 1 || warp == TCA_ISSUER2) {
-    if (lane == 0 && (warp == 1 || !SPLIT)) {
+  } else if (warp == 1) {
+    if (lane == 0) {
       const uint32_t idesc_o = umma_idesc_bf16(128, 32, 0, 1);
       const uint32_t zaddr = smem_u32(sZ);
       if (SPLIT) {
@@ -665,46 +629,15 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
           }
         }
       } else {
-      // one issuer thread per softmax group (warp 1 -> group 0, warp TCA_ISSUER2 -> group 1): a single thread serving both
-      // groups was the kernel's critical path (~3000 cycles of waits, descriptor arithmetic and issue per iteration)
-      const int g = (warp == 1) ? 0 : 1;
       const uint32_t idesc_s = umma_idesc_bf16(128, Pk, 0, 0);
-      const uint32_t ts = tmem + g * 256, to = ts + 192;
-      const uint64_t pdesc = umma_desc(smem_u32(sP + g * PB), 2048, 128);
-      const int KH = (PF == 168) ? a.khalf : 0;
-      for (int i = g; i < NIT + 2; i += 2) {
-        if (i >= 2) {
-          // O = P V of this group's previous tile; starts on the first KH key steps while the group still exponentiates
-          const int ip = i - 2, u = ip >> 1, kvb = (ip / RT) % TCA_KVBUF;
-          const bool tr = a.trace != nullptr && blockIdx.x == 0 && ip < a.trace_iters;
-          if (tr) a.trace[((size_t)ip * 3 + 2) * 8 + 3] = clock64();
-          const uint64_t vdesc = umma_desc(smem_u32(sV + kvb * KVB), 128, Pk * 16);
-          mbar_wait(&p_half[g], u & 1);
-          mbar_wait(&o_empty[g], (u & 1) ^ 1);
-          tc_fence_after();
-          for (int kk = 0; kk < KH; ++kk) umma_bf16(to, pdesc + (uint64_t)kk * 256, vdesc + (uint64_t)kk * 16, idesc_o, kk != 0 ? 1u : 0u);
-          mbar_wait(&p_ready[g], u & 1);
-          tc_fence_after();
-          if (tr) a.trace[((size_t)ip * 3 + 2) * 8 + 4] = clock64();
-          for (int kk = KH; kk < Pk / 16; ++kk) umma_bf16(to, pdesc + (uint64_t)kk * 256, vdesc + (uint64_t)kk * 16, idesc_o, kk != 0 ? 1u : 0u);
-          umma_commit(&o_full[g]);
-          umma_commit(&kv_empty[kvb]);          // RT arrivals (one per row tile of the head) free the K/V buffer
-        }
-        if (i < NIT) {
-          const int u = i >> 1, hi = i / RT, kvb = hi % TCA_KVBUF, qb = i & 3;
-          const bool tr = a.trace != nullptr && blockIdx.x == 0 && i < a.trace_iters;
-          if (tr) a.trace[((size_t)i * 3 + 2) * 8 + 0] = clock64();
-          mbar_wait(&kv_full[kvb], (hi / TCA_KVBUF) & 1);
+      for (int j = 0; j <= NIT; ++j) {
+        if (j < NIT) {
+          const int i = j, g = i & 1, u = i >> 1, rt = (i % per_seq) % RT, hi = i / RT, kvb = hi % TCA_KVBUF, qb = i & 3;
+          if (rt == 0) mbar_wait(&kv_full[kvb], (hi / TCA_KVBUF) & 1);
           mbar_wait(&q_full[qb], (i >> 2) & 1);
-          if (tr) a.trace[((size_t)i * 3 + 2) * 8 + 1] = clock64();
           mbar_wait(&s_empty[g], (u & 1) ^ 1);
-          if (PF == 168 && g == 1 && a.stagger) {
-            uint32_t spins = 0;
-            while (*halfcnt < (uint32_t)u + 1u) { if (++spins > (1u << 28)) asm volatile("trap;"); }
-          }
           tc_fence_after();
-          if (tr) a.trace[((size_t)i * 3 + 2) * 8 + 2] = clock64();
-          const uint32_t qa = smem_u32(sQ + qb * 6144), ka = smem_u32(sK + kvb * KVB);
+          const uint32_t qa = smem_u32(sQ + qb * 6144), ka = smem_u32(sK + kvb * KVB), ts = tmem + g * 256;
           // k-step 0: head dims 0..15 (chunks 0,1); k-step 1: dims 16..23 + the shared zero chunk
           umma_bf16(ts, umma_desc(qa, 2048, 128), umma_desc(ka, Pk * 16, 128), idesc_s, 0u);
           umma_bf16(ts, umma_desc(qa + 2 * 2048, zaddr - (qa + 2 * 2048), 128),
@@ -712,10 +645,22 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
           umma_commit(&s_full[g]);
           umma_commit(&q_empty[qb]);
         }
+        if (j >= 1) {
+          const int i = j - 1, g = i & 1, u = i >> 1, rt = (i % per_seq) % RT, hi = i / RT, kvb = hi % TCA_KVBUF;
+          mbar_wait(&p_ready[g], u & 1);
+          mbar_wait(&o_empty[g], (u & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t pa = smem_u32(sP + g * PB), va = smem_u32(sV + kvb * KVB), to = tmem + g * 256 + 192;
+          for (int kk = 0; kk < Pk / 16; ++kk)
+            umma_bf16(to, umma_desc(pa + kk * 2 * 2048, 2048, 128), umma_desc(va + kk * 256, 128, Pk * 16), idesc_o,
+                      kk != 0 ? 1u : 0u);
+          umma_commit(&o_full[g]);
+          if (rt == RT - 1) umma_commit(&kv_empty[kvb]);
+        }
       }
       }
     }
-  } else if (warp < TCA_ISSUER2) {
+  } else {
     const int q = warp & 3, g = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -735,10 +680,8 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       if (qnorm == nullptr || it >= NIT) return;
       const int seq = blockIdx.x + (it / per_seq) * gridDim.x, w = it % per_seq, h = w / RT, rt = w % RT;
       const int lrow = row - q_tail_offset(P, rt, h);
-      // volatile asm: the loads must issue HERE (one iteration early), not be sunk to their use
-      if (lrow >= 0 && lrow < min(128, P - rt * 128))
-        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(qn) : "l"(qnorm + ((size_t)seq * 4 + h) * P + rt * 128 + lrow));
-      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(km) : "l"(kmax + (size_t)seq * 4 + h));
+      if (lrow >= 0 && lrow < min(128, P - rt * 128)) qn = __ldg(qnorm + ((size_t)seq * 4 + h) * P + rt * 128 + lrow);
+      km = __uint_as_float(__ldg(kmax + (size_t)seq * 4 + h));
     };
     float qn_next, km_next;
     load_bound(SPLIT ? 0 : g, qn_next, km_next);
@@ -750,6 +693,8 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       const int lrow = row - roff;                       // query index inside the row tile
       const bool warp_active = q * 32 + 32 > roff && q * 32 < roff + rows_valid;
       const bool row_valid = lrow >= 0 && lrow < rows_valid;
+      const float qn = qn_next, km = km_next;
+      load_bound(i + (SPLIT ? 1 : 2), qn_next, km_next);
       // Upper bound of the row maximum without reading the scores (Cauchy-Schwarz on the bf16 operands, written by the
       // QKV epilogue): s_ij <= |q_i| max_j |k_j|.  Softmax is shift invariant, so any m >= max works as long as
       // 2^(s - m) stays representable: with m_b <= 40 every s - m_b lies in [-80, 0].  Rows with a larger bound (never
@@ -757,21 +702,13 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       float mb = 0.f;
       bool bounded = false;
       if (qnorm != nullptr && warp_active) {
-        mb = fmaf(qn_next * km_next, 1.01f, 1e-3f);
+        mb = fmaf(qn * km, 1.01f, 1e-3f);
         bounded = !__any_sync(0xffffffffu, !(mb <= 40.f));
       }
-      // consume this iteration's norms (above) BEFORE issuing the next iteration's loads: the scoreboard wait of the
-      // consumer would otherwise also cover the newly issued loads and expose their full latency
-      load_bound(i + (SPLIT ? 1 : 2), qn_next, km_next);
-      const bool tr = a.trace != nullptr && blockIdx.x == 0 && i < a.trace_iters && lane == 0 && q == (roff ? 2 : 0);
-      long long *trp = tr ? a.trace + ((size_t)i * 3 + g) * 8 : nullptr;
-      if (tr) trp[0] = clock64();
       mbar_wait(&s_full[g], u & 1);
       tc_fence_after();
-      if (tr) trp[1] = clock64();
       // V rows of the padded keys must be finite zeros (P is 0 there, but 0 * NaN = NaN)
-      // (every tile in the alternating mode: the two groups' P.V of one head are issued independently)
-      if (q == 2 && (SPLIT ? (rt == 0 && g == 1) : true)) {
+      if (rt == 0 && q == 2 && (!SPLIT || g == 1)) {
         const int npad = Pk - P, kvb = (i / RT) % KVBUFS;
         for (int jz = lane; jz < npad * 3; jz += 32) {
           const int gg = jz / npad, rr = P + jz % npad;
@@ -779,7 +716,6 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
         }
       }
       float m = -INFINITY, l = 0.f;
-      bool half_done = false;
       if (warp_active) {
         // Full 32-column blocks run unpredicated; only the tail block (columns [c_tail, P), then zero fill up to Pk)
         // carries per-element predicates.
@@ -823,64 +759,24 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
         uint4 *prow = reinterpret_cast<uint4 *>(myP) + row;
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
         if (PF > 0) {
-          // compile-time sequence length (168 / 336): five full 32-column blocks per group, hand-scheduled software
-          // pipeline over three register buffers: while block k is summed / packed / masked / stored (stage B), block
-          // k+1 is exponentiated (stage A) and block k+2 is in flight from TMEM.  Stage A and B alternate pair by pair
-          // in volatile asm, so the MUFU.EX2 of this warp issue ~4 instructions apart instead of in bursts that stall
-          // the warp on the 4-lane/clk XU pipe (ptxas clusters them otherwise: measured 2700 cycles per row block
-          // against the 1344-cycle MUFU floor).
+          // compile-time sequence length (168 / 336): five full blocks per group, the load of block k+1 in flight
+          // while block k is exponentiated (two register buffers)
           constexpr int NBLK = 5;
-          {
-          float t[3][32];
-          tmem_ld32_issue(TM_S + lane_base, t[0]);
-          tmem_wait_ld32(t[0]);
-          tmem_ld32_issue(TM_S + lane_base + 32, t[1]);
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            v_fadd2(t[0][c], t[0][c + 1], negm, negm);
-            v_ex2(t[0][c]); v_ex2(t[0][c + 1]);
-          }
+          float ta[32], tb[32];
+          tmem_ld32_issue(TM_S + lane_base, ta);
 #pragma unroll
           for (int k = 0; k < NBLK; ++k) {
-            float (&E)[32] = t[k % 3];
-            float (&R)[32] = t[(k + 1) % 3];
-            const bool more = k + 1 < NBLK;
-            if (more) {
-              tmem_wait_ld32(R);
-              if (k + 2 < NBLK) tmem_ld32_issue(TM_S + lane_base + (k + 2) * 32, t[(k + 2) % 3]);
-              v_fadd2(R[0], R[1], negm, negm);
+            if ((k & 1) == 0) {
+              tmem_wait_ld32(ta);
+              if (k + 1 < NBLK) tmem_ld32_issue(TM_S + lane_base + (k + 1) * 32, tb);
+              softmax_cols<32, DROP, false>(ta, negm, 32, 4, l0, l1, l2, l3, DROP ? hash32((ctr + k) ^ salt) : 0u, cadd, thr2,
+                                            prow + (size_t)(k * 4) * 128);
+            } else {
+              tmem_wait_ld32(tb);
+              if (k + 1 < NBLK) tmem_ld32_issue(TM_S + lane_base + (k + 1) * 32, ta);
+              softmax_cols<32, DROP, false>(tb, negm, 32, 4, l0, l1, l2, l3, DROP ? hash32((ctr + k) ^ salt) : 0u, cadd, thr2,
+                                            prow + (size_t)(k * 4) * 128);
             }
-            // Every dependent pair of instructions sits one pipeline step (~9 instructions) apart: the LCG state of pair
-            // p+1, the keep mask of pair p and the AND on the packed pair p-1 are issued in the same step.
-            uint32_t st = DROP ? hash32((ctr + k) ^ salt) : 0u;
-            if (DROP) v_lcg(st, cadd);
-            const uint32_t dst = smem_u32(prow + (size_t)(k * 4) * 128);
-            uint32_t w[8], m_prev = 0u;
-#pragma unroll
-            for (int pp = 0; pp < 16; ++pp) {
-              uint32_t st_next = st, m_cur = 0u;
-              if (more) v_ex2(R[2 * pp]);
-              if ((pp & 1) == 0) v_fadd2(l0, l1, E[2 * pp], E[2 * pp + 1]); else v_fadd2(l2, l3, E[2 * pp], E[2 * pp + 1]);
-              if (DROP) v_lcg(st_next, cadd);
-              v_pack(w[pp & 7], E[2 * pp], E[2 * pp + 1]);
-              if (more) v_ex2(R[2 * pp + 1]);
-              if (DROP) v_set(m_cur, st, thr2);
-              if (DROP && pp > 0) v_and(w[(pp - 1) & 7], m_prev);
-              if (more && pp + 1 < 16) v_fadd2(R[2 * pp + 2], R[2 * pp + 3], negm, negm);
-              if (pp > 0 && (pp & 3) == 0)
-                v_sts128(dst + (uint32_t)((pp >> 2) - 1) * 2048u, w[(pp - 4) & 7], w[(pp - 3) & 7], w[(pp - 2) & 7], w[(pp - 1) & 7]);
-              m_prev = m_cur; st = st_next;
-            }
-            if (DROP) v_and(w[7], m_prev);
-            v_sts128(dst + 3u * 2048u, w[4], w[5], w[6], w[7]);
-            if (!SPLIT && PF == 168 && k == TCA_KHALF / 2 - 1) {      // columns [0, 16 TCA_KHALF) of P are in shared memory
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&p_half[g]);
-              if (g == 0 && q == 0 && lane == 0) *halfcnt = (uint32_t)u + 1u;
-              half_done = true;
-            }
-          }
           }
           if (NBLK * 32 < Pkl) {                          // 16-column tail: PF = 168 (8 valid), group 0 of PF = 336 (16 valid)
             float t16[16];
@@ -919,12 +815,10 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&s_empty[g]); if (!half_done) mbar_arrive(&p_half[g]); mbar_arrive(&p_ready[g]); }
-      if (tr) trp[2] = clock64();
+      if (lane == 0) { mbar_arrive(&s_empty[g]); mbar_arrive(&p_ready[g]); }
       // epilogue: O / l  -> O tile image (token-tile format of the following out-projection GEMM)
       mbar_wait(&o_full[g], u & 1);
       tc_fence_after();
-      if (tr) trp[3] = clock64();
       float o[32];
       if (warp_active) tmem_ld32(TM_O + lane_base, o);
       tc_fence_before();
@@ -963,7 +857,6 @@ __global__ void __launch_bounds__(TCA_THREADS, 1) tc_attn_kernel(TcAttnArgs a) {
           dst[cc * 128] = pack8_bf16(x8);
         }
       }
-      if (tr) trp[4] = clock64();
     }
   }
   tc_fence_before();
@@ -1804,20 +1697,10 @@ extern "C" int step_tc_qkv(const void *x_img, const void *w_img, const float *bi
   return tc_linear_launch(a, (cudaStream_t)stream);
 }
 
-static long long *g_attn_trace = nullptr;     // set only inside step_tc_attention_trace
-static int g_attn_trace_iters = 0;
-
 static int tc_attn_launch(const void *q_img, const void *k_img, const void *v_img, void *o_img, const float *bound, int S, int P,
                           float drop_p, uint64_t seed, uint32_t site, cudaStream_t st) {
   TcAttnArgs a{};
-  a.bound = bound; a.trace = g_attn_trace; a.trace_iters = g_attn_trace_iters;
-  {
-    // A/B switches of the P = 168 route (profiles/r02_attention.md); the defaults are the measured best combination
-    const char *e;
-    a.khalf = (e = getenv("STEP_B200_ATTN_KHALF")) ? atoi(e) : TCA_KHALF;
-    a.stagger = (e = getenv("STEP_B200_ATTN_STAGGER")) ? atoi(e) : 1;
-    if (a.khalf != 0) a.khalf = TCA_KHALF;
-  }
+  a.bound = bound;
   a.q_img = (const uint8_t *)q_img; a.k_img = (const uint8_t *)k_img; a.v_img = (const uint8_t *)v_img; a.o_img = (uint8_t *)o_img;
   a.S = S; a.P = P; a.Pk = (P + 15) / 16 * 16; a.RT = (P + 127) / 128;
   if (a.Pk > 2 * TCA_KSPLIT) return fail(STEP_EUNSUPPORTED, "tc_attention: P=%lld > 352 is served by the fp32 path", P);
@@ -1846,19 +1729,6 @@ extern "C" int step_tc_attention(const void *q_img, const void *k_img, const voi
                                  int P, float drop_p, unsigned long long seed, void *stream) {
   STEP_REQUIRE(q_img && k_img && v_img && o_img && S > 0 && P > 0, "tc_attention: bad argument");
   return tc_attn_launch(q_img, k_img, v_img, o_img, bound, S, P, drop_p, seed, 0, (cudaStream_t)stream);
-}
-
-// Profiling aid: the same launch with clock64 stamps of CTA 0 written to `trace` ([trace_iters][3][8] int64: roles 0 / 1 = the two
-// softmax groups {wait S, S ready, P published, O ready, tile stored}, role 2 = the MMA issuer {enter, Q/K/V landed, S slot free,
-// (previous tile) enter PV, P ready}).  tools/attn_trace.py prints the timeline.
-extern "C" int step_tc_attention_trace(const void *q_img, const void *k_img, const void *v_img, void *o_img, const float *bound,
-                                       int S, int P, float drop_p, unsigned long long seed, long long *trace, int trace_iters,
-                                       void *stream) {
-  STEP_REQUIRE(q_img && k_img && v_img && o_img && trace && trace_iters > 0 && S > 0 && P > 0, "tc_attention_trace: bad argument");
-  g_attn_trace = trace; g_attn_trace_iters = trace_iters;
-  const int rc = tc_attn_launch(q_img, k_img, v_img, o_img, bound, S, P, drop_p, seed, 0, (cudaStream_t)stream);
-  g_attn_trace = nullptr; g_attn_trace_iters = 0;
-  return rc;
 }
 
 extern "C" size_t step_tc_seq_image_bytes(int B, int N, int P) {

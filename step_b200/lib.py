@@ -68,7 +68,6 @@ SIGNATURES = {
     "step_tc_attn_image_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "step_tc_qkv": (C.c_int, [vp, vp, f32p, C.c_int, C.c_int, vp, vp, vp, f32p, vp]),
     "step_tc_attention": (C.c_int, [vp, vp, vp, vp, f32p, C.c_int, C.c_int, C.c_float, ull, vp]),
-    "step_tc_attention_trace": (C.c_int, [vp, vp, vp, vp, f32p, C.c_int, C.c_int, C.c_float, ull, vp, C.c_int, vp]),
     "step_ts_encoder_bf16_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "step_ts_encoder_fwd_bf16": (C.c_int, [f32p, ll, ll, ll, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p,
                                            C.POINTER(TsLayerWeights), C.POINTER(TsLayerImages), C.c_int, f32p, f32p, f32p, vp, vp,
