@@ -652,12 +652,19 @@ extern "C" int step_dgl_conv_bwd(const float *dy2n, const float *x, int N, int L
   STEP_LAUNCH_CHECK("trunk_bn_bwd_stats_kernel");
   trunk_bn_bwd_finalize_kernel<<<1, 32, 0, st>>>(sums + 16, (double)N * d.L2, C2, g2, bn2_stats, eps, coef2, dg2, dbe2);
   STEP_LAUNCH_CHECK("trunk_bn_bwd_finalize_kernel");
-  int rc = allow_smem(trunk_conv2_bwd_kernel, conv2_bwd_smem());
-  if (rc) return rc;
-  const int gx = wave_aware_ctas(trunk_conv2_bwd_kernel, conv2_bwd_smem(), (d.L1 + TLB - 1) / TLB, N, 8);
-  trunk_conv2_bwd_kernel<<<dim3(gx, N), 256, conv2_bwd_smem(), st>>>(x, d, w1, b1, bn1_stats, eps, w2, dy2n, y2,
-                                                                    coef2, dy1n_scratch, dw2, db2, sums);
-  STEP_LAUNCH_CHECK("trunk_conv2_bwd_kernel");
+  int rc;
+  if (trunk_use_tc()) {
+    TcConv2BwdArgs t{};
+    t.x = x; t.w1 = w1; t.b1 = b1; t.bn1 = bn1_stats; t.eps = eps; t.w2 = w2; t.dy2n = dy2n; t.y2 = y2; t.coef2 = coef2;
+    t.dy1n = dy1n_scratch; t.dw2 = dw2; t.db2 = db2; t.sums1 = sums; t.N = N; t.L0 = L0; t.L1 = d.L1; t.L2 = d.L2;
+    if ((rc = trunk_conv2_tc_bwd_launch(t, st))) return rc;
+  } else {
+    if ((rc = allow_smem(trunk_conv2_bwd_kernel, conv2_bwd_smem()))) return rc;
+    const int gx = wave_aware_ctas(trunk_conv2_bwd_kernel, conv2_bwd_smem(), (d.L1 + TLB - 1) / TLB, N, 8);
+    trunk_conv2_bwd_kernel<<<dim3(gx, N), 256, conv2_bwd_smem(), st>>>(x, d, w1, b1, bn1_stats, eps, w2, dy2n, y2,
+                                                                      coef2, dy1n_scratch, dw2, db2, sums);
+    STEP_LAUNCH_CHECK("trunk_conv2_bwd_kernel");
+  }
   trunk_bn_bwd_finalize_kernel<<<1, 32, 0, st>>>(sums, (double)N * d.L1, C1, g1, bn1_stats, eps, coef1, dg1, dbe1);
   STEP_LAUNCH_CHECK("trunk_bn_bwd_finalize_kernel");
   trunk_conv1_bwd_kernel<<<dim3(wave_aware_ctas(trunk_conv1_bwd_kernel, 0, (d.L1 + 1023) / 1024, N, 6), N), 256, 0, st>>>(
