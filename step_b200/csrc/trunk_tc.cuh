@@ -230,6 +230,8 @@ inline int trunk_conv2_tc_launch(const TcConv2Args &a0, cudaStream_t st) {
 // Same pipeline as the forward: warp 1 issues, warps 2-9 build the planes of tile t+1 and run the d(y1n) epilogue of tile t-1.
 // ===========================================================================
 constexpr uint32_t TCV_WBIMG = 20 * 16 * 16;     // bytes of one re-ordered w2 image of the backward
+constexpr int TCVB_WORKERS = 512;                // 16 plane-builder / epilogue warps (the kernel is bound by their load latency)
+constexpr int TCVB_THREADS = TCVB_WORKERS + 64;
 
 struct TcConv2BwdArgs {
   const float *x, *w1, *b1, *bn1;   // bn1 [4][8]: mean, var, scale, shift
@@ -245,7 +247,7 @@ struct TcConv2BwdArgs {
 
 static size_t tcvb_smem_bytes() { return 2 * 6 * (size_t)TCV_PLANE + 2 * (size_t)TCV_WBIMG + 16 * 8 + (80 + 8 * 5 + 16 * 5) * 4 + 64; }
 
-__global__ void __launch_bounds__(TCV_THREADS, 1) trunk_conv2_tc_bwd_kernel(TcConv2BwdArgs a) {
+__global__ void __launch_bounds__(TCVB_THREADS, 1) trunk_conv2_tc_bwd_kernel(TcConv2BwdArgs a) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t tcvb_smem[];
   // stage layout: [dp hi h0][dp hi h1][dp lo h0][dp lo h1][y1n hi][y1n lo], TCV_PLANE bytes each
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(TCV_THREADS, 1) trunk_conv2_tc_bwd_kernel(TcCo
     reinterpret_cast<uint4 *>(sWl)[i] = pack8_bf16(lo);
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&built[i], 8); mbar_init(&consumed[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&built[i], TCVB_WORKERS / 32); mbar_init(&consumed[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], TCVB_WORKERS / 32); }
     mbar_init(dw_full, 1);
     fence_barrier_init();
   }
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(TCV_THREADS, 1) trunk_conv2_tc_bwd_kernel(TcCo
       umma_commit(dw_full);
     }
   } else if (warp >= 2) {
-    const int wt = threadIdx.x - 64;                 // 0..255
+    const int wt = threadIdx.x - 64;                 // 0..TCVB_WORKERS-1
     const int q = warp & 3, grp = (warp - 2) >> 2;
     float s1acc[8], s2acc[8], dbacc[16];
 #pragma unroll
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(TCV_THREADS, 1) trunk_conv2_tc_bwd_kernel(TcCo
       uint4 *pl = reinterpret_cast<uint4 *>(sPl + (size_t)s * 6 * TCV_PLANE);
       const float *xr = a.x + (size_t)n * a.L0;
       const size_t nb = (size_t)n * 16 * a.L2;
-      for (int r = wt; r < TCV_ROWS; r += 256) {
+      for (int r = wt; r < TCV_ROWS; r += TCVB_WORKERS) {
         // ---- dpre2 at l = t0 - 16 + r ----
         const int l = t0 - 16 + r;
         float hi[16], lo[16];
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(TCV_THREADS, 1) trunk_conv2_tc_bwd_kernel(TcCo
       tc_fence_after();
       const float *xr = a.x + (size_t)n * a.L0;
       float *o = a.dy1n + (size_t)n * 8 * a.L1;
-      for (int rt = grp; rt < TCV_TP / 128; rt += 2) {
+      for (int rt = grp; rt < TCV_TP / 128; rt += TCVB_WORKERS / 128) {
         float v[16];
         tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + s * 128 + rt * 16, v);
         const int p = t0 + rt * 128 + q * 32 + lane;
@@ -456,7 +458,7 @@ __global__ void __launch_bounds__(TCV_THREADS, 1) trunk_conv2_tc_bwd_kernel(TcCo
         for (int co = 0; co < 16; ++co) atomicAdd(a.dw2 + (co * 8 + ci) * 10 + tap, v[co]);
       }
     }
-    float *red = reinterpret_cast<float *>(sPl);               // [8 warps][32]: 16 db2 + 8 s1 + 8 s2
+    float *red = reinterpret_cast<float *>(sPl);               // [worker warps][32]: 16 db2 + 8 s1 + 8 s2
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
       const float t = warp_sum(dbacc[c]);
@@ -467,11 +469,11 @@ __global__ void __launch_bounds__(TCV_THREADS, 1) trunk_conv2_tc_bwd_kernel(TcCo
       const float t1 = warp_sum(s1acc[c]), t2 = warp_sum(s2acc[c]);
       if (lane == 0) { red[(warp - 2) * 32 + 16 + c] = t1; red[(warp - 2) * 32 + 24 + c] = t2; }
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(TCVB_WORKERS) : "memory");
     if (warp == 2) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += red[w * 32 + lane];
+      for (int w = 0; w < TCVB_WORKERS / 32; ++w) t += red[w * 32 + lane];
       if (lane < 16) atomicAdd(a.db2 + lane, t);
       else atomicAdd(a.sums1 + (lane - 16), (double)t);
     }
@@ -491,7 +493,7 @@ inline int trunk_conv2_tc_bwd_launch(const TcConv2BwdArgs &a0, cudaStream_t st) 
   if ((rc = allow_smem(trunk_conv2_tc_bwd_kernel, smem))) return rc;
   const long long total = (long long)a.N * a.tiles_per_node;
   const int grid = (int)(total < (long long)sms ? total : (long long)sms);
-  trunk_conv2_tc_bwd_kernel<<<grid, TCV_THREADS, smem, st>>>(a);
+  trunk_conv2_tc_bwd_kernel<<<grid, TCVB_THREADS, smem, st>>>(a);
   return check_launch("trunk_conv2_tc_bwd_kernel");
 }
 
