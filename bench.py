@@ -491,7 +491,8 @@ def rooflines(arm, args, pk):
     other = [{"kernel": "TSFormer encoder, 21 launches (tc_embed + 4 x [QKV, attention, out+LN1, FFN1, FFN2+LN2])"
               if args.precision == "bf16" else "TSFormer encoder, fp32 CUDA-core kernels",
               "bound": "tensor", "achieved": enc_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-              "frac": enc_tflops / pk["bf16_tflops"], "ms": enc_ms, "useful_flops": enc_flops}]
+              "frac": enc_tflops / pk["bf16_tflops"], "ms": enc_ms, "useful_flops": enc_flops,
+              "traffic": profile_traffic("r02_ncu_encoder_total.txt") if arm.ds == "METR-LA" and B == 32 and args.precision == "bf16" else None}]
     roofline = None
     if args.precision == "bf16":
         L = ops._L()
@@ -573,11 +574,12 @@ def rooflines(arm, args, pk):
                   "useful_flops": 6.0 * N * 100 * K})
     L0 = dgl.train_length
     conv_flops = 3.0 * 2.0 * N * (8 * 10 * (L0 - 9) + 16 * 80 * (L0 - 18))
-    other.append({"kernel": "D1 whole trunk fwd+bwd (conv1/bn1/conv2/bn2 CUDA-core kernels + the fc group above)", "bound": "hbm",
+    other.append({"kernel": "D1 whole trunk fwd+bwd (conv1 / BatchNorm kernels, conv2 fwd+bwd as in-place implicit GEMMs on tcgen05, + the fc group above)", "bound": "hbm",
                   "achieved": (fc_bytes + 4.0 * N * 16 * (L0 - 18) * 4.0) / (d1_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                   "unit": "GB/s", "frac": (fc_bytes + 4.0 * N * 16 * (L0 - 18) * 4.0) / (d1_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                   "ms": d1_ms, "algorithmic_bytes": fc_bytes + 4.0 * N * 16 * (L0 - 18) * 4.0,
                   "useful_flops": conv_flops + 6.0 * N * 100 * K,
+                  "traffic": profile_traffic("r02_ncu_trunk_total.txt") if arm.ds == "METR-LA" else None,
                   "note": "conv trunk bytes = y2 and y2n written in forward, read in backward (y1 is recomputed)"})
     del y2n, fcw
 
@@ -615,8 +617,8 @@ def rooflines(arm, args, pk):
     skip_b = 2.0 * B * N * 256 * 4
     g2_fwd_bytes = act + sup + B * N * 256 * 4.0
     g2_all_bytes = 2 * act + 2 * sup + 2 * stash + skip_b
-    other.append({"kernel": "G2 GWNet stack forward (step_gwnet_stack_fwd: 8 x [gated conv, node mixes, channel mix, BN stats] "
-                            "+ skip conv)", "bound": "hbm", "achieved": g2_fwd_bytes / (gw_fwd_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+    other.append({"kernel": "G2 GWNet stack forward (step_gwnet_stack_fwd: one gw_fused_fwd_kernel per gcn layer [gated conv, both "
+                            "diffusion hops on tcgen05, channel mixes, BN stats] + skip conv)", "bound": "hbm", "achieved": g2_fwd_bytes / (gw_fwd_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                   "unit": "GB/s", "frac": g2_fwd_bytes / (gw_fwd_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": gw_fwd_ms,
                   "algorithmic_bytes": g2_fwd_bytes,
                   "note": "algorithmic = layer inputs+outputs (32*N*116*4 B per sample) + dense supports + skip output; "
@@ -625,7 +627,7 @@ def rooflines(arm, args, pk):
                             "estimator)", "bound": "hbm", "achieved": g2_all_bytes / (gw_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                   "unit": "GB/s", "frac": g2_all_bytes / (gw_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": gw_ms,
                   "algorithmic_bytes": g2_all_bytes, "stash_bytes": stash,
-                  "traffic": profile_traffic("r02_ncu_gw_stack_total.txt"),
+                  "traffic": profile_traffic("r02_ncu_gw_stack_total.txt") if arm.ds == "METR-LA" and B == 32 else None,
                   "note": "algorithmic = 2 x (activations + supports) + stash written and read once + skip in/out"})
     model.tsformer.node_shard = shard
     return roofline, other
