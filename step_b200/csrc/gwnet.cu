@@ -653,11 +653,15 @@ struct GwFusedArgs {
   uint32_t drop_thr; float drop_scale; uint64_t key;
 };
 
-static size_t gwf_smem_bytes(const MixGeom &g) {
-  return 2 * (size_t)(2 * 4 * 128 * g.MT * 16) + 2 * (size_t)GWF_NT * 4 * g.Kpad * 16 + (size_t)GWF_NT * g.N * GC * 4 + 7 * 1024 * 4 +
+// TCM: the seven [32 x 32] channel mixes of the gcn on tcgen05 as well (u as bf16 hi/lo A-operand images, the weight blocks
+// as B images; W_s1 u accumulates into hop A's tile and W_0 u into hop B's, a_s = W_s2 u gets a scratch tile of its own)
+static size_t gwf_smem_bytes(const MixGeom &g, bool tcm) {
+  const size_t u_bytes = tcm ? (size_t)GWF_NT * 2 * 4 * 128 * g.MT * 16 : (size_t)GWF_NT * g.N * GC * 4;
+  return 2 * (size_t)(2 * 4 * 128 * g.MT * 16) + 2 * (size_t)GWF_NT * 4 * g.Kpad * 16 + u_bytes + 7 * 1024 * 4 +
          2 * 8 * 64 * 4 + 16 * 8 + 16;
 }
 
+template <bool TCM>
 __global__ void __launch_bounds__(GWF_THREADS, 1) gw_fused_fwd_kernel(GwFusedArgs a) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t gwf_smem[];
@@ -668,12 +672,16 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) gw_fused_fwd_kernel(GwFusedArg
   const uint32_t bimg = (uint32_t)GWF_NT * 4 * g.Kpad * 16;
   uint8_t *sA = gwf_smem;
   uint8_t *sBh = sA + 2 * stage_bytes, *sBl = sBh + bimg;
-  float *sU = reinterpret_cast<float *>(sBl + bimg);                 // [nt][N][32]
-  float *sW = sU + (size_t)GWF_NT * N * GC;                           // 7 x 1024
+  float *sU = reinterpret_cast<float *>(sBl + bimg);                 // !TCM: [nt][N][32] fp32
+  uint8_t *sUimg = sBl + bimg;                                        // TCM: [t][hi, lo][4 chunks][rows][16 B]
+  const uint32_t uimg_bytes = 4 * rows * 16;                          // one (t, hi|lo) image
+  float *sW = reinterpret_cast<float *>(sBl + bimg + (TCM ? (size_t)GWF_NT * 2 * uimg_bytes : (size_t)GWF_NT * N * GC * 4));   // 7 x 1024
+  uint8_t *sWimg = reinterpret_cast<uint8_t *>(sW);                   // TCM (after the conv): [7 blocks][hi, lo][4 chunks][32 rows][16 B]
   float *sRed = sW + 7 * 1024;                                        // [2][8 warps][64]
   uint64_t *bars = reinterpret_cast<uint64_t *>(sRed + 2 * 8 * 64);
   uint64_t *full = bars, *empty = bars + 2, *b_ready = bars + 4, *acc1_full = bars + 5, *hopb_done = bars + 6;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 7);
+  uint64_t *u_ready = bars + 7, *a_full = bars + 8, *a_empty = bars + 9;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t col = (size_t)N * GC;
   const int nslices = g.Kpad / 32;
@@ -681,12 +689,13 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) gw_fused_fwd_kernel(GwFusedArg
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(b_ready, 8); mbar_init(acc1_full, 1); mbar_init(hopb_done, 1);
+    mbar_init(u_ready, 8); mbar_init(a_full, 1); mbar_init(a_empty, 8);
     fence_barrier_init();
   }
   // B-image rows of the padding nodes [N, Kpad) stay zero for the whole kernel
   for (uint32_t i = threadIdx.x; i < 2 * bimg / 16; i += blockDim.x) reinterpret_cast<uint4 *>(sBh)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) tmem_alloc(tmem_slot, TCM ? 512 : 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -719,7 +728,34 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) gw_fused_fwd_kernel(GwFusedArg
       const uint32_t bh = smem_u32(sBh), bl = smem_u32(sBl);
       const uint32_t b_sbo = (uint32_t)g.Kpad * 16, a_lbo = rows * 16;
       uint32_t n = 0, ph = 0;
+      // channel mix of block k on the tensor core: D[128 nodes of tile m, 32] (+)= U_t[128, 32] W_k^T for every (t, m)
+      const uint32_t idesc_mix = umma_idesc_bf16(128, 32, 0, 0);
+      const uint32_t uimg = smem_u32(sUimg), wimg = smem_u32(sWimg);
+      auto mix = [&](int k, uint32_t dcol, uint32_t accumulate) {
+        for (int t = 0; t < nt; ++t)
+          for (int m = 0; m < g.MT; ++m) {
+            const uint32_t uh = uimg + (uint32_t)(t * 2) * uimg_bytes + m * 2048, ul = uh + uimg_bytes;
+            const uint32_t whi = wimg + (uint32_t)(k * 2) * 2048, wlo = whi + 2048;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t dah = umma_desc(uh + kk * 2 * a_lbo, a_lbo, 128), dal = umma_desc(ul + kk * 2 * a_lbo, a_lbo, 128);
+              const uint64_t dbh = umma_desc(whi + kk * 2 * 512, 512, 128), dbl = umma_desc(wlo + kk * 2 * 512, 512, 128);
+              const uint32_t d = tmem + dcol + m * 64 + t * 32;
+              umma_bf16(d, dah, dbh, idesc_mix, (accumulate | kk) != 0 ? 1u : 0u);
+              umma_bf16(d, dah, dbl, idesc_mix, 1u);
+              umma_bf16(d, dal, dbh, idesc_mix, 1u);
+            }
+          }
+      };
+      if (TCM) { mbar_wait(u_ready, 0); tc_fence_after(); }
       for (int s = 0; s < 3; ++s) {
+        if (TCM) {
+          // a_s = W_s2 u into the scratch tile (columns 256..), once the workers have read a_{s-1} out of it
+          mbar_wait(a_empty, (s & 1) ^ 1);
+          tc_fence_after();
+          mix(2 + 2 * s, 256, 0u);
+          umma_commit(a_full);
+        }
         for (int hop = 0; hop < 2; ++hop, ++ph) {
           mbar_wait(b_ready, ph & 1);
           tc_fence_after();
@@ -744,6 +780,8 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) gw_fused_fwd_kernel(GwFusedArg
             }
             umma_commit(&empty[st]);
           }
+          if (TCM && hop == 0) mix(1 + 2 * s, 0, 1u);              // q_s = P_s^T a_s + W_s1 u in the same accumulator
+          if (TCM && hop == 1 && s == 2) mix(0, 128, 1u);          // H += W_0 u
           umma_commit(hop ? hopb_done : acc1_full);
         }
       }
@@ -798,6 +836,7 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) gw_fused_fwd_kernel(GwFusedArg
           }
         }
         float *fo = a.f + ro, *go = a.g + ro, *uo = sU + ((size_t)t * N + node) * GC;
+        float uprev[4];
 #pragma unroll 1
         for (int cg = 0; cg < GC; cg += 4) {
           float fv[4], gv[4];
@@ -823,22 +862,70 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) gw_fused_fwd_kernel(GwFusedArg
           }
           *reinterpret_cast<float4 *>(fo + cg) = make_float4(fv[0], fv[1], fv[2], fv[3]);
           *reinterpret_cast<float4 *>(go + cg) = make_float4(gv[0], gv[1], gv[2], gv[3]);
-          *reinterpret_cast<float4 *>(uo + cg) = make_float4(fv[0] * gv[0], fv[1] * gv[1], fv[2] * gv[2], fv[3] * gv[3]);
+          if (!TCM) {
+            *reinterpret_cast<float4 *>(uo + cg) = make_float4(fv[0] * gv[0], fv[1] * gv[1], fv[2] * gv[2], fv[3] * gv[3]);
+          } else if ((cg & 4) == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) uprev[j] = fv[j] * gv[j];
+          } else {
+            // one 16-byte unit (8 channels) of the u A-operand images: chunk cg / 8, row = node
+            float hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float x = j < 4 ? uprev[j] : fv[j - 4] * gv[j - 4];
+              const float h = __bfloat162float(__float2bfloat16_rn(x));
+              hi[j] = h; lo[j] = x - h;
+            }
+            const uint32_t unit = (uint32_t)(cg >> 3) * rows + (uint32_t)node;
+            reinterpret_cast<uint4 *>(sUimg + (size_t)(t * 2) * uimg_bytes)[unit] = pack8_bf16(hi);
+            reinterpret_cast<uint4 *>(sUimg + (size_t)(t * 2 + 1) * uimg_bytes)[unit] = pack8_bf16(lo);
+          }
         }
       }
     }
     worker_sync();
-    // the 7 transposed [32x32] blocks of the gcn 1x1 conv: sW[k][ci][co] = mlp_w[co][k*32 + ci]
-    for (int i = wt; i < 7 * 1024; i += 256) {
-      const int k = i >> 10, co = (i >> 5) & 31, ci = i & 31;
-      sW[k * 1024 + ci * 32 + co] = a.w.mlp_w[(size_t)co * 224 + k * 32 + ci];
+    if (!TCM) {
+      // the 7 transposed [32x32] blocks of the gcn 1x1 conv: sW[k][ci][co] = mlp_w[co][k*32 + ci]
+      for (int i = wt; i < 7 * 1024; i += 256) {
+        const int k = i >> 10, co = (i >> 5) & 31, ci = i & 31;
+        sW[k * 1024 + ci * 32 + co] = a.w.mlp_w[(size_t)co * 224 + k * 32 + ci];
+      }
+      worker_sync();
+    } else {
+      // the 7 blocks as K-major B images (K = input channel): [k][hi, lo][4 chunks][32 rows = co][8 ci]
+      for (int i = wt; i < 7 * 4 * 32; i += 256) {
+        const int k = i >> 7, c = (i >> 5) & 3, co = i & 31;
+        const float *src = a.w.mlp_w + (size_t)co * 224 + k * 32 + c * 8;
+        float hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float h = __bfloat162float(__float2bfloat16_rn(src[j]));
+          hi[j] = h; lo[j] = src[j] - h;
+        }
+        reinterpret_cast<uint4 *>(sWimg + (size_t)(k * 2) * 2048)[c * 32 + co] = pack8_bf16(hi);
+        reinterpret_cast<uint4 *>(sWimg + (size_t)(k * 2 + 1) * 2048)[c * 32 + co] = pack8_bf16(lo);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(u_ready);
     }
-    worker_sync();
 
     // ---- P2: per support: a_s -> hop A -> q_s -> hop B ----
     for (int s = 0; s < 3; ++s) {
       float arow[GWF_NT][GC];
-      if (valid) {
+      if (TCM) {
+        mbar_wait(a_full, s & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int t = 0; t < GWF_NT; ++t) {
+          if (t >= nt) continue;
+          if (m < g.MT) tmem_ld32(tmem + lane_base + 256 + m * 64 + t * 32, arow[t]);
+          if (valid) store_row(a.a[s] + ((size_t)b * a.Tout + t0 + t) * col + (size_t)node * GC, arow[t]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_empty);
+      } else if (valid) {
 #pragma unroll
         for (int t = 0; t < GWF_NT; ++t) {
           if (t >= nt) continue;
@@ -868,9 +955,11 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) gw_fused_fwd_kernel(GwFusedArg
         float qrow[GC];
         if (m < g.MT) tmem_ld32(tmem + lane_base + m * 64 + t * 32, qrow);
         if (valid) {
-          float u[GC];
-          load_row(sU + ((size_t)t * N + node) * GC, u);
-          matvec_t_reg(sW + (1 + 2 * s) * 1024, u, qrow);
+          if (!TCM) {
+            float u[GC];
+            load_row(sU + ((size_t)t * N + node) * GC, u);
+            matvec_t_reg(sW + (1 + 2 * s) * 1024, u, qrow);
+          }
           store_row(a.q[s] + ((size_t)b * a.Tout + t0 + t) * col + (size_t)node * GC, qrow);
           put_b_row(t, qrow);                                 // hop A has completed (acc1_full): the image is free
         }
@@ -894,12 +983,15 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) gw_fused_fwd_kernel(GwFusedArg
       if (m < g.MT) tmem_ld32(tmem + lane_base + 128 + m * 64 + t * 32, h);
       if (valid) {
         const size_t ro = ((size_t)b * a.Tout + t0 + t) * col + (size_t)node * GC;
-        float u[GC], r[GC];
-        load_row(sU + ((size_t)t * N + node) * GC, u);
+        float r[GC];
         load_row(a.zin + ((size_t)b * a.Tin + t0 + t + a.dil) * col + (size_t)node * GC, r);
 #pragma unroll
         for (int c = 0; c < GC; ++c) h[c] += a.w.mlp_b[c];
-        matvec_t_reg(sW, u, h);
+        if (!TCM) {
+          float u[GC];
+          load_row(sU + ((size_t)t * N + node) * GC, u);
+          matvec_t_reg(sW, u, h);
+        }
         if (a.drop_thr) dropout_row(h, (uint64_t)ro, a.drop_thr, a.drop_scale, a.key);
 #pragma unroll
         for (int c = 0; c < GC; ++c) {
@@ -927,7 +1019,7 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) gw_fused_fwd_kernel(GwFusedArg
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
+  if (warp == 1) tmem_dealloc(tmem, TCM ? 512 : 256);
 }
 
 // ---------------------------------------------------------------------------
@@ -1466,7 +1558,13 @@ static bool gw_use_tc(int N) {
 static bool gw_use_fused(const MixGeom &g) {
   const char *e = getenv("STEP_B200_GW_FUSED");
   if (e != nullptr && strcmp(e, "0") == 0) return false;
-  return g.MT <= 2 && gwf_smem_bytes(g) <= 227 * 1024;
+  return g.MT <= 2 && gwf_smem_bytes(g, false) <= 227 * 1024;
+}
+// STEP_B200_GW_FUSED=1 keeps the CUDA-core channel mixes inside the fused kernel (default: on tcgen05 when the plan fits)
+static bool gw_fused_tc_mix(const MixGeom &g) {
+  const char *e = getenv("STEP_B200_GW_FUSED");
+  if (e != nullptr && strcmp(e, "1") == 0) return false;
+  return gwf_smem_bytes(g, true) <= 227 * 1024;
 }
 
 static size_t fwd_smem_bytes(int N) { return ((size_t)N * GC + 7 * 1024) * sizeof(float); }
@@ -1553,8 +1651,13 @@ extern "C" int step_gwnet_stack_fwd(const float *x0, const float *P1, const floa
           fa.q[s] = a.q[s]; fa.a[s] = stash + p.off_a[i][s];
           fa.img[s] = m.img[s]; fa.img_bstride[s] = m.img_bstride[s];
         }
-        if ((rc = allow_smem(gw_fused_fwd_kernel, 227 * 1024))) return rc;
-        gw_fused_fwd_kernel<<<dim3((a.Tout + GWF_NT - 1) / GWF_NT, B), GWF_THREADS, gwf_smem_bytes(geom), st>>>(fa);
+        if (gw_fused_tc_mix(geom)) {
+          if ((rc = allow_smem(gw_fused_fwd_kernel<true>, 227 * 1024))) return rc;
+          gw_fused_fwd_kernel<true><<<dim3((a.Tout + GWF_NT - 1) / GWF_NT, B), GWF_THREADS, gwf_smem_bytes(geom, true), st>>>(fa);
+        } else {
+          if ((rc = allow_smem(gw_fused_fwd_kernel<false>, 227 * 1024))) return rc;
+          gw_fused_fwd_kernel<false><<<dim3((a.Tout + GWF_NT - 1) / GWF_NT, B), GWF_THREADS, gwf_smem_bytes(geom, false), st>>>(fa);
+        }
         STEP_LAUNCH_CHECK("gw_fused_fwd_kernel");
       } else {
       gw_layer_fwd_kernel<1><<<dim3(a.Tout, B), GW_THREADS, fwd_smem_bytes(N), st>>>(a);

@@ -282,9 +282,12 @@ def test_gwnet_forward_backward_matches_oracle(N, B):
 @pytest.mark.parametrize("N,B,drop", [(23, 3, 0.0), (207, 3, 0.0), (170, 2, 0.3), (256, 1, 0.0), (129, 2, 0.3)])
 def test_gwnet_fused_layer_kernel_matches_split_path(N, B, drop):
     """gw_fused_fwd_kernel (one launch per layer: gated conv + both diffusion hops on tcgen05 + channel mixing + BatchNorm
-    sums, all in shared memory / TMEM) against the five-launch split path (STEP_B200_GW_FUSED=0): same MMAs in the same K
-    order and the same CUDA-core channel mixes, so outputs, batch statistics and - through the unchanged backward that
-    consumes the stash - every gradient agree to fp32 rounding; dropout draws are identical."""
+    sums, all in shared memory / TMEM) against the five-launch split path (STEP_B200_GW_FUSED=0).
+    STEP_B200_GW_FUSED=1: channel mixes on CUDA cores as in the split path - same MMAs in the same K order, outputs, batch
+    statistics and (through the unchanged backward that consumes the stash) gradients agree to fp32 rounding.
+    Default: the seven channel mixes run on tcgen05 too (split-bf16, ~2^-17 relative per product): outputs agree to 1e-4
+    (measured 4e-6), gradients to 5e-3 (the epilogue's ReLUs flip for a few pre-activations within that distance of zero).
+    Dropout draws are identical in all three."""
     import os
     from conftest import gw_args
     from step.step_arch.graphwavenet import GraphWaveNet
@@ -292,30 +295,37 @@ def test_gwnet_fused_layer_kernel_matches_split_path(N, B, drop):
     state = {k[len("backend."):]: v for k, v in sd.items()}
     state.update({k[len("backend."):]: v for k, v in O.bn_buffers("PEMS08").items() if k.startswith("backend.")})
     outs = {}
-    for fused in ("1", "0"):
-        os.environ["STEP_B200_GW_FUSED"] = fused
-        model = GraphWaveNet(**gw_args(N))
-        model.load_state_dict(state, strict=True)
-        model = model.to(DEV).train()
-        model.dropout = drop
-        torch.manual_seed(5)
-        adj_g = adj.to(DEV).requires_grad_(True)
-        out = model(history.to(DEV), hidden_last.to(DEV), adj_g)
-        out.square().sum().backward()
-        outs[fused] = (out.detach().clone(), adj_g.grad.clone(), model.bn[3].running_var.clone(),
-                       {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
-    os.environ.pop("STEP_B200_GW_FUSED", None)
-    a, b = outs["1"], outs["0"]
-    assert torch.isfinite(a[0]).all()
-    assert rel_err(a[0], b[0]) < 1e-5 and rel_err(a[1], b[1]) < 1e-4 and rel_err(a[2], b[2]) < 1e-5
-    assert a[3].keys() == b[3].keys()
+    try:
+        for fused in ("tc", "1", "0"):
+            if fused == "tc":
+                os.environ.pop("STEP_B200_GW_FUSED", None)
+            else:
+                os.environ["STEP_B200_GW_FUSED"] = fused
+            model = GraphWaveNet(**gw_args(N))
+            model.load_state_dict(state, strict=True)
+            model = model.to(DEV).train()
+            model.dropout = drop
+            torch.manual_seed(5)
+            adj_g = adj.to(DEV).requires_grad_(True)
+            out = model(history.to(DEV), hidden_last.to(DEV), adj_g)
+            out.square().sum().backward()
+            outs[fused] = (out.detach().clone(), adj_g.grad.clone(), model.bn[3].running_var.clone(),
+                           {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    finally:
+        os.environ.pop("STEP_B200_GW_FUSED", None)
+    b = outs["0"]
     gmax = max(float(v.abs().max()) for v in b[3].values())
-    for k in a[3]:
-        # the mlp bias feeds a training-mode BatchNorm: its gradient is mathematically zero, both paths return rounding noise
-        if float(b[3][k].abs().max()) < 1e-6 * gmax:
-            assert float(a[3][k].abs().max()) < 1e-5 * gmax, k
-            continue
-        assert rel_l2(a[3][k], b[3][k]) < 1e-4, k
+    for name, t_out, t_dp, t_bn, t_g in (("1", 1e-5, 1e-4, 1e-5, 1e-4), ("tc", 1e-4, 5e-3, 1e-4, 5e-3)):
+        a = outs[name]
+        assert torch.isfinite(a[0]).all()
+        assert rel_err(a[0], b[0]) < t_out and rel_err(a[1], b[1]) < t_dp and rel_err(a[2], b[2]) < t_bn, name
+        assert a[3].keys() == b[3].keys()
+        for k in a[3]:
+            # the mlp bias feeds a training-mode BatchNorm: its gradient is mathematically zero, every path returns rounding noise
+            if float(b[3][k].abs().max()) < 1e-6 * gmax:
+                assert float(a[3][k].abs().max()) < 1e-4 * gmax, (name, k)
+                continue
+            assert rel_l2(a[3][k], b[3][k]) < t_g, (name, k)
 
 
 def test_gwnet_eval_mode_and_dropout():
