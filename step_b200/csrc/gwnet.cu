@@ -627,15 +627,21 @@ __global__ void __launch_bounds__(GW_THREADS, 2) gw_layer_fwd_kernel(GwFwdArgs a
 // ---------------------------------------------------------------------------
 // ONE launch per Graph WaveNet layer (forward): the whole layer body of graphwavenet/model.py:169-213 for a
 // (sample, pair of time steps) column block - gated dilated conv, the three supports' two diffusion hops and the 1x1
-// mixing (Horner form, see the header), dropout, residual, BatchNorm partial sums - with the neighbour aggregation on
-// tcgen05 INSIDE the kernel: nothing but the layer input, the stash rows the backward needs and the layer output touch HBM.
-//   workers (8 warps, thread = node):  u = tanh(.) * sigmoid(.)  -> shared memory;  a_s = W_s2 u -> stash + bf16 hi/lo B image
-//   MMA lane:                          m_s = P_s^T a_s   (A = P_s^T images streamed by the TMA lane, K slices of 32 nodes)
-//   workers:                           q_s = W_s1 u + m_s (TMEM -> registers) -> stash + B image (overwrites a_s)
-//   MMA lane:                          H  += P_s^T q_s   (second accumulator, accumulated over the three supports)
-//   workers:                           h = H + W_0 u + b -> dropout -> + BN(residual) -> z, BN partial sums
-// Numerically identical operations to the split path (gw_layer_fwd_kernel<1,2,3> + 2 x tc_mix_kernel: same split-bf16 MMAs
-// in the same K order, same CUDA-core channel mixes); N <= 256 (two 128-row tiles).  grid = (ceil(T_out / 2), B), 1 CTA/SM.
+// mixing (Horner form, see the header), dropout, residual, BatchNorm partial sums - with every product on tcgen05 INSIDE
+// the kernel (template TCM = true): nothing but the layer input, the stash rows the backward needs and the layer output
+// touch HBM, and the CUDA cores only do the elementwise work (BN on load, tanh / sigmoid, hi/lo splits, dropout, residual).
+//   workers (8 warps, thread = node):  z_t, z_{t+dil} (BN applied) -> bf16 hi/lo A images (in the idle support-slice ring)
+//   MMA lane:                          [f | g] pre-activations = sum_tap Z_tap W_tap            (K = 64, N = 64)
+//   workers:                           u = tanh(.) * sigmoid(.) -> f, g stash; u as bf16 hi/lo A images
+//   MMA lane:                          a_s = U W_s2^T (scratch tile)                              (K = 32, N = 32 per time step)
+//   workers:                           a_s -> stash + bf16 hi/lo B image
+//   MMA lane:                          q_s = P_s^T a_s + U W_s1^T  (A = P_s^T images streamed by the TMA lane, K slices of 32 nodes)
+//   workers:                           q_s (TMEM -> registers) -> stash + B image (overwrites a_s)
+//   MMA lane:                          H  += P_s^T q_s (accumulated over the three supports), finally H += U W_0^T
+//   workers:                           h = H + b -> dropout -> + BN(residual) -> z, BN partial sums
+// All MMAs are split-bf16 (hi*hi + hi*lo + lo*hi).  TCM = false keeps the conv and the channel mixes on CUDA cores
+// (numerically identical to the split path gw_layer_fwd_kernel<1,2,3> + 2 x tc_mix_kernel; STEP_B200_GW_FUSED=1).
+// N <= 256 (two 128-row tiles).  grid = (ceil(T_out / 2), B), 1 CTA/SM.
 // ---------------------------------------------------------------------------
 constexpr int GWF_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 workers
 constexpr int GWF_NT = 2;             // time steps per CTA
@@ -680,8 +686,8 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) gw_fused_fwd_kernel(GwFusedArg
   float *sRed = sW + 7 * 1024;                                        // [2][8 warps][64]
   uint64_t *bars = reinterpret_cast<uint64_t *>(sRed + 2 * 8 * 64);
   uint64_t *full = bars, *empty = bars + 2, *b_ready = bars + 4, *acc1_full = bars + 5, *hopb_done = bars + 6;
-  uint64_t *u_ready = bars + 7, *a_full = bars + 8, *a_empty = bars + 9;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
+  uint64_t *u_ready = bars + 7, *a_full = bars + 8, *a_empty = bars + 9, *z_ready = bars + 10, *conv_full = bars + 11;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t col = (size_t)N * GC;
   const int nslices = g.Kpad / 32;
@@ -689,7 +695,7 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) gw_fused_fwd_kernel(GwFusedArg
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(b_ready, 8); mbar_init(acc1_full, 1); mbar_init(hopb_done, 1);
-    mbar_init(u_ready, 8); mbar_init(a_full, 1); mbar_init(a_empty, 8);
+    mbar_init(u_ready, 8); mbar_init(a_full, 1); mbar_init(a_empty, 8); mbar_init(z_ready, 8); mbar_init(conv_full, 1);
     fence_barrier_init();
   }
   // B-image rows of the padding nodes [N, Kpad) stay zero for the whole kernel
@@ -705,6 +711,9 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) gw_fused_fwd_kernel(GwFusedArg
     // ------------------------------ TMA lane: P_s^T image slices, 6 passes (3 supports x 2 hops) ------------------------------
     if (lane == 0) {
       uint32_t n = 0;
+      if (TCM) {                                                // the ring holds the conv's input images until then
+        for (int t = 0; t < nt; ++t) mbar_wait(conv_full, t & 1);
+      }
       for (int s = 0; s < 3; ++s) {
         const uint8_t *img_hi = a.img[s] + (size_t)b * a.img_bstride[s], *img_lo = img_hi + g.img_bytes;
         for (int hop = 0; hop < 2; ++hop) {
@@ -747,7 +756,30 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) gw_fused_fwd_kernel(GwFusedArg
             }
           }
       };
-      if (TCM) { mbar_wait(u_ready, 0); tc_fence_after(); }
+      if (TCM) {
+        // gated conv: per time step 4 K-steps (tap 0: channels 0-15, 16-31; tap 1: ...) x 3 split products per row tile
+        const uint32_t idesc_conv = umma_idesc_bf16(128, 64, 0, 0);
+        const uint32_t zimg = smem_u32(sA);
+        for (int t = 0; t < nt; ++t) {
+          mbar_wait(z_ready, t & 1);
+          tc_fence_after();
+          for (int m = 0; m < g.MT; ++m) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t zh = zimg + (uint32_t)((kk >> 1) * 2) * uimg_bytes + (uint32_t)(2 * (kk & 1)) * a_lbo + m * 2048, zl = zh + uimg_bytes;
+              const uint64_t dah = umma_desc(zh, a_lbo, 128), dal = umma_desc(zl, a_lbo, 128);
+              const uint64_t dbh = umma_desc(wimg + kk * 2 * 1024, 1024, 128), dbl = umma_desc(wimg + 8192 + kk * 2 * 1024, 1024, 128);
+              const uint32_t d = tmem + m * 64;
+              umma_bf16(d, dah, dbh, idesc_conv, kk != 0 ? 1u : 0u);
+              umma_bf16(d, dah, dbl, idesc_conv, 1u);
+              umma_bf16(d, dal, dbh, idesc_conv, 1u);
+            }
+          }
+          umma_commit(conv_full);
+        }
+        mbar_wait(u_ready, 0);
+        tc_fence_after();
+      }
       for (int s = 0; s < 3; ++s) {
         if (TCM) {
           // a_s = W_s2 u into the scratch tile (columns 256..), once the workers have read a_{s-1} out of it
@@ -811,79 +843,151 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) gw_fused_fwd_kernel(GwFusedArg
       }
     };
 
-    // ---- P1: gated dilated conv (filter / gate taps staged in sW) ----
-    for (int i = wt; i < 1024; i += 256) {
-      sW[i] = a.w.filter_w[2 * i]; sW[1024 + i] = a.w.filter_w[2 * i + 1];
-      sW[2048 + i] = a.w.gate_w[2 * i]; sW[3072 + i] = a.w.gate_w[2 * i + 1];
-    }
-    worker_sync();
-    if (valid) {
-#pragma unroll
-      for (int t = 0; t < GWF_NT; ++t) {
-        if (t >= nt) continue;
-        const float *z0 = a.zin + ((size_t)b * a.Tin + t0 + t) * col + (size_t)node * GC;
-        const float *z1 = a.zin + ((size_t)b * a.Tin + t0 + t + a.dil) * col + (size_t)node * GC;
-        const size_t ro = ((size_t)b * a.Tout + t0 + t) * col + (size_t)node * GC;
-        float r0[GC], r1[GC];
-        load_row(z0, r0);
-        load_row(z1, r1);
-        if (a.has_in_bn) {
-#pragma unroll
-          for (int c = 0; c < GC; ++c) {
-            const float sc = a.in_scale[c], sh = a.in_shift[c];
-            r0[c] = fmaf(r0[c], sc, sh);
-            r1[c] = fmaf(r1[c], sc, sh);
+    if (!TCM) {
+      // ---- P1: gated dilated conv (filter / gate taps staged in sW) ----
+      for (int i = wt; i < 1024; i += 256) {
+        sW[i] = a.w.filter_w[2 * i]; sW[1024 + i] = a.w.filter_w[2 * i + 1];
+        sW[2048 + i] = a.w.gate_w[2 * i]; sW[3072 + i] = a.w.gate_w[2 * i + 1];
+      }
+      worker_sync();
+      if (valid) {
+  #pragma unroll
+        for (int t = 0; t < GWF_NT; ++t) {
+          if (t >= nt) continue;
+          const float *z0 = a.zin + ((size_t)b * a.Tin + t0 + t) * col + (size_t)node * GC;
+          const float *z1 = a.zin + ((size_t)b * a.Tin + t0 + t + a.dil) * col + (size_t)node * GC;
+          const size_t ro = ((size_t)b * a.Tout + t0 + t) * col + (size_t)node * GC;
+          float r0[GC], r1[GC];
+          load_row(z0, r0);
+          load_row(z1, r1);
+          if (a.has_in_bn) {
+  #pragma unroll
+            for (int c = 0; c < GC; ++c) {
+              const float sc = a.in_scale[c], sh = a.in_shift[c];
+              r0[c] = fmaf(r0[c], sc, sh);
+              r1[c] = fmaf(r1[c], sc, sh);
+            }
+          }
+          float *fo = a.f + ro, *go = a.g + ro, *uo = sU + ((size_t)t * N + node) * GC;
+  #pragma unroll 1
+          for (int cg = 0; cg < GC; cg += 4) {
+            float fv[4], gv[4];
+  #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int co = cg + j;
+              const float4 *wf0 = reinterpret_cast<const float4 *>(sW + co * GC);
+              const float4 *wf1 = reinterpret_cast<const float4 *>(sW + 1024 + co * GC);
+              const float4 *wg0 = reinterpret_cast<const float4 *>(sW + 2048 + co * GC);
+              const float4 *wg1 = reinterpret_cast<const float4 *>(sW + 3072 + co * GC);
+              float f0 = a.w.filter_b[co], f1 = 0.f, f2 = 0.f, f3 = 0.f, g0 = a.w.gate_b[co], g1 = 0.f, g2 = 0.f, g3 = 0.f;
+  #pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 A0 = wf0[c4], A1 = wf1[c4], G0 = wg0[c4], G1 = wg1[c4];
+                ffma2(f0, f1, A0.x, A0.y, r0[4 * c4], r0[4 * c4 + 1]); ffma2(f2, f3, A0.z, A0.w, r0[4 * c4 + 2], r0[4 * c4 + 3]);
+                ffma2(f0, f1, A1.x, A1.y, r1[4 * c4], r1[4 * c4 + 1]); ffma2(f2, f3, A1.z, A1.w, r1[4 * c4 + 2], r1[4 * c4 + 3]);
+                ffma2(g0, g1, G0.x, G0.y, r0[4 * c4], r0[4 * c4 + 1]); ffma2(g2, g3, G0.z, G0.w, r0[4 * c4 + 2], r0[4 * c4 + 3]);
+                ffma2(g0, g1, G1.x, G1.y, r1[4 * c4], r1[4 * c4 + 1]); ffma2(g2, g3, G1.z, G1.w, r1[4 * c4 + 2], r1[4 * c4 + 3]);
+              }
+              const float af = (f0 + f1) + (f2 + f3), ag = (g0 + g1) + (g2 + g3);
+              fv[j] = tanhf(af);
+              gv[j] = 1.0f / (1.0f + expf(-ag));
+            }
+            *reinterpret_cast<float4 *>(fo + cg) = make_float4(fv[0], fv[1], fv[2], fv[3]);
+            *reinterpret_cast<float4 *>(go + cg) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+            *reinterpret_cast<float4 *>(uo + cg) = make_float4(fv[0] * gv[0], fv[1] * gv[1], fv[2] * gv[2], fv[3] * gv[3]);
           }
         }
-        float *fo = a.f + ro, *go = a.g + ro, *uo = sU + ((size_t)t * N + node) * GC;
-        float uprev[4];
-#pragma unroll 1
-        for (int cg = 0; cg < GC; cg += 4) {
-          float fv[4], gv[4];
+      }
+      worker_sync();
+    } else {
+      // ---- P1 on tcgen05: the gated dilated conv as D[128 nodes, 64 = filter | gate] = sum_tap Z_tap[128, 32] W_tap[32, 64] ----
+      // One time step at a time: its two input rows (taps t and t + dil, BatchNorm applied on load) become bf16 hi/lo
+      // A-operand images in the (still idle) support-slice ring, the issuer runs 4 K-steps x 3 split products per row
+      // tile into TMEM columns [64 m, 64 m + 64), the workers turn the accumulators into f, g (stash) and the u images.
+      {
+        // conv weights as B images [hi, lo][8 chunks = (tap, ci / 8)][64 rows = filter co | gate co][8 ci]
+        for (int i = wt; i < 8 * 64; i += 256) {
+          const int chunk = i >> 6, r = i & 63, tap = chunk >> 2, c = chunk & 3;
+          const float *wsrc = (r < 32 ? a.w.filter_w : a.w.gate_w) + ((size_t)(r & 31) * 32 + c * 8) * 2 + tap;
+          float hi[8], lo[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int co = cg + j;
-            const float4 *wf0 = reinterpret_cast<const float4 *>(sW + co * GC);
-            const float4 *wf1 = reinterpret_cast<const float4 *>(sW + 1024 + co * GC);
-            const float4 *wg0 = reinterpret_cast<const float4 *>(sW + 2048 + co * GC);
-            const float4 *wg1 = reinterpret_cast<const float4 *>(sW + 3072 + co * GC);
-            float f0 = a.w.filter_b[co], f1 = 0.f, f2 = 0.f, f3 = 0.f, g0 = a.w.gate_b[co], g1 = 0.f, g2 = 0.f, g3 = 0.f;
-#pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-              const float4 A0 = wf0[c4], A1 = wf1[c4], G0 = wg0[c4], G1 = wg1[c4];
-              ffma2(f0, f1, A0.x, A0.y, r0[4 * c4], r0[4 * c4 + 1]); ffma2(f2, f3, A0.z, A0.w, r0[4 * c4 + 2], r0[4 * c4 + 3]);
-              ffma2(f0, f1, A1.x, A1.y, r1[4 * c4], r1[4 * c4 + 1]); ffma2(f2, f3, A1.z, A1.w, r1[4 * c4 + 2], r1[4 * c4 + 3]);
-              ffma2(g0, g1, G0.x, G0.y, r0[4 * c4], r0[4 * c4 + 1]); ffma2(g2, g3, G0.z, G0.w, r0[4 * c4 + 2], r0[4 * c4 + 3]);
-              ffma2(g0, g1, G1.x, G1.y, r1[4 * c4], r1[4 * c4 + 1]); ffma2(g2, g3, G1.z, G1.w, r1[4 * c4 + 2], r1[4 * c4 + 3]);
-            }
-            const float af = (f0 + f1) + (f2 + f3), ag = (g0 + g1) + (g2 + g3);
-            fv[j] = tanhf(af);
-            gv[j] = 1.0f / (1.0f + expf(-ag));
+          for (int j = 0; j < 8; ++j) {
+            const float w = wsrc[2 * j];
+            const float h = __bfloat162float(__float2bfloat16_rn(w));
+            hi[j] = h; lo[j] = w - h;
           }
-          *reinterpret_cast<float4 *>(fo + cg) = make_float4(fv[0], fv[1], fv[2], fv[3]);
-          *reinterpret_cast<float4 *>(go + cg) = make_float4(gv[0], gv[1], gv[2], gv[3]);
-          if (!TCM) {
-            *reinterpret_cast<float4 *>(uo + cg) = make_float4(fv[0] * gv[0], fv[1] * gv[1], fv[2] * gv[2], fv[3] * gv[3]);
-          } else if ((cg & 4) == 0) {
+          reinterpret_cast<uint4 *>(sWimg)[i] = pack8_bf16(hi);
+          reinterpret_cast<uint4 *>(sWimg + 8192)[i] = pack8_bf16(lo);
+        }
+      }
+      for (int t = 0; t < nt; ++t) {
+        if (valid) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) uprev[j] = fv[j] * gv[j];
-          } else {
-            // one 16-byte unit (8 channels) of the u A-operand images: chunk cg / 8, row = node
-            float hi[8], lo[8];
+          for (int tap = 0; tap < 2; ++tap) {
+            const float *zr = a.zin + ((size_t)b * a.Tin + t0 + t + tap * a.dil) * col + (size_t)node * GC;
+            float r[GC];
+            load_row(zr, r);
+            if (a.has_in_bn) {
+#pragma unroll
+              for (int c = 0; c < GC; ++c) r[c] = fmaf(r[c], a.in_scale[c], a.in_shift[c]);
+            }
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              float hi[8], lo[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float h = __bfloat162float(__float2bfloat16_rn(r[c8 * 8 + j]));
+                hi[j] = h; lo[j] = r[c8 * 8 + j] - h;
+              }
+              const uint32_t unit = (uint32_t)c8 * rows + (uint32_t)node;
+              reinterpret_cast<uint4 *>(sA + (size_t)(tap * 2) * uimg_bytes)[unit] = pack8_bf16(hi);
+              reinterpret_cast<uint4 *>(sA + (size_t)(tap * 2 + 1) * uimg_bytes)[unit] = pack8_bf16(lo);
+            }
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(z_ready);
+        mbar_wait(conv_full, t & 1);
+        tc_fence_after();
+        float acc[64];
+        if (m < g.MT) {
+          float h32[32];
+          tmem_ld32(tmem + lane_base + m * 64, h32);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) acc[c] = h32[c];
+          tmem_ld32(tmem + lane_base + m * 64 + 32, h32);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) acc[32 + c] = h32[c];
+        }
+        tc_fence_before();
+        if (valid) {
+          const size_t ro = ((size_t)b * a.Tout + t0 + t) * col + (size_t)node * GC;
+          float *fo = a.f + ro, *go = a.g + ro;
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            float fv[8], gv[8], hi[8], lo[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float x = j < 4 ? uprev[j] : fv[j - 4] * gv[j - 4];
+              const int co = c8 * 8 + j;
+              fv[j] = tanhf(acc[co] + a.w.filter_b[co]);
+              gv[j] = 1.0f / (1.0f + expf(-(acc[32 + co] + a.w.gate_b[co])));
+              const float x = fv[j] * gv[j];
               const float h = __bfloat162float(__float2bfloat16_rn(x));
               hi[j] = h; lo[j] = x - h;
             }
-            const uint32_t unit = (uint32_t)(cg >> 3) * rows + (uint32_t)node;
+            *reinterpret_cast<float4 *>(fo + c8 * 8) = make_float4(fv[0], fv[1], fv[2], fv[3]);
+            *reinterpret_cast<float4 *>(fo + c8 * 8 + 4) = make_float4(fv[4], fv[5], fv[6], fv[7]);
+            *reinterpret_cast<float4 *>(go + c8 * 8) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+            *reinterpret_cast<float4 *>(go + c8 * 8 + 4) = make_float4(gv[4], gv[5], gv[6], gv[7]);
+            const uint32_t unit = (uint32_t)c8 * rows + (uint32_t)node;
             reinterpret_cast<uint4 *>(sUimg + (size_t)(t * 2) * uimg_bytes)[unit] = pack8_bf16(hi);
             reinterpret_cast<uint4 *>(sUimg + (size_t)(t * 2 + 1) * uimg_bytes)[unit] = pack8_bf16(lo);
           }
         }
       }
+      worker_sync();
     }
-    worker_sync();
     if (!TCM) {
       // the 7 transposed [32x32] blocks of the gcn 1x1 conv: sW[k][ci][co] = mlp_w[co][k*32 + ci]
       for (int i = wt; i < 7 * 1024; i += 256) {

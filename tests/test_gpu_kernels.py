@@ -285,8 +285,9 @@ def test_gwnet_fused_layer_kernel_matches_split_path(N, B, drop):
     sums, all in shared memory / TMEM) against the five-launch split path (STEP_B200_GW_FUSED=0).
     STEP_B200_GW_FUSED=1: channel mixes on CUDA cores as in the split path - same MMAs in the same K order, outputs, batch
     statistics and (through the unchanged backward that consumes the stash) gradients agree to fp32 rounding.
-    Default: the seven channel mixes run on tcgen05 too (split-bf16, ~2^-17 relative per product): outputs agree to 1e-4
-    (measured 4e-6), gradients to 5e-3 (the epilogue's ReLUs flip for a few pre-activations within that distance of zero).
+    Default: the gated conv and the seven channel mixes run on tcgen05 too (split-bf16, ~2^-17 relative per product): outputs
+    agree to 1e-4 (measured 8e-6); gradients to 2e-2 of the tensor's max (measured <= 8e-3: the output perturbation flips the
+    epilogue's ReLUs and, with dropout, reweights a few paths - the model-level golden tests hold the reference parity).
     Dropout draws are identical in all three."""
     import os
     from conftest import gw_args
@@ -315,7 +316,7 @@ def test_gwnet_fused_layer_kernel_matches_split_path(N, B, drop):
         os.environ.pop("STEP_B200_GW_FUSED", None)
     b = outs["0"]
     gmax = max(float(v.abs().max()) for v in b[3].values())
-    for name, t_out, t_dp, t_bn, t_g in (("1", 1e-5, 1e-4, 1e-5, 1e-4), ("tc", 1e-4, 5e-3, 1e-4, 5e-3)):
+    for name, t_out, t_dp, t_bn, t_g in (("1", 1e-5, 1e-4, 1e-5, 1e-4), ("tc", 1e-4, 2e-2, 1e-4, 2e-2)):
         a = outs[name]
         assert torch.isfinite(a[0]).all()
         assert rel_err(a[0], b[0]) < t_out and rel_err(a[1], b[1]) < t_dp and rel_err(a[2], b[2]) < t_bn, name
