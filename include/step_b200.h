@@ -197,6 +197,11 @@ int step_tc_qkv(const void *x_img, const void *w_img, const float *bias, int S, 
  * two-pass row maximum.  Both are the same softmax up to bf16 rounding of the probabilities. */
 int step_tc_attention(const void *q_img, const void *k_img, const void *v_img, void *o_img, const float *bound, int S, int P,
                       float drop_p, unsigned long long seed, void *stream);
+/* Host-only arithmetic: the bf16x2 threshold of the attention-probability dropout (transformer_layers.py:10-11 -> the dropout
+ * inside nn.MultiheadAttention).  A probability is kept iff the 16-bit half of its random word, read as a bf16 number, is
+ * >= the threshold half (NaN patterns compare false): exactly floor(65536 p) of the 65536 patterns are dropped for
+ * p >= 254/65536 (tests/test_host_logic.py enumerates them). */
+unsigned int step_tc_attn_drop_threshold(float drop_p);
 size_t step_ts_encoder_bf16_workspace_bytes(int B, int N, int P);
 /* Whole encoder in bf16: series -> hidden [B,N,P,96] fp32 (same contract as step_ts_encoder_fwd). */
 int step_ts_encoder_fwd_bf16(const float *series, long long sB, long long sT, long long sN, int B, int N, int P,

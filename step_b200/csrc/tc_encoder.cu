@@ -1731,6 +1731,12 @@ extern "C" int step_tc_attention(const void *q_img, const void *k_img, const voi
   return tc_attn_launch(q_img, k_img, v_img, o_img, bound, S, P, drop_p, seed, 0, (cudaStream_t)stream);
 }
 
+// host-only: the packed bf16x2 threshold pattern the attention kernel compares its random halves with (see drop_thr_bf16x2)
+extern "C" unsigned int step_tc_attn_drop_threshold(float drop_p) {
+  if (!(drop_p > 0.f) || !(drop_p < 1.f)) return 0u;
+  return drop_thr_bf16x2((uint32_t)(drop_p * 65536.0f));
+}
+
 extern "C" size_t step_tc_seq_image_bytes(int B, int N, int P) {
   const size_t R = (size_t)(N + 127) / 128 * 128;
   return (size_t)B * P * 12 * R * 16;

@@ -66,6 +66,7 @@ SIGNATURES = {
     "step_gwnet_dropout_probe": (C.c_int, [f32p, ll, C.c_float, ull, C.c_int, f32p, vp]),
     "step_tc_linear_drop": (C.c_int, [vp, vp, f32p, ll, C.c_int, C.c_int, C.c_int, vp, f32p, f32p, vp, f32p, C.c_float, ull, vp]),
     "step_tc_attn_image_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "step_tc_attn_drop_threshold": (C.c_uint, [C.c_float]),
     "step_tc_qkv": (C.c_int, [vp, vp, f32p, C.c_int, C.c_int, vp, vp, vp, f32p, vp]),
     "step_tc_attention": (C.c_int, [vp, vp, vp, vp, f32p, C.c_int, C.c_int, C.c_float, ull, vp]),
     "step_ts_encoder_bf16_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

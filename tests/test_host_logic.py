@@ -232,3 +232,26 @@ def test_run_py_never_touches_a_real_dataset_directory(tmp_path):
         assert (real / "data_in12_out12.pkl").read_bytes() == b"user data"
     finally:
         os.chdir(cwd)
+
+
+def test_attention_dropout_threshold_drops_exactly_p_of_the_bf16_patterns():
+    """The attention kernel decides two keep flags per 32-bit random word by comparing each 16-bit half, READ AS A bf16 NUMBER,
+    with a threshold (one HSET2.BF16 per two probabilities).  Enumerate all 65536 patterns with the comparison semantics of
+    the hardware (IEEE ordered >=: NaN is false, -0 == +0) and check that exactly floor(65536 p) patterns are dropped - the
+    keep probability is exact although the patterns are compared as floats, not as integers."""
+    import numpy as np
+    from step_b200 import lib
+    h = lib.load()
+    pats = np.arange(65536, dtype=np.uint32)
+    vals = (pats << 16).view(np.float32)                         # bf16 pattern -> its float value
+    for p in (0.1, 0.05, 0.3, 0.25, 0.004, 0.45, 0.5):
+        thr2 = int(h.step_tc_attn_drop_threshold(p))
+        assert (thr2 & 0xFFFF) == (thr2 >> 16)                   # both halves carry the same threshold
+        thr = np.array([(thr2 & 0xFFFF) << 16], dtype=np.uint32).view(np.float32)[0]
+        with np.errstate(invalid="ignore"):
+            kept = int(np.count_nonzero(vals >= thr))
+        want_dropped = int(np.float32(p) * np.float32(65536.0))
+        # +-0 compare equal: at p >= 0.498 the count can be off by the two zero patterns
+        tol = 0 if want_dropped <= 254 + 32640 else 2
+        assert abs((65536 - kept) - max(want_dropped, 254)) <= tol, (p, 65536 - kept, want_dropped)
+    assert h.step_tc_attn_drop_threshold(0.0) == 0
